@@ -1,0 +1,112 @@
+"""CUDA hair BSDF vs the CPU checker on seeded tuples.
+
+Tolerance: north_star asks for 1e-5 relative on eval/pdf.  Because the device
+code re-states the oracle's arithmetic (operation order, no FMA contraction,
+glibc's expf/logf/sinf/cosf/atan2f algorithms) the results are expected to be
+bit-identical; the test asserts the 1e-5 bound and reports the exact-match rate.
+"""
+import numpy as np
+import pytest
+
+from tuples import make_tuples
+from yocto_hair_b200 import hair
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star: "within 1e-5 relative"
+N = 1_000_000
+
+
+def rel_err(a, b):
+    a, b = a.astype(np.float64), b.astype(np.float64)
+    den = np.maximum(np.abs(b), 1e-30)
+    err = np.abs(a - b) / den
+    err[(a == b)] = 0
+    return err
+
+
+@pytest.fixture(scope="module")
+def data(ref):
+    t = make_tuples(ref, N)
+    t["ref_brdf"] = ref.hair_brdf(t["materials"], t["v"], t["normals"], t["tangents"])
+    return t
+
+
+def test_rng_bit_exact(ref, lib):
+    for seed, seq in [(961748941, 7), (1301081, 1), (0, 0), (2**63 + 5, 2**40 + 3)]:
+        assert np.array_equal(hair.rng_floats(seed, seq, 4096).view(np.uint32),
+                              ref.rng_floats(seed, seq, 4096).view(np.uint32))
+
+
+def test_libm_bit_exact(ref, lib):
+    rng = np.random.default_rng(1)
+    n = 2_000_000
+    xs = {
+        0: rng.uniform(-100, 20, n), 1: np.exp(rng.uniform(-40, 40, n)), 2: rng.uniform(-130, 130, n),
+        3: rng.uniform(-130, 130, n), 5: rng.uniform(-1, 1, n), 6: rng.uniform(-1, 1, n),
+        7: rng.uniform(0.1, 5, n),
+    }
+    for fn, a in xs.items():
+        d, r = hair.libm(fn, a), ref.libm(fn, a)
+        mism = np.count_nonzero(d.view(np.uint32) != r.view(np.uint32))
+        assert mism == 0, f"libm fn {fn}: {mism} of {n} differ"
+    a, b = rng.normal(size=n), rng.normal(size=n)
+    assert np.array_equal(hair.libm(4, a, b).view(np.uint32), ref.libm(4, a, b).view(np.uint32))
+
+
+def test_eval_hair_brdf(data, ref):
+    dev = hair.eval_hair_brdf(data["materials"], data["v"], data["normals"], data["tangents"])
+    d, r = hair.brdf_view(dev)[:, :27], hair.brdf_view(data["ref_brdf"])[:, :27]  # skip frame origin (+-0)
+    err = rel_err(d, r)
+    print("eval_hair_brdf: max rel err %.3g, exact %.6f" % (err.max(), np.mean(d == r)))
+    assert err.max() <= REL_TOL
+
+
+def test_eval_and_pdf(data, ref):
+    b = data["ref_brdf"]
+    f_d, f_r = hair.eval_hair_scattering(b, data["wo"], data["wi"]), ref.hair_eval(b, data["wo"], data["wi"])
+    p_d, p_r = hair.sample_hair_scattering_pdf(b, data["wo"], data["wi"]), ref.hair_pdf(b, data["wo"], data["wi"])
+    assert np.all(np.isfinite(f_r) == np.isfinite(f_d))
+    ok = np.isfinite(f_r).all(axis=1) & np.isfinite(p_r)
+    ef, ep = rel_err(f_d[ok], f_r[ok]), rel_err(p_d[ok], p_r[ok])
+    print("eval: max rel %.3g exact %.6f | pdf: max rel %.3g exact %.6f (%d tuples)" % (
+        ef.max(), np.mean(f_d[ok] == f_r[ok]), ep.max(), np.mean(p_d[ok] == p_r[ok]), ok.sum()))
+    assert ef.max() <= REL_TOL and ep.max() <= REL_TOL
+
+
+def test_sample_then_eval(data, ref):
+    b = data["ref_brdf"]
+    w_d, w_r = hair.sample_hair_scattering(b, data["wo"], data["rn"]), ref.hair_sample(b, data["wo"], data["rn"])
+    ok = np.isfinite(w_r).all(axis=1)
+    assert np.array_equal(np.isfinite(w_d).all(axis=1), ok)
+    err = np.abs(w_d[ok].astype(np.float64) - w_r[ok]).max()
+    print("sample: max abs err %.3g exact %.6f" % (err, np.mean(w_d[ok] == w_r[ok])))
+    assert err <= REL_TOL
+    # f and pdf at the sampled direction (the values trace_path consumes)
+    f_d, f_r = hair.eval_hair_scattering(b, data["wo"], w_r), ref.hair_eval(b, data["wo"], w_r)
+    p_d, p_r = hair.sample_hair_scattering_pdf(b, data["wo"], w_r), ref.hair_pdf(b, data["wo"], w_r)
+    ok2 = ok & np.isfinite(f_r).all(axis=1) & np.isfinite(p_r)
+    assert rel_err(f_d[ok2], f_r[ok2]).max() <= REL_TOL
+    assert rel_err(p_d[ok2], p_r[ok2]).max() <= REL_TOL
+
+
+def test_golden_known_answers(lib):
+    """Known-answer vectors of SURVEY.md section 8a (generated from the reference)."""
+    g = np.load(__import__("pathlib").Path(__file__).parent / "golden" / "hair_kat.npz")
+    mats = hair.make_materials(len(g["v"]), sigma_a=g["sigma_a"], beta_m=g["beta_m"], beta_n=g["beta_n"],
+                               alpha=g["alpha"], color=g["color"], eumelanin=g["eumelanin"],
+                               pheomelanin=g["pheomelanin"])
+    b = hair.eval_hair_brdf(mats, g["v"], g["normals"], g["tangents"])
+    assert rel_err(hair.brdf_view(b)[:, :27], g["brdf"][:, :27]).max() <= REL_TOL
+    assert rel_err(hair.eval_hair_scattering(b, g["wo"], g["wi"]), g["f"]).max() <= REL_TOL
+    assert rel_err(hair.sample_hair_scattering_pdf(b, g["wo"], g["wi"]), g["pdf"]).max() <= REL_TOL
+    assert np.abs(hair.sample_hair_scattering(b, g["wo"], g["rn"]) - g["ws"]).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("which", range(4))
+def test_reference_selftests_on_device(which, lib):
+    """white_furnace / white_furnace_sampled / sampling_weights / sampling_consistency,
+    yocto_extension.cpp:555-693, run against the CUDA BSDF."""
+    passed, worst = hair.hair_selftest(which)
+    print(hair.SELFTESTS[which], "worst deviation", worst)
+    assert passed

@@ -1,0 +1,62 @@
+// Error plumbing shared by the C-ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+#include "../../include/yocto_hair_b200.h"
+
+namespace yh {
+
+std::string& last_error_storage();
+yh_status    fail(yh_status code, const char* fmt, ...);
+// true when a CUDA device is usable; otherwise sets YH_ERR_NO_DEVICE
+bool         require_device();
+
+#define YH_CUDA(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t err_ = (call);                                                              \
+    if (err_ != cudaSuccess)                                                                \
+      return yh::fail(YH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(err_), \
+          __FILE__, __LINE__);                                                              \
+  } while (0)
+
+#define YH_REQUIRE_DEVICE()                          \
+  do {                                               \
+    if (!yh::require_device()) return YH_ERR_NO_DEVICE; \
+  } while (0)
+
+// device buffer with RAII (host-side owner)
+template <typename T>
+struct dev_buffer {
+  T*     ptr   = nullptr;
+  size_t count = 0;
+  dev_buffer() = default;
+  dev_buffer(const dev_buffer&)            = delete;
+  dev_buffer& operator=(const dev_buffer&) = delete;
+  ~dev_buffer() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr   = nullptr;
+    count = 0;
+  }
+  cudaError_t alloc(size_t n) {
+    release();
+    count = n;
+    if (n == 0) return cudaSuccess;
+    return cudaMalloc((void**)&ptr, n * sizeof(T));
+  }
+  cudaError_t upload(const T* host, size_t n) {
+    cudaError_t e = alloc(n);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpy(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  size_t bytes() const { return count * sizeof(T); }
+};
+
+// number of SMs of the current device (148 on B200), cached
+int sm_count();
+
+}  // namespace yh
