@@ -217,6 +217,10 @@ typedef struct yh_trace_stats {
   int64_t nodes_visited, prims_tested; /* only in a stats build (else 0)    */
 } yh_trace_stats;
 yh_status yh_state_stats(const yh_state* state, yh_trace_stats* stats);
+/* When enabled, yh_trace_samples brackets the traversal and the shading
+ * kernels of every iteration with CUDA events on the state's stream and fills
+ * traverse_ms / shade_ms (also enabled by YH_PROFILE_KERNELS=1).            */
+yh_status yh_state_set_profiling(yh_state* state, int enabled);
 
 /* Copies results to the host.  Any pointer may be null.
  *  render : 4 floats/pixel = accumulated / samples  (state->render)

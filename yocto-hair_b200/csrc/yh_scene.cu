@@ -1,0 +1,600 @@
+// Scene upload, GPU LBVH build over line / triangle primitives, light tables.
+// Replaces the bodies of init_bvh (yocto_pathtrace.cpp:652-818) and init_lights
+// (:1695-1740) behind the C ABI.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "yh_scene.cuh"
+
+namespace yh {
+
+// ---------------------------------------------------------------- kernels --
+
+// One reference = one (primitive, sub-span) pair with its padded bounds.
+struct ref_bounds {
+  float4 lo;  // min.xyz, -
+  float4 hi;  // max.xyz, -
+};
+
+__device__ __forceinline__ vec3f ldv(const float* p, int i) { return {p[3 * i], p[3 * i + 1], p[3 * i + 2]}; }
+
+// Number of references a primitive gets: long thin segments are bounded by up
+// to max_split boxes along their length (aspect target: span <= 8 diameters).
+__device__ __forceinline__ int split_count(const vec3f& p0, const vec3f& p1, float r0, float r1, int max_split) {
+  if (max_split <= 1) return 1;
+  float len = length(p1 - p0);
+  float dia = fmaxf(r0 + r1, 1e-12f);  // mean diameter
+  int   k   = (int)ceilf(len / (8.0f * dia));
+  return k < 1 ? 1 : (k > max_split ? max_split : k);
+}
+
+__global__ void k_count_refs(int is_lines, const int* elems, const float* pos, const float* radius, int n,
+    int max_split, int* counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int k = 1;
+  if (is_lines) {
+    int a = elems[2 * i], b = elems[2 * i + 1];
+    k     = split_count(ldv(pos, a), ldv(pos, b), radius[a], radius[b], max_split);
+  }
+  counts[i] = k;
+}
+
+// Padding keeps every box conservative with respect to the rounding of the
+// exact primitive test (the hit point of an accepted intersection always lies
+// inside the padded box of the sub-span that contains its segment parameter).
+__device__ __forceinline__ void pad_box(vec3f& lo, vec3f& hi) {
+  float m   = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))),
+      fmaxf(fabsf(lo.z), fabsf(hi.z)));
+  float eps = 4e-7f * m + 1e-30f;
+  lo        = lo - eps;
+  hi        = hi + eps;
+}
+
+__global__ void k_make_refs(int is_lines, const int* elems, const float* pos, const float* radius, int n,
+    const int* offsets, const int* counts, ref_bounds* refs, int* ref_prim, vec3f cmin, vec3f cinv,
+    unsigned long long* keys, int* ref_ids) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int first = offsets[i], k = counts[i];
+  if (is_lines) {
+    int   a = elems[2 * i], b = elems[2 * i + 1];
+    vec3f p0 = ldv(pos, a), p1 = ldv(pos, b);
+    float r0 = radius[a], r1 = radius[b];
+    for (int s = 0; s < k; s++) {
+      float s0 = (float)s / (float)k, s1 = (float)(s + 1) / (float)k;
+      vec3f pa = p0 + (p1 - p0) * s0, pb = p0 + (p1 - p0) * s1;
+      float ra = r0 * (1 - s0) + r1 * s0, rb = r0 * (1 - s1) + r1 * s1;
+      // the interpolated radius can exceed both ends' by rounding only; widen a hair
+      ra         = ra * 1.000001f;
+      rb         = rb * 1.000001f;
+      bbox3f box = k == 1 ? line_bounds(p0, p1, r0, r1) : line_bounds(pa, pb, ra, rb);
+      pad_box(box.min, box.max);
+      refs[first + s]     = {make_float4(box.min.x, box.min.y, box.min.z, 0), make_float4(box.max.x, box.max.y, box.max.z, 0)};
+      ref_prim[first + s] = i;
+    }
+  } else {
+    int    a = elems[3 * i], b = elems[3 * i + 1], c = elems[3 * i + 2];
+    bbox3f box = triangle_bounds(ldv(pos, a), ldv(pos, b), ldv(pos, c));
+    pad_box(box.min, box.max);
+    refs[first]     = {make_float4(box.min.x, box.min.y, box.min.z, 0), make_float4(box.max.x, box.max.y, box.max.z, 0)};
+    ref_prim[first] = i;
+  }
+  // 63-bit Morton key of each reference's box centre
+  for (int s = 0; s < k; s++) {
+    ref_bounds r = refs[first + s];
+    float cx = ((r.lo.x + r.hi.x) * 0.5f - cmin.x) * cinv.x;
+    float cy = ((r.lo.y + r.hi.y) * 0.5f - cmin.y) * cinv.y;
+    float cz = ((r.lo.z + r.hi.z) * 0.5f - cmin.z) * cinv.z;
+    auto  q  = [](float v) -> unsigned long long {
+      v = fminf(fmaxf(v * 2097152.0f, 0.0f), 2097151.0f);
+      unsigned long long x = (unsigned long long)v;  // 21 bits
+      x = (x | x << 32) & 0x1f00000000ffffull;
+      x = (x | x << 16) & 0x1f0000ff0000ffull;
+      x = (x | x << 8) & 0x100f00f00f00f00full;
+      x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+      x = (x | x << 2) & 0x1249249249249249ull;
+      return x;
+    };
+    keys[first + s]    = (q(cx) << 2) | (q(cy) << 1) | q(cz);
+    ref_ids[first + s] = first + s;
+  }
+}
+
+// Karras 2012, "Maximizing parallelism in the construction of BVHs": one thread
+// per internal node of the binary radix tree over the sorted keys.
+__device__ __forceinline__ int lcp(const unsigned long long* keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+// child encoding inside the build: >= 0 internal node, < 0 leaf ~position
+__global__ void k_hierarchy(const unsigned long long* keys, int n, int* left, int* right, int* first,
+    int* last, int* parent_inner, int* parent_leaf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d    = (lcp(keys, n, i, i + 1) - lcp(keys, n, i, i - 1)) < 0 ? -1 : 1;
+  int dmin = lcp(keys, n, i, i - d);
+  int lmax = 2;
+  while (lcp(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (lcp(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j     = i + l * d;
+  int dnode = lcp(keys, n, i, j);
+  int s     = 0;
+  int t     = l;
+  do {
+    t = (t + 1) >> 1;
+    if (lcp(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  first[i] = lo;
+  last[i]  = hi;
+  if (lo == gamma) {
+    left[i]            = ~gamma;
+    parent_leaf[gamma] = i;
+  } else {
+    left[i]             = gamma;
+    parent_inner[gamma] = i;
+  }
+  if (hi == gamma + 1) {
+    right[i]               = ~(gamma + 1);
+    parent_leaf[gamma + 1] = i;
+  } else {
+    right[i]                = gamma + 1;
+    parent_inner[gamma + 1] = i;
+  }
+  if (i == 0) parent_inner[0] = -1;
+}
+
+// Bottom-up bounds: the second thread to reach a node merges its children.
+__global__ void k_refit(int n, const int* sorted_ref, const ref_bounds* refs, const int* left,
+    const int* right, const int* parent_inner, const int* parent_leaf, int* flags, ref_bounds* node_box) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int node = parent_leaf[j];
+  while (node >= 0) {
+    __threadfence();
+    if (atomicAdd(&flags[node], 1) == 0) return;
+    __threadfence();
+    int        l = left[node], r = right[node];
+    ref_bounds a = l < 0 ? refs[sorted_ref[~l]] : ((volatile ref_bounds*)node_box)[l].lo.x == 0 ? node_box[l] : node_box[l];
+    ref_bounds b = r < 0 ? refs[sorted_ref[~r]] : node_box[r];
+    ref_bounds m;
+    m.lo = make_float4(fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z), 0);
+    m.hi = make_float4(fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z), 0);
+    node_box[node] = m;
+    node           = parent_inner[node];
+  }
+}
+
+__global__ void k_keep_flags(int n_inner, const int* first, const int* last, int* keep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inner) return;
+  keep[i] = (last[i] - first[i] + 1) > kLeafMax ? 1 : 0;
+}
+
+__device__ __forceinline__ int leaf_code(int first_ref, int count) { return ~((first_ref << 3) | (count - 1)); }
+
+// Writes the final 64-byte nodes (children's boxes inside the parent).
+__global__ void k_emit_nodes(int n_inner, const int* keep, const int* new_index, const int* left,
+    const int* right, const int* first, const int* last, const int* sorted_ref, const ref_bounds* refs,
+    const ref_bounds* node_box, float4* nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_inner || !keep[i]) return;
+  int        child[2] = {left[i], right[i]};
+  ref_bounds box[2];
+  int        code[2];
+  for (int c = 0; c < 2; c++) {
+    int ch = child[c];
+    if (ch < 0) {
+      box[c]  = refs[sorted_ref[~ch]];
+      code[c] = leaf_code(~ch, 1);
+    } else {
+      box[c] = node_box[ch];
+      code[c] = keep[ch] ? new_index[ch] : leaf_code(first[ch], last[ch] - first[ch] + 1);
+    }
+  }
+  float4* o = nodes + 4 * (size_t)new_index[i];
+  o[0]      = make_float4(box[0].lo.x, box[0].lo.y, box[0].lo.z, box[0].hi.x);
+  o[1]      = make_float4(box[0].hi.y, box[0].hi.z, box[1].lo.x, box[1].lo.y);
+  o[2]      = make_float4(box[1].lo.z, box[1].hi.x, box[1].hi.y, box[1].hi.z);
+  o[3]      = make_float4(__int_as_float(code[0]), __int_as_float(code[1]), 0, 0);
+}
+
+// Leaf-ordered primitive records.
+__global__ void k_emit_prims(int is_lines, int n_refs, const int* sorted_ref, const int* ref_prim,
+    const int* elems, const float* pos, const float* radius, float4* prims, int* ref_elem) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_refs) return;
+  int prim = ref_prim[sorted_ref[j]];
+  if (is_lines) {
+    int   a = elems[2 * prim], b = elems[2 * prim + 1];
+    vec3f p0 = ldv(pos, a), p1 = ldv(pos, b);
+    prims[2 * (size_t)j]     = make_float4(p0.x, p0.y, p0.z, radius[a]);
+    prims[2 * (size_t)j + 1] = make_float4(p1.x, p1.y, p1.z, radius[b]);
+    ref_elem[j]              = prim;
+  } else {
+    int   a = elems[3 * prim], b = elems[3 * prim + 1], c = elems[3 * prim + 2];
+    vec3f p0 = ldv(pos, a), p1 = ldv(pos, b), p2 = ldv(pos, c);
+    prims[3 * (size_t)j]     = make_float4(p0.x, p0.y, p0.z, __int_as_float(prim));
+    prims[3 * (size_t)j + 1] = make_float4(p1.x, p1.y, p1.z, 0);
+    prims[3 * (size_t)j + 2] = make_float4(p2.x, p2.y, p2.z, 0);
+    ref_elem[j]              = prim;
+  }
+}
+
+// ------------------------------------------------------------ host driver --
+
+static yh_status build_shape_bvh(host_shape& sh, int max_split) {
+  bool lines = sh.is_lines();
+  int  n     = sh.num_elems();
+  sh.root = 0, sh.num_refs = 0, sh.num_nodes = 0;
+  sh.root_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+  if (n == 0) return YH_OK;
+  if (!lines) max_split = 1;
+  const int B = 256;
+  auto      G = [&](int c) { return (c + B - 1) / B; };
+
+  // references
+  dev_buffer<int> counts, offsets;
+  YH_CUDA(counts.alloc(n));
+  YH_CUDA(offsets.alloc(n));
+  k_count_refs<<<G(n), B>>>(lines, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, n, max_split, counts.ptr);
+  YH_CUDA(cudaGetLastError());
+  size_t            tmp_bytes = 0;
+  dev_buffer<char>  tmp;
+  YH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.ptr, offsets.ptr, n));
+  YH_CUDA(tmp.alloc(tmp_bytes));
+  YH_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, counts.ptr, offsets.ptr, n));
+  int last_off = 0, last_cnt = 0;
+  YH_CUDA(cudaMemcpy(&last_off, offsets.ptr + (n - 1), 4, cudaMemcpyDeviceToHost));
+  YH_CUDA(cudaMemcpy(&last_cnt, counts.ptr + (n - 1), 4, cudaMemcpyDeviceToHost));
+  int R = last_off + last_cnt;
+  if (R >= (1 << 28)) return fail(YH_ERR_UNSUPPORTED, "shape has %d BVH references (limit 2^28)", R);
+
+  // centre bounds for Morton quantisation (host pass over the vertices)
+  vec3f cmin = {flt_max, flt_max, flt_max}, cmax = {-flt_max, -flt_max, -flt_max};
+  for (size_t v = 0; v + 2 < sh.positions.size(); v += 3) {
+    vec3f p = {sh.positions[v], sh.positions[v + 1], sh.positions[v + 2]};
+    cmin    = min3(cmin, p);
+    cmax    = max3(cmax, p);
+  }
+  vec3f ext  = cmax - cmin;
+  vec3f cinv = {ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f, ext.z > 0 ? 1.0f / ext.z : 0.0f};
+
+  dev_buffer<ref_bounds>         refs;
+  dev_buffer<int>                ref_prim, ids_in, ids_out;
+  dev_buffer<unsigned long long> keys_in, keys_out;
+  YH_CUDA(refs.alloc(R));
+  YH_CUDA(ref_prim.alloc(R));
+  YH_CUDA(ids_in.alloc(R));
+  YH_CUDA(ids_out.alloc(R));
+  YH_CUDA(keys_in.alloc(R));
+  YH_CUDA(keys_out.alloc(R));
+  k_make_refs<<<G(n), B>>>(lines, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, n, offsets.ptr,
+      counts.ptr, refs.ptr, ref_prim.ptr, cmin, cinv, keys_in.ptr, ids_in.ptr);
+  YH_CUDA(cudaGetLastError());
+  tmp_bytes = 0;
+  YH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.ptr, keys_out.ptr, ids_in.ptr, ids_out.ptr, R, 0, 63));
+  YH_CUDA(tmp.alloc(tmp_bytes));
+  YH_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys_in.ptr, keys_out.ptr, ids_in.ptr, ids_out.ptr, R, 0, 63));
+
+  // leaf-ordered primitive records
+  YH_CUDA(sh.d_prims.alloc((size_t)R * (lines ? 2 : 3)));
+  YH_CUDA(sh.d_ref_elem.alloc(R));
+  k_emit_prims<<<G(R), B>>>(lines, R, ids_out.ptr, ref_prim.ptr, sh.d_elems.ptr, sh.d_positions.ptr,
+      sh.d_radius.ptr, sh.d_prims.ptr, sh.d_ref_elem.ptr);
+  YH_CUDA(cudaGetLastError());
+  sh.num_refs = R;
+
+  if (R <= kLeafMax) {  // the whole shape is one leaf
+    sh.root = ~((0 << 3) | (R - 1));
+    std::vector<ref_bounds> h(R);
+    YH_CUDA(cudaMemcpy(h.data(), refs.ptr, sizeof(ref_bounds) * R, cudaMemcpyDeviceToHost));
+    for (auto& r : h) {
+      sh.root_bbox.min = min3(sh.root_bbox.min, vec3f{r.lo.x, r.lo.y, r.lo.z});
+      sh.root_bbox.max = max3(sh.root_bbox.max, vec3f{r.hi.x, r.hi.y, r.hi.z});
+    }
+    return YH_OK;
+  }
+
+  // hierarchy + bounds
+  int             ni = R - 1;
+  dev_buffer<int> left, right, first, last, parent_inner, parent_leaf, flags, keep, new_index;
+  dev_buffer<ref_bounds> node_box;
+  YH_CUDA(left.alloc(ni));
+  YH_CUDA(right.alloc(ni));
+  YH_CUDA(first.alloc(ni));
+  YH_CUDA(last.alloc(ni));
+  YH_CUDA(parent_inner.alloc(ni));
+  YH_CUDA(parent_leaf.alloc(R));
+  YH_CUDA(flags.alloc(ni));
+  YH_CUDA(keep.alloc(ni));
+  YH_CUDA(new_index.alloc(ni));
+  YH_CUDA(node_box.alloc(ni));
+  YH_CUDA(cudaMemset(flags.ptr, 0, flags.bytes()));
+  k_hierarchy<<<G(ni), B>>>(keys_out.ptr, R, left.ptr, right.ptr, first.ptr, last.ptr, parent_inner.ptr, parent_leaf.ptr);
+  YH_CUDA(cudaGetLastError());
+  k_refit<<<G(R), B>>>(R, ids_out.ptr, refs.ptr, left.ptr, right.ptr, parent_inner.ptr, parent_leaf.ptr, flags.ptr, node_box.ptr);
+  YH_CUDA(cudaGetLastError());
+  k_keep_flags<<<G(ni), B>>>(ni, first.ptr, last.ptr, keep.ptr);
+  YH_CUDA(cudaGetLastError());
+  tmp_bytes = 0;
+  YH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep.ptr, new_index.ptr, ni));
+  YH_CUDA(tmp.alloc(tmp_bytes));
+  YH_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, keep.ptr, new_index.ptr, ni));
+  int k_last = 0, i_last = 0;
+  YH_CUDA(cudaMemcpy(&k_last, keep.ptr + (ni - 1), 4, cudaMemcpyDeviceToHost));
+  YH_CUDA(cudaMemcpy(&i_last, new_index.ptr + (ni - 1), 4, cudaMemcpyDeviceToHost));
+  int kept = k_last + i_last;  // node 0 (the root) is kept because R > kLeafMax, and gets index 0
+  YH_CUDA(sh.d_nodes.alloc((size_t)kept * 4));
+  k_emit_nodes<<<G(ni), B>>>(ni, keep.ptr, new_index.ptr, left.ptr, right.ptr, first.ptr, last.ptr,
+      ids_out.ptr, refs.ptr, node_box.ptr, sh.d_nodes.ptr);
+  YH_CUDA(cudaGetLastError());
+  ref_bounds rb;
+  YH_CUDA(cudaMemcpy(&rb, node_box.ptr, sizeof(rb), cudaMemcpyDeviceToHost));
+  sh.root_bbox = {{rb.lo.x, rb.lo.y, rb.lo.z}, {rb.hi.x, rb.hi.y, rb.hi.z}};
+  sh.root      = 0;
+  sh.num_nodes = kept;
+  YH_CUDA(cudaDeviceSynchronize());
+  return YH_OK;
+}
+
+// transform_bbox(frame, bbox), yocto_math.h:3172-3182, plus padding
+static bbox3f transform_bbox_padded(const frame3f& f, const bbox3f& b) {
+  bbox3f out = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+  for (int c = 0; c < 8; c++) {
+    vec3f p = {c & 4 ? b.max.x : b.min.x, c & 2 ? b.max.y : b.min.y, c & 1 ? b.max.z : b.min.z};
+    vec3f q = transform_point(f, p);
+    out.min = min3(out.min, q);
+    out.max = max3(out.max, q);
+  }
+  float m   = std::max({std::fabs(out.min.x), std::fabs(out.min.y), std::fabs(out.min.z), std::fabs(out.max.x),
+      std::fabs(out.max.y), std::fabs(out.max.z)});
+  float eps = 4e-6f * m + 1e-30f;
+  out.min   = out.min - eps;
+  out.max   = out.max + eps;
+  return out;
+}
+
+}  // namespace yh
+
+using namespace yh;
+
+yh::dev_scene yh_scene::view() const {
+  dev_scene v{};
+  v.shapes = d_shapes.ptr, v.materials = d_materials.ptr, v.objects = d_objects.ptr;
+  v.textures = d_textures.ptr, v.environments = d_environments.ptr, v.lights = d_lights.ptr;
+  v.num_shapes = (int)shapes.size(), v.num_materials = (int)materials.size();
+  v.num_objects = (int)objects.size(), v.num_textures = (int)textures.size();
+  v.num_environments = (int)environments.size(), v.num_lights = (int)lights.size();
+  return v;
+}
+yh_scene::~yh_scene() {
+  for (auto s : shapes) delete s;
+  for (auto t : tex_dev) delete t;
+  for (auto c : light_cdfs) delete c;
+}
+
+static frame3f to_frame(const float* f) {
+  return {{f[0], f[1], f[2]}, {f[3], f[4], f[5]}, {f[6], f[7], f[8]}, {f[9], f[10], f[11]}};
+}
+static vec3f to_vec(const float* f) { return {f[0], f[1], f[2]}; }
+
+static yh_status upload_tables(yh_scene* sc) {
+  std::vector<dev_shape> ds;
+  for (auto s : sc->shapes) {
+    dev_shape d{};
+    d.nodes = s->d_nodes.ptr, d.prims = s->d_prims.ptr, d.ref_elem = s->d_ref_elem.ptr;
+    d.root = s->root, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0;
+    d.has_normals = s->normals.empty() ? 0 : 1;
+    d.positions = s->d_positions.ptr, d.normals = s->d_normals.ptr, d.elems = s->d_elems.ptr;
+    d.num_elems = s->num_elems();
+    ds.push_back(d);
+  }
+  YH_CUDA(sc->d_shapes.upload(ds.data(), ds.size()));
+  YH_CUDA(sc->d_materials.upload(sc->materials.data(), sc->materials.size()));
+  YH_CUDA(sc->d_objects.upload(sc->objects.data(), sc->objects.size()));
+  YH_CUDA(sc->d_textures.upload(sc->textures.data(), sc->textures.size()));
+  YH_CUDA(sc->d_environments.upload(sc->environments.data(), sc->environments.size()));
+  YH_CUDA(sc->d_lights.upload(sc->lights.data(), sc->lights.size()));
+  return YH_OK;
+}
+
+extern "C" {
+
+yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
+  YH_REQUIRE_DEVICE();
+  if (!d || !out) return fail(YH_ERR_INVALID, "yh_scene_create: null argument");
+  *out = nullptr;
+  // ---- validate: anything outside the hot-path scope fails loudly ----
+  for (int i = 0; i < d->num_materials; i++) {
+    auto& m = d->materials[i];
+    if (m.specular != 0 || m.metallic != 0 || m.transmission != 0)
+      return fail(YH_ERR_UNSUPPORTED,
+          "material %d: specular/metallic/transmission lobes are outside the hair hot path (SURVEY 8a P13)", i);
+    if (m.scattering[0] != 0 || m.scattering[1] != 0 || m.scattering[2] != 0)
+      return fail(YH_ERR_UNSUPPORTED, "material %d: volumetric scattering is outside the hot path", i);
+    int texs[] = {m.emission_tex, m.color_tex, m.specular_tex, m.metallic_tex, m.roughness_tex,
+        m.transmission_tex, m.spectint_tex, m.scattering_tex, m.opacity_tex, m.normal_tex};
+    for (int t : texs)
+      if (t >= 0) return fail(YH_ERR_UNSUPPORTED, "material %d: material textures are outside the hot path", i);
+  }
+  for (int i = 0; i < d->num_objects; i++) {
+    auto& o = d->objects[i];
+    if (o.shape < 0 || o.shape >= d->num_shapes || o.material < 0 || o.material >= d->num_materials)
+      return fail(YH_ERR_INVALID, "object %d: shape/material index out of range", i);
+  }
+  for (int i = 0; i < d->num_environments; i++)
+    if (d->environments[i].emission_tex >= d->num_textures)
+      return fail(YH_ERR_INVALID, "environment %d: texture index out of range", i);
+  for (int i = 0; i < d->num_shapes; i++) {
+    auto& s = d->shapes[i];
+    if (s.num_lines && s.num_triangles) return fail(YH_ERR_INVALID, "shape %d has both lines and triangles", i);
+    if (s.num_lines && s.num_radius != s.num_positions)
+      return fail(YH_ERR_INVALID, "shape %d: lines need one radius per vertex", i);
+    if (s.num_normals && s.num_normals != s.num_positions)
+      return fail(YH_ERR_INVALID, "shape %d: normals/positions size mismatch", i);
+    for (int k = 0; k < 2 * s.num_lines; k++)
+      if (s.lines[k] < 0 || s.lines[k] >= s.num_positions) return fail(YH_ERR_INVALID, "shape %d: line index out of range", i);
+    for (int k = 0; k < 3 * s.num_triangles; k++)
+      if (s.triangles[k] < 0 || s.triangles[k] >= s.num_positions)
+        return fail(YH_ERR_INVALID, "shape %d: triangle index out of range", i);
+  }
+  auto sc = new yh_scene{};
+  cudaGetDevice(&sc->device);
+  auto bail = [&](yh_status st) {
+    delete sc;
+    return st;
+  };
+  for (int i = 0; i < d->num_shapes; i++) {
+    auto& s  = d->shapes[i];
+    auto  hs = new host_shape{};
+    sc->shapes.push_back(hs);
+    hs->positions.assign(s.positions, s.positions + 3 * (size_t)s.num_positions);
+    if (s.num_normals) hs->normals.assign(s.normals, s.normals + 3 * (size_t)s.num_normals);
+    if (s.num_radius) hs->radius.assign(s.radius, s.radius + s.num_radius);
+    if (s.num_lines) hs->lines.assign(s.lines, s.lines + 2 * (size_t)s.num_lines);
+    if (s.num_triangles) hs->triangles.assign(s.triangles, s.triangles + 3 * (size_t)s.num_triangles);
+    if (hs->d_positions.upload(hs->positions.data(), hs->positions.size()) != cudaSuccess ||
+        hs->d_normals.upload(hs->normals.data(), hs->normals.size()) != cudaSuccess ||
+        hs->d_radius.upload(hs->radius.data(), hs->radius.size()) != cudaSuccess ||
+        hs->d_elems.upload(hs->is_lines() ? hs->lines.data() : hs->triangles.data(),
+            hs->is_lines() ? hs->lines.size() : hs->triangles.size()) != cudaSuccess)
+      return bail(fail(YH_ERR_CUDA, "shape %d: device upload failed: %s", i, cudaGetErrorString(cudaGetLastError())));
+  }
+  for (int i = 0; i < d->num_textures; i++) {
+    auto& t = d->textures[i];
+    if (!t.colorf || t.width <= 0 || t.height <= 0) return bail(fail(YH_ERR_INVALID, "texture %d is empty", i));
+    sc->tex_host.emplace_back(t.colorf, t.colorf + 3 * (size_t)t.width * t.height);
+    auto buf = new dev_buffer<float>{};
+    sc->tex_dev.push_back(buf);
+    if (buf->upload(t.colorf, 3 * (size_t)t.width * t.height) != cudaSuccess)
+      return bail(fail(YH_ERR_CUDA, "texture %d: device upload failed", i));
+    sc->textures.push_back({buf->ptr, t.width, t.height});
+  }
+  for (int i = 0; i < d->num_materials; i++) {
+    auto&        m = d->materials[i];
+    dev_material dm{};
+    dm.emission = to_vec(m.emission), dm.color = to_vec(m.color), dm.opacity = m.opacity, dm.thin = m.thin;
+    dm.eumelanin = m.eumelanin, dm.pheomelanin = m.pheomelanin, dm.sigma_a = to_vec(m.sigma_a);
+    dm.beta_m = m.beta_m, dm.beta_n = m.beta_n, dm.alpha = m.alpha, dm.eta = m.eta;
+    sc->materials.push_back(dm);
+  }
+  for (int i = 0; i < d->num_objects; i++) {
+    dev_object o{};
+    o.frame     = to_frame(d->objects[i].frame);
+    o.inv_frame = inverse_nonrigid(o.frame);  // inverse(frame, non_rigid_frames = true), :1012
+    o.shape = d->objects[i].shape, o.material = d->objects[i].material;
+    sc->objects.push_back(o);
+  }
+  for (int i = 0; i < d->num_environments; i++) {
+    dev_environment e{};
+    e.frame     = to_frame(d->environments[i].frame);
+    e.inv_frame = inverse_rigid(e.frame);  // inverse(environment->frame), :539
+    e.emission  = to_vec(d->environments[i].emission);
+    e.tex       = d->environments[i].emission_tex;
+    sc->environments.push_back(e);
+  }
+  yh_status st = upload_tables(sc);
+  if (st != YH_OK) return bail(st);
+  *out = sc;
+  return YH_OK;
+}
+
+void yh_scene_destroy(yh_scene* scene) { delete scene; }
+
+yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
+  YH_REQUIRE_DEVICE();
+  if (!sc) return fail(YH_ERR_INVALID, "yh_scene_init_bvh: scene is null");
+  int max_split = params && params->max_split > 0 ? params->max_split : 1;
+  if (max_split > 8) max_split = 8;
+  sc->stats = yh_bvh_stats{};
+  for (auto s : sc->shapes) {
+    yh_status st = build_shape_bvh(*s, max_split);
+    if (st != YH_OK) return st;
+    sc->stats.num_primitives += s->num_elems();
+    sc->stats.num_references += s->num_refs;
+    sc->stats.num_nodes += s->num_nodes;
+    sc->stats.node_bytes += (int64_t)s->d_nodes.bytes();
+    sc->stats.prim_bytes += (int64_t)s->d_prims.bytes() + (int64_t)s->d_ref_elem.bytes();
+  }
+  for (auto& o : sc->objects) {
+    auto s = sc->shapes[o.shape];
+    o.bbox = s->num_refs ? transform_bbox_padded(o.frame, s->root_bbox)
+                         : bbox3f{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+  }
+  sc->bvh_built = true;
+  return upload_tables(sc);
+}
+
+yh_status yh_scene_bvh_stats(const yh_scene* sc, yh_bvh_stats* stats) {
+  if (!sc || !stats) return fail(YH_ERR_INVALID, "yh_scene_bvh_stats: null argument");
+  if (!sc->bvh_built) return fail(YH_ERR_STATE, "yh_scene_bvh_stats: call yh_scene_init_bvh first");
+  *stats = sc->stats;
+  return YH_OK;
+}
+
+// init_lights, yocto_pathtrace.cpp:1695-1740: one light per emissive triangle
+// object (cumulative triangle areas) and per emissive environment (cumulative
+// max(rgb) * sin(theta) per texel).  The running float sums are sequential in
+// the reference, so they are formed on the host in the same order.
+yh_status yh_scene_init_lights(yh_scene* sc) {
+  YH_REQUIRE_DEVICE();
+  if (!sc) return fail(YH_ERR_INVALID, "yh_scene_init_lights: scene is null");
+  for (auto c : sc->light_cdfs) delete c;
+  sc->light_cdfs.clear();
+  sc->lights.clear();
+  for (int oi = 0; oi < (int)sc->objects.size(); oi++) {
+    auto& o = sc->objects[oi];
+    auto& m = sc->materials[o.material];
+    if (m.emission == vec3f{0, 0, 0}) continue;
+    auto s = sc->shapes[o.shape];
+    if (s->triangles.empty()) continue;
+    int                nt = (int)s->triangles.size() / 3;
+    std::vector<float> cdf(nt);
+    for (int idx = 0; idx < nt; idx++) {
+      auto  p  = [&](int k) { int v = s->triangles[3 * idx + k]; return vec3f{s->positions[3 * v], s->positions[3 * v + 1], s->positions[3 * v + 2]}; };
+      vec3f p0 = p(0), p1 = p(1), p2 = p(2);
+      cdf[idx] = length(cross(p1 - p0, p2 - p0)) / 2;  // triangle_area, yocto_math.h:3306
+      if (idx) cdf[idx] += cdf[idx - 1];
+    }
+    auto buf = new dev_buffer<float>{};
+    sc->light_cdfs.push_back(buf);
+    YH_CUDA(buf->upload(cdf.data(), cdf.size()));
+    sc->lights.push_back({oi, -1, buf->ptr, nt});
+  }
+  for (int ei = 0; ei < (int)sc->environments.size(); ei++) {
+    auto& e = sc->environments[ei];
+    if (e.emission == vec3f{0, 0, 0}) continue;
+    dev_light l{-1, ei, nullptr, 0};
+    if (e.tex >= 0) {
+      int                w = sc->textures[e.tex].width, h = sc->textures[e.tex].height;
+      auto&              px = sc->tex_host[e.tex];
+      std::vector<float> cdf((size_t)w * h);
+      for (size_t i = 0; i < cdf.size(); i++) {
+        int   iy = (int)(i / w);
+        float th = (iy + 0.5f) * pif / h;
+        float mx = fmax_(fmax_(px[3 * i], px[3 * i + 1]), px[3 * i + 2]);
+        cdf[i]   = mx * std::sin(th);
+        if (i) cdf[i] += cdf[i - 1];
+      }
+      auto buf = new dev_buffer<float>{};
+      sc->light_cdfs.push_back(buf);
+      YH_CUDA(buf->upload(cdf.data(), cdf.size()));
+      l.cdf = buf->ptr, l.cdf_size = (int)cdf.size();
+    }
+    sc->lights.push_back(l);
+  }
+  sc->lights_built = true;
+  return upload_tables(sc);
+}
+
+}  // extern "C"

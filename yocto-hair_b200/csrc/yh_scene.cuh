@@ -1,0 +1,127 @@
+// Device-side scene layout (what lives in HBM) and its host owner.
+//
+//   shape BVH    : binary LBVH, 64-byte nodes that hold BOTH children's boxes
+//                  (4 x float4, one 128-bit load each):
+//                    n0 = c0.min.xyz, c0.max.x     n1 = c0.max.yz, c1.min.xy
+//                    n2 = c1.min.z,  c1.max.xyz    n3 = int child0, child1, -, -
+//                  child >= 0: index of an inner node; child < 0: leaf packed as
+//                  ~((first_ref << 3) | (count - 1)), count <= 8.
+//   references   : leaf-ordered primitive records, so one leaf is one
+//                  contiguous run of 32-byte (line) / 48-byte (triangle) records:
+//                    line     = {p0.xyz, r0}, {p1.xyz, r1}
+//                    triangle = {p0.xyz, element}, {p1.xyz, -}, {p2.xyz, -}
+//                  a long segment may be referenced by several leaves (each
+//                  reference bounds a sub-span of it) — the test always runs on
+//                  the whole segment, so hit records do not depend on splitting.
+//   shading data : the reference's own arrays (positions, normals = hair
+//                  tangents, lines / triangles) for eval_position / eval_normal.
+#pragma once
+#include <vector>
+
+#include "yh_common.cuh"
+#include "yh_intersect.cuh"
+
+namespace yh {
+
+constexpr int kLeafMax = 4;  // the reference's bvh_max_prims (yocto_pathtrace.cpp:598)
+
+struct dev_shape {
+  const float4* nodes;
+  const float4* prims;
+  const int*    ref_elem;   // lines: element id of each reference
+  int           root;       // child encoding of the whole tree (leaf if < 0); 0 refs -> empty
+  int           num_refs;
+  int           is_lines;
+  int           has_normals;
+  const float*  positions;  // xyz
+  const float*  normals;    // xyz (hair tangents for lines)
+  const int*    elems;      // lines: 2 ints, triangles: 3 ints
+  int           num_elems;
+};
+
+struct dev_material {
+  vec3f emission;
+  vec3f color;
+  float opacity;
+  int   thin;
+  // hair block (yocto_pathtrace.h:310-316)
+  float eumelanin, pheomelanin;
+  vec3f sigma_a;
+  float beta_m, beta_n, alpha, eta;
+};
+
+struct dev_object {
+  frame3f frame;
+  frame3f inv_frame;  // inverse(frame, non_rigid = true)
+  bbox3f  bbox;       // world-space bounds of the shape root (padded)
+  int     shape, material;
+};
+
+struct dev_texture {
+  const float* pixels;  // rgb float
+  int          width, height;
+};
+
+struct dev_environment {
+  frame3f frame;
+  frame3f inv_frame;  // inverse(frame) = rigid
+  vec3f   emission;
+  int     tex;
+};
+
+// trace lights, yocto_pathtrace.h:383-387
+struct dev_light {
+  int          object;       // -1 when this is an environment light
+  int          environment;  // -1 when this is an object light
+  const float* cdf;
+  int          cdf_size;
+};
+
+struct dev_scene {
+  const dev_shape*       shapes;
+  const dev_material*    materials;
+  const dev_object*      objects;
+  const dev_texture*     textures;
+  const dev_environment* environments;
+  const dev_light*       lights;
+  int num_shapes, num_materials, num_objects, num_textures, num_environments, num_lights;
+};
+
+// Host-side copy of one shape (kept for light CDFs and BVH set-up).
+struct host_shape {
+  std::vector<float> positions, normals, radius;
+  std::vector<int>   lines, triangles;
+  dev_buffer<float>  d_positions, d_normals, d_radius;
+  dev_buffer<int>    d_elems;
+  dev_buffer<float4> d_nodes, d_prims;
+  dev_buffer<int>    d_ref_elem;
+  int                root = 0, num_refs = 0, num_nodes = 0;
+  bbox3f             root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+  int  num_elems() const { return is_lines() ? (int)lines.size() / 2 : (int)triangles.size() / 3; }
+  bool is_lines() const { return !lines.empty(); }
+};
+
+}  // namespace yh
+
+struct yh_scene {
+  std::vector<yh::host_shape*>      shapes;
+  std::vector<yh::dev_material>     materials;
+  std::vector<yh::dev_object>       objects;
+  std::vector<yh::dev_environment>  environments;
+  std::vector<std::vector<float>>   tex_host;  // rgb float
+  std::vector<yh::dev_texture>      textures;
+  std::vector<yh::dev_buffer<float>*> tex_dev;
+  std::vector<yh::dev_light>        lights;
+  std::vector<yh::dev_buffer<float>*> light_cdfs;
+  yh::dev_buffer<yh::dev_shape>       d_shapes;
+  yh::dev_buffer<yh::dev_material>    d_materials;
+  yh::dev_buffer<yh::dev_object>      d_objects;
+  yh::dev_buffer<yh::dev_texture>     d_textures;
+  yh::dev_buffer<yh::dev_environment> d_environments;
+  yh::dev_buffer<yh::dev_light>       d_lights;
+  bool bvh_built = false, lights_built = false;
+  int  device = 0;
+  yh_bvh_stats stats{};
+  yh::dev_scene view() const;
+  ~yh_scene();
+};

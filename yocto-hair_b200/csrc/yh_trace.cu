@@ -1,0 +1,716 @@
+// Wavefront path integrator: replaces trace_samples -> trace_sample ->
+// trace_path (yocto_pathtrace.cpp:1380-1511, :1676-1689, :1992-2026).
+//
+// One path "slot" per owned pixel.  The reference keeps ONE PCG32 stream per
+// pixel and consumes it sample after sample, so a pixel's samples are strictly
+// sequential; the parallelism is across pixels.  A slot that finishes a sample
+// immediately regenerates the next camera ray for its pixel (until the call's
+// quota is met), so every lane stays busy until the tail of the call.
+//
+// Per iteration:
+//   k_intersect      one thread per active slot: closest hit, then the slot id
+//                    is appended to the miss / surface / hair queue
+//                    (warp ballot + one atomic per warp).
+//   k_shade_miss     environment radiance, finish sample, regenerate.
+//   k_shade_surface  diffuse surfaces (sphere, floor, area lights).
+//   k_shade_hair     hair BSDF: sample / eval / pdf, MIS with the lights.
+// Each shading kernel appends surviving or regenerated slots to the next
+// iteration's active queue.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "yh_shade.cuh"
+
+namespace yh {
+
+struct dev_camera {
+  frame3f frame;
+  float   lens;
+  vec2f   film;
+  float   focus, aperture;
+};
+
+// Path state, structure of arrays indexed by slot.
+struct path_state {
+  float4*             ray_o;     // o.xyz, -
+  float4*             ray_d;     // d.xyz, -
+  float4*             weight;    // weight.xyz, hit alpha
+  float4*             radiance;  // radiance.xyz, bounce (int bits)
+  int4*               hit;       // object, element, u bits, v bits
+  unsigned long long* rng_state;
+  unsigned long long* rng_inc;
+  int*                remaining;  // samples still to start for this slot in this call
+  int*                pixel;      // image pixel index j * width + i
+  float4*             accum;      // image layout, pixel.accumulated
+  int*                samples;    // image layout, pixel.samples
+};
+
+struct queues {
+  int* active[2];  // slot ids
+  int* miss;
+  int* surface;
+  int* hair;
+  // counts: [0] active cur, [1] active next, [2] miss, [3] surface, [4] hair
+  int* count;
+  // statistics: [0] rays, [1] light rays, [2] samples, [3] nodes, [4] prims
+  unsigned long long* stats;
+};
+
+struct trace_consts {
+  int   width, height, bounces;
+  float clamp;
+};
+
+// warp-aggregated queue append
+__device__ __forceinline__ void queue_push(int* queue, int* counter, bool pred, int value) {
+  unsigned mask = __ballot_sync(__activemask(), pred);
+  if (!pred) return;
+  int lane   = threadIdx.x & 31;
+  int leader = __ffs(mask) - 1;
+  int base   = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(mask));
+  base = __shfl_sync(mask, base, leader);
+  queue[base + __popc(mask & ((1u << lane) - 1))] = value;
+}
+
+// sample_camera / eval_camera, yocto_pathtrace.cpp:211-229.  GCC evaluates the
+// two rand2f arguments of the call at :1680 right to left: the LENS sample is
+// drawn first, the pixel sample second (verified against the oracle build).
+__device__ __forceinline__ ray3f camera_ray(const dev_camera& cam, const trace_consts& tc, int pixel, rng_state& rng) {
+  vec2f luv = rand2f(rng);
+  vec2f puv = rand2f(rng);
+  int   i = pixel % tc.width, j = pixel / tc.width;
+  vec2f uv = {div_((float)i + puv.x, (float)tc.width), div_((float)j + puv.y, (float)tc.height)};
+  vec3f q  = {cam.film.x * (0.5f - uv.x), cam.film.y * (uv.y - 0.5f), cam.lens};
+  vec3f dc = -normalize(q);
+  vec3f e  = {0, 0, 0};
+  if (cam.aperture != 0) {  // sample_disk, yocto_math.h:4897-4901
+    float r = sqrt_(luv.y), phi = 2 * pif * luv.x;
+    e = {div_(cosf_(phi) * r * cam.aperture, 2.0f), div_(sinf_(phi) * r * cam.aperture, 2.0f), 0};
+  }
+  vec3f p = dc * cam.focus / fabs_(dc.z);
+  vec3f d = normalize(p - e);
+  return {transform_point(cam.frame, e), transform_direction(cam.frame, d), ray_eps, flt_max};
+}
+
+__device__ __forceinline__ void start_sample(const path_state& ps, const dev_camera& cam, const trace_consts& tc,
+    int slot, rng_state& rng) {
+  ray3f ray       = camera_ray(cam, tc, ps.pixel[slot], rng);
+  ps.ray_o[slot]  = make_float4(ray.o.x, ray.o.y, ray.o.z, 0);
+  ps.ray_d[slot]  = make_float4(ray.d.x, ray.d.y, ray.d.z, 0);
+  ps.weight[slot] = make_float4(1, 1, 1, 0);
+  ps.radiance[slot] = make_float4(0, 0, 0, __int_as_float(0));
+}
+
+// trace_sample tail, :1683-1688, then regenerate or retire the slot.
+__device__ __forceinline__ bool finish_sample(const path_state& ps, const dev_camera& cam, const trace_consts& tc,
+    int slot, vec3f radiance, float alpha, rng_state& rng) {
+  if (!isfinite3(radiance)) radiance = {0, 0, 0};
+  float m = max3(radiance);
+  if (m > tc.clamp) radiance = radiance * div_(tc.clamp, m);
+  int    px = ps.pixel[slot];
+  float4 a  = ps.accum[px];
+  a.x += radiance.x, a.y += radiance.y, a.z += radiance.z, a.w += alpha;
+  ps.accum[px] = a;
+  ps.samples[px] += 1;
+  int left = ps.remaining[slot];
+  if (left > 0) {
+    ps.remaining[slot] = left - 1;
+    start_sample(ps, cam, tc, slot, rng);
+    return true;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) k_start(path_state ps, queues q, dev_camera cam, trace_consts tc,
+    int num_slots, int num_samples) {
+  int  slot = blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = slot < num_slots && num_samples > 0;
+  if (live) {
+    rng_state rng = {ps.rng_state[slot], ps.rng_inc[slot]};
+    if (tc.bounces <= 0) {
+      // the path loop (:1395) never runs: black sample, alpha 0, camera draws still consumed
+      int px = ps.pixel[slot];
+      for (int s = 0; s < num_samples; s++) camera_ray(cam, tc, px, rng);
+      ps.samples[px] += num_samples;
+      live = false;
+    } else {
+      ps.remaining[slot] = num_samples - 1;
+      start_sample(ps, cam, tc, slot, rng);
+    }
+    ps.rng_state[slot] = rng.state;
+  }
+  queue_push(q.active[0], q.count + 0, live, slot);
+}
+
+__global__ void __launch_bounds__(kTraceBlock) k_intersect(dev_scene sc, path_state ps, queues q, int cur) {
+  __shared__ int smem_stack[kStackShared * kTraceBlock];
+  int            n = q.count[cur];
+  unsigned long long nv = 0, pt = 0;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    int  idx  = base + threadIdx.x;
+    bool live = idx < n;
+    int  slot = live ? q.active[cur][idx] : 0;
+    int  kind = -1;
+    if (live) {
+      float4     o = ps.ray_o[slot], d = ps.ray_d[slot];
+      trav_stack st;
+      st.smem = smem_stack + threadIdx.x;
+      st.sp   = 0;
+      hit_record h = intersect_scene(sc, {{o.x, o.y, o.z}, {d.x, d.y, d.z}, ray_eps, flt_max}, st, false, &nv, &pt);
+      ps.hit[slot] = make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y));
+      kind = !h.hit ? 0 : (sc.shapes[sc.objects[h.object].shape].is_lines ? 2 : 1);
+    }
+    queue_push(q.miss, q.count + 2, kind == 0, slot);
+    queue_push(q.surface, q.count + 3, kind == 1, slot);
+    queue_push(q.hair, q.count + 4, kind == 2, slot);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.stats + 0, (unsigned long long)n);
+#ifdef YH_TRAVERSAL_STATS
+  atomicAdd(q.stats + 3, nv);
+  atomicAdd(q.stats + 4, pt);
+#endif
+}
+
+// miss: radiance += weight * eval_environment, break (:1398-1401)
+__global__ void __launch_bounds__(256) k_shade_miss(dev_scene sc, path_state ps, queues q, dev_camera cam,
+    trace_consts tc, int next) {
+  int n = q.count[2];
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    int  idx  = base + threadIdx.x;
+    bool live = idx < n, again = false;
+    int  slot = live ? q.miss[idx] : 0;
+    if (live) {
+      float4    d = ps.ray_d[slot], w = ps.weight[slot], r = ps.radiance[slot];
+      vec3f     radiance = vec3f{r.x, r.y, r.z} + vec3f{w.x, w.y, w.z} * eval_environment(sc, {d.x, d.y, d.z});
+      rng_state rng      = {ps.rng_state[slot], ps.rng_inc[slot]};
+      again              = finish_sample(ps, cam, tc, slot, radiance, w.w, rng);
+      ps.rng_state[slot] = rng.state;
+    }
+    queue_push(q.active[next], q.count + next, again, slot);
+  }
+}
+
+// The body of trace_path for one surface vertex, :1417-1507.  HAIR selects the
+// lobe set at compile time so the two kernels stay divergence-free inside.
+template <bool HAIR>
+__device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_state& ps, const dev_camera& cam,
+    const trace_consts& tc, int slot, trav_stack& st, unsigned int& light_rays) {
+  float4    o4 = ps.ray_o[slot], d4 = ps.ray_d[slot], w4 = ps.weight[slot], r4 = ps.radiance[slot];
+  int4      h4 = ps.hit[slot];
+  rng_state rng = {ps.rng_state[slot], ps.rng_inc[slot]};
+  vec3f     ray_d = {d4.x, d4.y, d4.z}, weight = {w4.x, w4.y, w4.z}, radiance = {r4.x, r4.y, r4.z};
+  int       bounce = __float_as_int(r4.w);
+  int       object = h4.x, element = h4.y;
+  vec2f     uv = {__int_as_float(h4.z), __int_as_float(h4.w)};
+  const dev_object&   ob  = sc.objects[object];
+  const dev_material& mat = sc.materials[ob.material];
+  (void)o4;
+
+  vec3f outgoing = -ray_d;
+  vec3f position = eval_position(sc, object, element, uv);
+  // eval_shading_normal, :350-369
+  vec3f normal, tangent;
+  if (HAIR) {
+    tangent = eval_normal(sc, object, element, uv);
+    normal  = orthonormalize(outgoing, tangent);
+  } else {
+    normal = eval_normal(sc, object, element, uv);
+    if (mat.thin) normal = dot(normal, outgoing) >= 0 ? normal : -normal;
+  }
+  vec3f emission = mat.emission;  // eval_emission with no texture, :397-402
+
+  // opacity, :423-424, :453, :1429-1433 (mean of the {1,1,1} texture default is exactly 1)
+  float opacity = mat.opacity * div_(1.0f + 1.0f + 1.0f, 3.0f);
+  if (opacity > 0.999f) opacity = 1;
+  bool finished = false;
+  if (opacity < 1 && rand1f(rng) >= opacity) {
+    vec3f no = position + ray_d * 1e-2f;
+    ps.ray_o[slot] = make_float4(no.x, no.y, no.z, 0);  // same direction, bounce not counted
+  } else {
+    float alpha = 1.0f;
+    radiance    = radiance + weight * emission;  // :1437
+
+    // eval_brdf, :405-492: with specular = metallic = transmission = 0 the only
+    // surface lobe is diffuse = color and roughness ends at 1 (never delta).
+    vec3f         incoming;
+    vec3f         brdfcos;
+    float         brdf_pdf;
+    hair_brdf     hb;
+    hair_wo_terms ht;
+    if (HAIR) {
+      hair_material hm = {mat.sigma_a, mat.beta_m, mat.beta_n, mat.alpha, mat.eta, mat.color, mat.eumelanin,
+          mat.pheomelanin};
+      hb = eval_hair_brdf(hm, uv.y, normal, tangent);  // :474-490
+      ht = hair_prepare_wo(hb, outgoing);
+    }
+    vec3f diffuse     = mat.color;
+    float dmax        = max3(diffuse);
+    float diffuse_pdf = dmax != 0 ? div_(dmax, dmax) : 0.0f;  // diffuse_pdf / pdf_sum, :456-471
+    // MIS one-sample model, :1441-1451.  Argument evaluation order of the oracle
+    // build (GCC, right to left): rand2f before rand1f, see camera_ray().
+    if (rand1f(rng) < 0.5f) {
+      vec2f rn  = rand2f(rng);
+      float rnl = rand1f(rng);
+      if (HAIR) {
+        incoming = sample_hair_scattering(hb, ht, rn);  // :1133-1135
+      } else {  // sample_brdfcos diffuse lobe, :1141-1144; yocto_math.h:4515-4519
+        incoming = {0, 0, 0};
+        if (diffuse_pdf != 0 && rnl < diffuse_pdf && !(dot(normal, outgoing) <= 0))
+          incoming = sample_hemisphere_cos(normal, rn);
+      }
+    } else {
+      vec2f ruv = rand2f(rng);
+      float rel = rand1f(rng);
+      float rl  = rand1f(rng);
+      incoming  = sample_lights(sc, position, rl, rel, ruv);
+    }
+    if (HAIR) {
+      brdfcos  = eval_hair_scattering(hb, ht, incoming);        // :1071-1073
+      brdf_pdf = sample_hair_scattering_pdf(hb, ht, incoming);  // :1219-1221
+    } else {
+      // eval_diffuse_reflection / sample_diffuse_reflection_pdf, yocto_math.h:4427, :4572
+      brdfcos  = {0, 0, 0};
+      brdf_pdf = 0;
+      float ni = dot(normal, incoming), no = dot(normal, outgoing);
+      if (nonzero(diffuse)) {
+        vec3f lobe = (ni <= 0 || no <= 0) ? vec3f{0, 0, 0} : vec3f{1, 1, 1} / pif * ni;
+        brdfcos    = brdfcos + diffuse * lobe;
+      }
+      if (diffuse_pdf != 0) brdf_pdf += diffuse_pdf * ((ni <= 0 || no <= 0) ? 0.0f : div_(ni, pif));
+    }
+    float light_pdf = sample_lights_pdf(sc, position, incoming, st, light_rays);
+    weight          = weight * (brdfcos / (0.5f * brdf_pdf + 0.5f * light_pdf));
+
+    ps.ray_o[slot] = make_float4(position.x, position.y, position.z, 0);
+    ps.ray_d[slot] = make_float4(incoming.x, incoming.y, incoming.z, 0);
+
+    // :1500-1507, then the loop condition bounce < params.bounces
+    if ((weight == vec3f{0, 0, 0}) || !isfinite3(weight)) finished = true;
+    if (!finished && bounce > 3) {
+      float rr_prob = fmin_(0.99f, max3(weight));
+      if (rand1f(rng) >= rr_prob) finished = true;
+      else weight = weight * div_(1.0f, rr_prob);
+    }
+    bounce += 1;
+    if (bounce >= tc.bounces) finished = true;
+    w4.w = alpha;
+  }
+  bool again;
+  if (finished) {
+    again = finish_sample(ps, cam, tc, slot, radiance, w4.w, rng);
+  } else {
+    ps.weight[slot]   = make_float4(weight.x, weight.y, weight.z, w4.w);
+    ps.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, __int_as_float(bounce));
+    again             = true;
+  }
+  ps.rng_state[slot] = rng.state;
+  return again;
+}
+
+template <bool HAIR>
+__global__ void __launch_bounds__(kTraceBlock) k_shade(dev_scene sc, path_state ps, queues q, dev_camera cam,
+    trace_consts tc, int next) {
+  __shared__ int smem_stack[kStackShared * kTraceBlock];
+  int            n     = q.count[HAIR ? 4 : 3];
+  const int*     queue = HAIR ? q.hair : q.surface;
+  unsigned int   light_rays = 0;
+  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+    int  idx  = base + threadIdx.x;
+    bool live = idx < n, again = false;
+    int  slot = live ? queue[idx] : 0;
+    if (live) {
+      trav_stack st;
+      st.smem = smem_stack + threadIdx.x;
+      st.sp   = 0;
+      again   = shade_vertex<HAIR>(sc, ps, cam, tc, slot, st, light_rays);
+    }
+    queue_push(q.active[next], q.count + next, again, slot);
+  }
+  if (light_rays) atomicAdd(q.stats + 1, (unsigned long long)light_rays);
+}
+
+__global__ void k_reset_counts(int* count, int next) {
+  count[next] = 0;
+  count[2] = count[3] = count[4] = 0;
+}
+
+// init_state, yocto_pathtrace.cpp:1931-1946: pixel k takes the k-th draw of the
+// master stream make_rng(1301081): seq = rand1i(rng, 1 << 31) / 2 + 1.
+__host__ __device__ inline rng_state rng_skip(rng_state rng, unsigned long long delta) {
+  unsigned long long cur_mult = 6364136223846793005ULL, cur_plus = rng.inc, acc_mult = 1u, acc_plus = 0u;
+  while (delta > 0) {
+    if (delta & 1) {
+      acc_mult *= cur_mult;
+      acc_plus = acc_plus * cur_mult + cur_plus;
+    }
+    cur_plus = (cur_mult + 1) * cur_plus;
+    cur_mult *= cur_mult;
+    delta >>= 1;
+  }
+  rng.state = acc_mult * rng.state + acc_plus;
+  return rng;
+}
+__global__ void k_init_slots(path_state ps, const int* slot_pixel, int num_slots, unsigned long long seed) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= num_slots) return;
+  int       px     = slot_pixel[slot];
+  rng_state master = rng_skip(make_rng(1301081), (unsigned long long)px);
+  uint32_t  r      = advance_rng(master) & 0x7fffffffu;  // % (1 << 31)
+  rng_state rng    = make_rng(seed, (uint64_t)(r / 2 + 1));
+  ps.rng_state[slot] = rng.state;
+  ps.rng_inc[slot]   = rng.inc;
+  ps.pixel[slot]     = px;
+  ps.remaining[slot] = 0;
+}
+
+__global__ void k_resolve(const float4* accum, const int* samples, float4* render, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = accum[i];
+  int    s = samples[i];
+  // pixel.accumulated / pixel.samples, :1688 (render stays 0 before the first sample)
+  render[i] = s > 0 ? make_float4(div_(a.x, (float)s), div_(a.y, (float)s), div_(a.z, (float)s), div_(a.w, (float)s))
+                    : make_float4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(kTraceBlock) k_intersect_batch(dev_scene sc, const yh_ray* rays, long long n,
+    int find_any, yh_hit* hits) {
+  __shared__ int smem_stack[kStackShared * kTraceBlock];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    yh_ray     r = rays[i];
+    trav_stack st;
+    st.smem = smem_stack + threadIdx.x;
+    st.sp   = 0;
+    hit_record h = intersect_scene(sc, {{r.o[0], r.o[1], r.o[2]}, {r.d[0], r.d[1], r.d[2]}, r.tmin, r.tmax}, st,
+        find_any != 0);
+    hits[i] = {h.object, h.element, {h.uv.x, h.uv.y}, h.distance, h.hit ? 1 : 0};
+  }
+}
+
+}  // namespace yh
+
+using namespace yh;
+
+struct yh_state {
+  const yh_scene* scene = nullptr;
+  dev_camera      camera{};
+  yh_trace_params params{};
+  int             width = 0, height = 0, num_slots = 0;
+  int             rank = 0, world = 1;
+  dev_buffer<float4>             ray_o, ray_d, weight, radiance, accum, render;
+  dev_buffer<int4>               hit;
+  dev_buffer<unsigned long long> rng_state, rng_inc, stats;
+  dev_buffer<int>                remaining, pixel, samples, q_active0, q_active1, q_miss, q_surface, q_hair, q_count;
+  int*            host_counts = nullptr;  // pinned
+  cudaStream_t    stream      = nullptr;
+  cudaEvent_t     ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> ev_pool;
+  bool            profile = false;
+  yh_trace_stats  last{};
+  path_state      ps() {
+    return {ray_o.ptr, ray_d.ptr, weight.ptr, radiance.ptr, hit.ptr, rng_state.ptr, rng_inc.ptr, remaining.ptr,
+        pixel.ptr, accum.ptr, samples.ptr};
+  }
+  queues qs() { return {{q_active0.ptr, q_active1.ptr}, q_miss.ptr, q_surface.ptr, q_hair.ptr, q_count.ptr, stats.ptr}; }
+  ~yh_state() {
+    if (host_counts) cudaFreeHost(host_counts);
+    for (auto e : ev_pool) cudaEventDestroy(e);
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// Slot order: 32x32 tiles round-robin over ranks; inside a tile 8x4 pixel
+// blocks, so one warp starts with a compact bundle of camera rays.
+static std::vector<int> owned_pixels(int w, int h, int rank, int world) {
+  std::vector<int> px;
+  const int        T   = 32;
+  int              tx  = (w + T - 1) / T, ty = (h + T - 1) / T;
+  for (int t = 0; t < tx * ty; t++) {
+    if (t % world != rank) continue;
+    int x0 = (t % tx) * T, y0 = (t / tx) * T;
+    for (int by = 0; by < T; by += 4)
+      for (int bx = 0; bx < T; bx += 8)
+        for (int y = 0; y < 4; y++)
+          for (int x = 0; x < 8; x++) {
+            int i = x0 + bx + x, j = y0 + by + y;
+            if (i < w && j < h) px.push_back(j * w + i);
+          }
+  }
+  return px;
+}
+
+static yh_status assign_slots(yh_state* st) {
+  std::vector<int> px = owned_pixels(st->width, st->height, st->rank, st->world);
+  st->num_slots       = (int)px.size();
+  size_t n            = px.size() ? px.size() : 1;
+  YH_CUDA(st->ray_o.alloc(n));
+  YH_CUDA(st->ray_d.alloc(n));
+  YH_CUDA(st->weight.alloc(n));
+  YH_CUDA(st->radiance.alloc(n));
+  YH_CUDA(st->hit.alloc(n));
+  YH_CUDA(st->rng_state.alloc(n));
+  YH_CUDA(st->rng_inc.alloc(n));
+  YH_CUDA(st->remaining.alloc(n));
+  YH_CUDA(st->pixel.alloc(n));
+  YH_CUDA(st->q_active0.alloc(n));
+  YH_CUDA(st->q_active1.alloc(n));
+  YH_CUDA(st->q_miss.alloc(n));
+  YH_CUDA(st->q_surface.alloc(n));
+  YH_CUDA(st->q_hair.alloc(n));
+  if (st->num_slots) {
+    dev_buffer<int> d_px;
+    YH_CUDA(d_px.upload(px.data(), px.size()));
+    k_init_slots<<<(st->num_slots + 255) / 256, 256, 0, st->stream>>>(st->ps(), d_px.ptr, st->num_slots, st->params.seed);
+    YH_CUDA(cudaGetLastError());
+    YH_CUDA(cudaStreamSynchronize(st->stream));
+  }
+  return YH_OK;
+}
+
+extern "C" {
+
+yh_status yh_state_create(const yh_scene* scene, const yh_camera_desc* camera, const yh_trace_params* params,
+    yh_state** out) {
+  YH_REQUIRE_DEVICE();
+  if (!scene || !camera || !params || !out) return fail(YH_ERR_INVALID, "yh_state_create: null argument");
+  *out = nullptr;
+  if (params->shader != YH_SHADER_PATH)
+    return fail(YH_ERR_UNSUPPORTED, "shader %d: only the MIS path shader (trace_path) is on the hot path", params->shader);
+  if (!scene->bvh_built || !scene->lights_built)
+    return fail(YH_ERR_STATE, "yh_state_create: call yh_scene_init_bvh and yh_scene_init_lights first");
+  if (scene->lights.empty())
+    return fail(YH_ERR_INVALID, "scene has no lights (the reference's sample_lights is undefined then)");
+  if (params->resolution <= 0 || params->bounces < 0) return fail(YH_ERR_INVALID, "bad trace params");
+  auto st    = new yh_state{};
+  st->scene  = scene;
+  st->params = *params;
+  st->camera = {{{camera->frame[0], camera->frame[1], camera->frame[2]}, {camera->frame[3], camera->frame[4], camera->frame[5]},
+                    {camera->frame[6], camera->frame[7], camera->frame[8]}, {camera->frame[9], camera->frame[10], camera->frame[11]}},
+      camera->lens, {camera->film[0], camera->film[1]}, camera->focus, camera->aperture};
+  // image size, :1933-1939
+  float fx = camera->film[0], fy = camera->film[1];
+  if (fx > fy) {
+    st->width  = params->resolution;
+    st->height = (int)std::round(params->resolution * fy / fx);
+  } else {
+    st->width  = (int)std::round(params->resolution * fx / fy);
+    st->height = params->resolution;
+  }
+  auto bail = [&](yh_status s) {
+    delete st;
+    return s;
+  };
+  if (st->width <= 0 || st->height <= 0) return bail(fail(YH_ERR_INVALID, "empty image"));
+  size_t np = (size_t)st->width * st->height;
+  if (cudaStreamCreate(&st->stream) != cudaSuccess || cudaEventCreate(&st->ev_begin) != cudaSuccess ||
+      cudaEventCreate(&st->ev_end) != cudaSuccess || cudaMallocHost((void**)&st->host_counts, 64) != cudaSuccess)
+    return bail(fail(YH_ERR_CUDA, "stream/event creation failed"));
+  if (st->accum.alloc(np) != cudaSuccess || st->render.alloc(np) != cudaSuccess || st->samples.alloc(np) != cudaSuccess ||
+      st->q_count.alloc(8) != cudaSuccess || st->stats.alloc(8) != cudaSuccess)
+    return bail(fail(YH_ERR_CUDA, "device allocation failed"));
+  cudaMemset(st->accum.ptr, 0, st->accum.bytes());
+  cudaMemset(st->render.ptr, 0, st->render.bytes());
+  cudaMemset(st->samples.ptr, 0, st->samples.bytes());
+  cudaMemset(st->stats.ptr, 0, st->stats.bytes());
+  yh_status s = assign_slots(st);
+  if (s != YH_OK) return bail(s);
+  const char* prof = getenv("YH_PROFILE_KERNELS");
+  st->profile      = prof && prof[0] == '1';
+  *out             = st;
+  return YH_OK;
+}
+
+void yh_state_destroy(yh_state* state) { delete state; }
+
+yh_status yh_state_size(const yh_state* st, int* width, int* height) {
+  if (!st || !width || !height) return fail(YH_ERR_INVALID, "yh_state_size: null argument");
+  *width = st->width, *height = st->height;
+  return YH_OK;
+}
+
+yh_status yh_state_set_shard(yh_state* st, int rank, int world) {
+  YH_REQUIRE_DEVICE();
+  if (!st || world <= 0 || rank < 0 || rank >= world) return fail(YH_ERR_INVALID, "yh_state_set_shard: bad rank/world");
+  st->rank = rank, st->world = world;
+  cudaMemset(st->accum.ptr, 0, st->accum.bytes());
+  cudaMemset(st->samples.ptr, 0, st->samples.bytes());
+  return assign_slots(st);
+}
+
+yh_status yh_state_set_profiling(yh_state* st, int enabled) {
+  if (!st) return fail(YH_ERR_INVALID, "yh_state_set_profiling: state is null");
+  st->profile = enabled != 0;
+  return YH_OK;
+}
+
+yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* stop) {
+  YH_REQUIRE_DEVICE();
+  if (!st || num_samples < 0) return fail(YH_ERR_INVALID, "yh_trace_samples: bad argument");
+  st->last = yh_trace_stats{};
+  if (num_samples == 0 || st->num_slots == 0) return YH_OK;
+  dev_scene    sc = st->scene->view();
+  path_state   ps = st->ps();
+  queues       q  = st->qs();
+  trace_consts tc = {st->width, st->height, st->params.bounces, st->params.clamp};
+  cudaStream_t s  = st->stream;
+  int          sms = sm_count();
+  YH_CUDA(cudaMemsetAsync(q.count, 0, 8 * sizeof(int), s));
+  YH_CUDA(cudaMemsetAsync(q.stats, 0, 8 * sizeof(unsigned long long), s));
+  YH_CUDA(cudaEventRecord(st->ev_begin, s));
+  k_start<<<(st->num_slots + 255) / 256, 256, 0, s>>>(ps, q, st->camera, tc, st->num_slots, num_samples);
+  int64_t launches = 1, iterations = 0;
+  int     grid_t = sms * 8, grid_s = sms * 4;
+  int     cur = 0;
+  size_t  ev_used = 0;
+  auto    ev = [&]() -> cudaEvent_t {
+    if (ev_used == st->ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      st->ev_pool.push_back(e);
+    }
+    cudaEvent_t e = st->ev_pool[ev_used++];
+    cudaEventRecord(e, s);
+    return e;
+  };
+  bool    prof = st->profile;
+  int64_t min_iters = num_samples;  // every sample needs at least one iteration
+  while (true) {
+    int next = cur ^ 1;
+    k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
+    if (prof) ev();
+    k_intersect<<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, cur);
+    if (prof) ev();
+    k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
+    k_shade<false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+    k_shade<true><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+    if (prof) ev();
+    launches += 5;
+    iterations++;
+    cur = next;
+    if (iterations >= min_iters && (iterations % 4 == 0 || iterations < min_iters + 4)) {
+      YH_CUDA(cudaMemcpyAsync(st->host_counts, q.count, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      YH_CUDA(cudaStreamSynchronize(s));
+      if (st->host_counts[cur] == 0) break;
+    }
+    if (stop && *stop) break;
+    if (iterations > (int64_t)num_samples * (st->params.bounces + 2) * 64 + 1024)
+      return fail(YH_ERR_STATE, "yh_trace_samples: wavefront did not drain after %lld iterations", (long long)iterations);
+  }
+  YH_CUDA(cudaEventRecord(st->ev_end, s));
+  YH_CUDA(cudaEventSynchronize(st->ev_end));
+  YH_CUDA(cudaGetLastError());
+  unsigned long long hs[8];
+  YH_CUDA(cudaMemcpy(hs, q.stats, sizeof(hs), cudaMemcpyDeviceToHost));
+  float ms = 0;
+  YH_CUDA(cudaEventElapsedTime(&ms, st->ev_begin, st->ev_end));
+  st->last.samples    = (int64_t)st->num_slots * num_samples;
+  st->last.rays       = (int64_t)hs[0];
+  st->last.light_rays = (int64_t)hs[1];
+  st->last.iterations = iterations;
+  st->last.launches   = launches;
+  st->last.device_ms  = ms;
+  st->last.nodes_visited = (int64_t)hs[3];
+  st->last.prims_tested  = (int64_t)hs[4];
+  if (prof) {
+    float tt = 0, ts = 0;
+    for (size_t i = 0; i + 2 < ev_used; i += 3) {  // three events per iteration
+      float a = 0, b = 0;
+      cudaEventElapsedTime(&a, st->ev_pool[i], st->ev_pool[i + 1]);
+      cudaEventElapsedTime(&b, st->ev_pool[i + 1], st->ev_pool[i + 2]);
+      tt += a, ts += b;
+    }
+    st->last.traverse_ms = tt, st->last.shade_ms = ts;
+  }
+  return YH_OK;
+}
+
+yh_status yh_state_stats(const yh_state* st, yh_trace_stats* stats) {
+  if (!st || !stats) return fail(YH_ERR_INVALID, "yh_state_stats: null argument");
+  *stats = st->last;
+  return YH_OK;
+}
+
+yh_status yh_state_download(const yh_state* cst, float* render, float* accum, int* samples) {
+  YH_REQUIRE_DEVICE();
+  if (!cst) return fail(YH_ERR_INVALID, "yh_state_download: state is null");
+  auto   st = const_cast<yh_state*>(cst);
+  size_t np = (size_t)st->width * st->height;
+  if (render) {
+    k_resolve<<<(int)((np + 255) / 256), 256, 0, st->stream>>>(st->accum.ptr, st->samples.ptr, st->render.ptr, (int)np);
+    YH_CUDA(cudaGetLastError());
+    YH_CUDA(cudaMemcpyAsync(render, st->render.ptr, np * 16, cudaMemcpyDeviceToHost, st->stream));
+  }
+  if (accum) YH_CUDA(cudaMemcpyAsync(accum, st->accum.ptr, np * 16, cudaMemcpyDeviceToHost, st->stream));
+  if (samples) YH_CUDA(cudaMemcpyAsync(samples, st->samples.ptr, np * 4, cudaMemcpyDeviceToHost, st->stream));
+  YH_CUDA(cudaStreamSynchronize(st->stream));
+  return YH_OK;
+}
+
+yh_status yh_state_buffers_dev(yh_state* st, float** accum_dev, int** samples_dev) {
+  if (!st) return fail(YH_ERR_INVALID, "yh_state_buffers_dev: state is null");
+  if (accum_dev) *accum_dev = (float*)st->accum.ptr;
+  if (samples_dev) *samples_dev = st->samples.ptr;
+  return YH_OK;
+}
+
+yh_status yh_state_download_rng(const yh_state* st, uint64_t* rng) {
+  YH_REQUIRE_DEVICE();
+  if (!st || !rng) return fail(YH_ERR_INVALID, "yh_state_download_rng: null argument");
+  // image layout: 2 x uint64 per pixel; pixels this rank does not own stay 0
+  size_t                          np = (size_t)st->width * st->height;
+  std::vector<unsigned long long> s(st->num_slots), inc(st->num_slots);
+  std::vector<int>                px(st->num_slots);
+  YH_CUDA(cudaMemcpy(s.data(), st->rng_state.ptr, 8 * (size_t)st->num_slots, cudaMemcpyDeviceToHost));
+  YH_CUDA(cudaMemcpy(inc.data(), st->rng_inc.ptr, 8 * (size_t)st->num_slots, cudaMemcpyDeviceToHost));
+  YH_CUDA(cudaMemcpy(px.data(), st->pixel.ptr, 4 * (size_t)st->num_slots, cudaMemcpyDeviceToHost));
+  memset(rng, 0, np * 16);
+  for (int i = 0; i < st->num_slots; i++) {
+    rng[2 * (size_t)px[i]]     = s[i];
+    rng[2 * (size_t)px[i] + 1] = inc[i];
+  }
+  return YH_OK;
+}
+
+yh_status yh_intersect_batch_dev(const yh_scene* scene, const yh_ray* rays_dev, int64_t n, int find_any,
+    yh_hit* hits_dev, float* ms) {
+  YH_REQUIRE_DEVICE();
+  if (!scene || n < 0 || (n > 0 && (!rays_dev || !hits_dev))) return fail(YH_ERR_INVALID, "yh_intersect_batch_dev: bad argument");
+  if (!scene->bvh_built) return fail(YH_ERR_STATE, "yh_intersect_batch: call yh_scene_init_bvh first");
+  if (n == 0) return YH_OK;
+  cudaEvent_t e0, e1;
+  YH_CUDA(cudaEventCreate(&e0));
+  YH_CUDA(cudaEventCreate(&e1));
+  int64_t g = (n + kTraceBlock - 1) / kTraceBlock;
+  int64_t cap = (int64_t)sm_count() * 16;
+  YH_CUDA(cudaEventRecord(e0));
+  k_intersect_batch<<<(int)(g < cap ? g : cap), kTraceBlock>>>(scene->view(), rays_dev, n, find_any, hits_dev);
+  YH_CUDA(cudaEventRecord(e1));
+  YH_CUDA(cudaEventSynchronize(e1));
+  YH_CUDA(cudaGetLastError());
+  float t = 0;
+  YH_CUDA(cudaEventElapsedTime(&t, e0, e1));
+  if (ms) *ms = t;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return YH_OK;
+}
+
+yh_status yh_intersect_batch(const yh_scene* scene, const yh_ray* rays, int64_t n, int find_any, yh_hit* hits) {
+  YH_REQUIRE_DEVICE();
+  if (!scene || n < 0 || (n > 0 && (!rays || !hits))) return fail(YH_ERR_INVALID, "yh_intersect_batch: bad argument");
+  if (n == 0) return YH_OK;
+  dev_buffer<yh_ray> dr;
+  dev_buffer<yh_hit> dh;
+  YH_CUDA(dr.upload(rays, n));
+  YH_CUDA(dh.alloc(n));
+  yh_status st = yh_intersect_batch_dev(scene, dr.ptr, n, find_any, dh.ptr, nullptr);
+  if (st != YH_OK) return st;
+  YH_CUDA(cudaMemcpy(hits, dh.ptr, dh.bytes(), cudaMemcpyDeviceToHost));
+  return YH_OK;
+}
+
+}  // extern "C"

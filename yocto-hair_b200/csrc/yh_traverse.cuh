@@ -1,0 +1,169 @@
+// Closest-hit traversal of the two-level scene: objects (linear, bounds
+// culled) -> shape LBVH (yh_scene.cuh layout).  Restates intersect_scene_bvh /
+// intersect_shape_bvh (yocto_pathtrace.cpp:821-1028): the ray is taken to
+// object space with inverse(frame, non_rigid = true), the direction is NOT
+// renormalised (t is preserved), and every primitive test is the reference's
+// own arithmetic, so object / element / uv / distance agree bit for bit.  The
+// box tests are free to differ: boxes are padded, hence conservative.
+#pragma once
+#include "yh_scene.cuh"
+
+namespace yh {
+
+constexpr int kStackShared = 24;  // entries per thread kept in shared memory
+constexpr int kStackLocal  = 72;  // overflow (LBVH chains can be deep)
+constexpr int kTraceBlock  = 128;
+
+struct hit_record {
+  int   object, element;
+  vec2f uv;
+  float distance;
+  bool  hit;
+};
+
+// Per-thread traversal stack: the first kStackShared entries are interleaved
+// in shared memory (entry e of thread t at smem[e * blockDim.x + t], so a warp
+// touches 32 consecutive banks), deeper entries spill to local memory.
+struct trav_stack {
+  int* smem;
+  int  local[kStackLocal];
+  int  sp;
+  __device__ __forceinline__ void push(int v) {
+    if (sp < kStackShared) smem[sp * kTraceBlock] = v;
+    else local[sp - kStackShared] = v;
+    sp++;
+  }
+  __device__ __forceinline__ int pop() {
+    sp--;
+    return sp < kStackShared ? smem[sp * kTraceBlock] : local[sp - kStackShared];
+  }
+};
+
+#ifdef YH_TRAVERSAL_STATS
+#define YH_STAT(x) x
+#else
+#define YH_STAT(x)
+#endif
+
+// Traverses one shape with an object-space ray.  On a hit updates ray.tmax,
+// ref (leaf-order reference index), uv, and returns true.
+__device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref,
+    vec2f& uv, bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
+  if (sh.num_refs == 0) return false;
+  bool  hit  = false;
+  // reciprocal direction and origin pre-multiplied: slab distances become one FMA each
+  float idx = 1.0f / ray.d.x, idy = 1.0f / ray.d.y, idz = 1.0f / ray.d.z;
+  float ox = -ray.o.x * idx, oy = -ray.o.y * idy, oz = -ray.o.z * idz;
+  const float4* __restrict__ nodes = sh.nodes;
+  const float4* __restrict__ prims = sh.prims;
+  int base = st.sp;
+  int cur  = sh.root;
+  while (true) {
+    if (cur >= 0) {
+      const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1),
+                   n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
+      YH_STAT(if (nodes_visited)(*nodes_visited)++;)
+      // child 0: min = n0.xyz, max = n0.w n1.x n1.y ; child 1: min = n1.z n1.w n2.x, max = n2.yzw
+      float a0 = __fmaf_rn(n0.x, idx, ox), b0 = __fmaf_rn(n0.w, idx, ox);
+      float a1 = __fmaf_rn(n0.y, idy, oy), b1 = __fmaf_rn(n1.x, idy, oy);
+      float a2 = __fmaf_rn(n0.z, idz, oz), b2 = __fmaf_rn(n1.y, idz, oz);
+      float tn0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), ray.tmin));
+      float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), ray.tmax));
+      float c0 = __fmaf_rn(n1.z, idx, ox), d0 = __fmaf_rn(n2.y, idx, ox);
+      float c1 = __fmaf_rn(n1.w, idy, oy), d1 = __fmaf_rn(n2.z, idy, oy);
+      float c2 = __fmaf_rn(n2.x, idz, oz), d2 = __fmaf_rn(n2.w, idz, oz);
+      float tn1 = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), ray.tmin));
+      float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), ray.tmax));
+      // generous slack on both ends (padding + this keep the test conservative)
+      bool h0 = tn0 * 0.9999995f <= tf0 * 1.0000005f, h1 = tn1 * 0.9999995f <= tf1 * 1.0000005f;
+      int  ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        bool swap = tn1 < tn0;
+        st.push(swap ? ch0 : ch1);
+        cur = swap ? ch1 : ch0;
+        continue;
+      } else if (h0) {
+        cur = ch0;
+        continue;
+      } else if (h1) {
+        cur = ch1;
+        continue;
+      }
+    } else {
+      int code = ~cur, first = code >> 3, count = (code & 7) + 1;
+      if (sh.is_lines) {
+        for (int k = 0; k < count; k++) {
+          const float4 a = __ldg(prims + 2 * (size_t)(first + k)), b = __ldg(prims + 2 * (size_t)(first + k) + 1);
+          YH_STAT(if (prims_tested)(*prims_tested)++;)
+          if (intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uv, ray.tmax)) {
+            hit = true;
+            ref = first + k;
+          }
+        }
+      } else {
+        for (int k = 0; k < count; k++) {
+          const float4 a = __ldg(prims + 3 * (size_t)(first + k)), b = __ldg(prims + 3 * (size_t)(first + k) + 1),
+                       c = __ldg(prims + 3 * (size_t)(first + k) + 2);
+          YH_STAT(if (prims_tested)(*prims_tested)++;)
+          if (intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uv, ray.tmax)) {
+            hit = true;
+            ref = first + k;
+          }
+        }
+      }
+      if (find_any && hit) {
+        st.sp = base;
+        return true;
+      }
+    }
+    if (st.sp == base) break;
+    cur = st.pop();
+  }
+  return hit;
+}
+
+// conservative ray / box test for the object level
+__device__ __forceinline__ bool hits_box(const ray3f& ray, const bbox3f& b) {
+  float idx = 1.0f / ray.d.x, idy = 1.0f / ray.d.y, idz = 1.0f / ray.d.z;
+  float a0 = (b.min.x - ray.o.x) * idx, b0 = (b.max.x - ray.o.x) * idx;
+  float a1 = (b.min.y - ray.o.y) * idy, b1 = (b.max.y - ray.o.y) * idy;
+  float a2 = (b.min.z - ray.o.z) * idz, b2 = (b.max.z - ray.o.z) * idz;
+  float tn = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), ray.tmin));
+  float tf = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), ray.tmax));
+  return tn * 0.999999f <= tf * 1.000001f;
+}
+
+// intersect_instance_bvh, yocto_pathtrace.cpp:1031-1037
+__device__ __forceinline__ bool intersect_instance(const dev_scene& sc, int object, const ray3f& ray,
+    trav_stack& st, int& element, vec2f& uv, float& distance, bool find_any,
+    unsigned long long* nv = nullptr, unsigned long long* pt = nullptr) {
+  const dev_object& ob = sc.objects[object];
+  const dev_shape&  sh = sc.shapes[ob.shape];
+  ray3f             r  = {transform_point(ob.inv_frame, ray.o), transform_vector(ob.inv_frame, ray.d), ray.tmin, ray.tmax};
+  int               ref = -1;
+  if (!intersect_shape(sh, r, st, ref, uv, find_any, nv, pt)) return false;
+  distance = r.tmax;
+  element  = __ldg(sh.ref_elem + ref);
+  return true;
+}
+
+// intersect_scene_bvh, yocto_pathtrace.cpp:934-1028
+__device__ __forceinline__ hit_record intersect_scene(const dev_scene& sc, ray3f ray, trav_stack& st,
+    bool find_any, unsigned long long* nv = nullptr, unsigned long long* pt = nullptr) {
+  hit_record h;
+  h.object = -1, h.element = -1, h.uv = {0, 0}, h.distance = 0, h.hit = false;
+  for (int o = 0; o < sc.num_objects; o++) {
+    if (!hits_box(ray, sc.objects[o].bbox)) continue;
+    int   element;
+    vec2f uv;
+    float dist;
+    if (intersect_instance(sc, o, ray, st, element, uv, dist, find_any, nv, pt)) {
+      h.hit = true, h.object = o, h.element = element, h.uv = uv, h.distance = dist;
+      ray.tmax = dist;
+      if (find_any) return h;
+    }
+  }
+  return h;
+}
+
+}  // namespace yh

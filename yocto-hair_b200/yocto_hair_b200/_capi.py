@@ -134,6 +134,7 @@ PROTOTYPES = {
     "yh_state_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "yh_trace_samples": (C.c_int, [_P, C.c_int, _P]),
     "yh_state_stats": (C.c_int, [_P, C.POINTER(TraceStats)]),
+    "yh_state_set_profiling": (C.c_int, [_P, C.c_int]),
     "yh_state_download": (C.c_int, [_P, _P, _P, _P]),
     "yh_state_buffers_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "yh_state_download_rng": (C.c_int, [_P, _P]),
