@@ -34,6 +34,10 @@ for name, (sc, cam) in dict(block=synth.hair_block_scene(nseg), straight=synth.s
           f"= {len(rays)/ms/1e3:.1f} Mrays/s")
     bad = np.nonzero(~same_hit)[0][:3]
     for b in bad: print("   mismatch", rays[b], hr[b], hd[b])
+    bi = np.nonzero(both)[0][~ids]
+    for b in bi[:16]:
+        print("   id mismatch ray", b, "ref", hr[b]["object"], hr[b]["element"], repr(hr[b]["distance"]), hr[b]["uv"],
+              "dev", hd[b]["object"], hd[b]["element"], repr(hd[b]["distance"]), hd[b]["uv"])
     p = make_params(resolution=res)
     st_r = rs.state(cam, p); tr = st_r.trace_samples(spp); r_r, a_r, s_r, rng_r = st_r.download()
     st_d = ds.init_state(cam, p); stats = st_d.trace_samples(spp); r_d, a_d, s_d = st_d.download(); rng_d = st_d.rng()
