@@ -1,0 +1,249 @@
+"""CUDA traversal + wavefront integrator vs the CPU checker (SURVEY.md 8a rows
+P5-P19, M1-M7; 8d "Image parity").
+
+Integer / index outputs (hit flag, object, element) must be bit-exact; because
+the primitive tests restate the reference's arithmetic and exact-t ties are
+resolved in the reference's own visiting order, uv / distance and whole renders
+(accumulation buffer, sample counts, per-pixel PCG32 state) are bit-identical
+too, and the tests assert exactly that.  Converged-image rel-MSE (the north_star
+criterion) is asserted on top with its stated tolerance.
+"""
+import numpy as np
+import pytest
+
+from yocto_hair_b200 import _capi as capi
+from yocto_hair_b200 import synth
+from yocto_hair_b200.pathtrace import DeviceScene, make_rays
+from yocto_hair_b200.scene import (Camera, Environment, Material, Object, Scene, Shape, make_params)
+
+pytestmark = pytest.mark.gpu
+
+SCENES = {
+    "block": lambda: synth.hair_block_scene(24_000),
+    "straight": lambda: synth.straight_hair_scene(20_000),
+    "curly": lambda: synth.curly_hair_scene(40_000),
+    "straight_uniform_env": lambda: synth.straight_hair_scene(12_000, sky=False, area_lights=False),
+}
+
+
+def ray_set(scene, cam, n_random=200_000, n_camera=100_000):
+    return np.concatenate([synth.random_rays(scene, n_random), synth.camera_rays(cam, 256, 256, n_camera)])
+
+
+def assert_hits_identical(hr, hd):
+    assert np.array_equal(hr["hit"], hd["hit"])
+    h = hr["hit"] == 1
+    assert np.array_equal(hr["object"][h], hd["object"][h])
+    assert np.array_equal(hr["element"][h], hd["element"][h])
+    assert np.array_equal(hr["distance"][h].view(np.uint32), hd["distance"][h].view(np.uint32))
+    assert np.array_equal(hr["uv"][h].view(np.uint32), hd["uv"][h].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+@pytest.mark.parametrize("max_split", [0, 4])
+def test_hit_records_bit_exact(name, max_split, ref):
+    scene, cam = SCENES[name]()
+    rays = ray_set(scene, cam)
+    rs = ref.scene(scene)
+    hr = rs.intersect(rays.view(np.float32).reshape(-1, 8), threads=8)
+    ds = DeviceScene(scene).init_bvh(max_split).init_lights()
+    hd = ds.intersect(rays)
+    assert 0.05 < hr["hit"].mean() < 0.95  # the set exercises both outcomes
+    assert_hits_identical(hr, hd)
+    # find_any: any hit is a valid answer, the flag must agree
+    ha = ds.intersect(rays[:50_000], find_any=True)
+    assert np.array_equal(ha["hit"], hr["hit"][:50_000])
+    rs.close(); ds.close()
+
+
+@pytest.mark.parametrize("name", sorted(SCENES))
+def test_render_bit_identical(name, ref):
+    scene, cam = SCENES[name]()
+    p = make_params(resolution=160)
+    rs = ref.scene(scene)
+    st_r = rs.state(cam, p)
+    st_r.trace_samples(6)
+    r_r, a_r, s_r, rng_r = st_r.download()
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    st_d = ds.init_state(cam, p)
+    stats = st_d.trace_samples(6)
+    r_d, a_d, s_d = st_d.download()
+    assert (st_d.width, st_d.height) == (st_r.width, st_r.height)
+    assert stats.samples == st_d.width * st_d.height * 6 and stats.rays >= stats.samples
+    assert np.array_equal(s_r, s_d)
+    assert np.array_equal(rng_r, st_d.rng())
+    assert np.array_equal(a_r.view(np.uint32), a_d.view(np.uint32))
+    assert np.array_equal(r_r.view(np.uint32), r_d.view(np.uint32))
+    st_r.close(); rs.close(); st_d.close(); ds.close()
+
+
+def rel_mse(x, y):
+    """mean((x - y)^2 / (y^2 + 1e-2)) on linear RGB."""
+    x, y = x[..., :3].astype(np.float64), y[..., :3].astype(np.float64)
+    return float(np.mean((x - y) ** 2 / (y ** 2 + 1e-2)))
+
+
+def test_converged_image_rel_mse(ref):
+    """GPU render with ANOTHER seed against two reference renders: its error must
+    sit at the Monte Carlo noise floor.  Tolerance: relMSE(GPU,
+    CPU_A) <= 1.5 * relMSE(CPU_B, CPU_A) and mean luminance within 0.5 %."""
+    scene, cam = synth.curly_hair_scene(40_000)
+    spp, res = 96, 128
+    rs = ref.scene(scene)
+    imgs = {}
+    for tag, seed in (("A", 961748941), ("B", 20240229)):
+        st = rs.state(cam, make_params(resolution=res, seed=seed))
+        st.trace_samples(spp)
+        imgs[tag] = st.download()[0]
+        st.close()
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    st = ds.init_state(cam, make_params(resolution=res, seed=777))
+    st.trace_samples(spp)
+    gpu = st.render()
+    floor = rel_mse(imgs["B"], imgs["A"])
+    err = rel_mse(gpu, imgs["A"])
+    lum = lambda im: float((im[..., :3] @ np.array([0.2126, 0.7152, 0.0722])).mean())  # noqa: E731
+    print("relMSE gpu-vs-A %.4g, B-vs-A %.4g, mean lum gpu %.5f A %.5f" % (err, floor, lum(gpu), lum(imgs["A"])))
+    assert err <= 1.5 * floor
+    assert abs(lum(gpu) / lum(imgs["A"]) - 1) <= 5e-3
+    st.close(); ds.close(); rs.close()
+
+
+def test_samples_are_additive_and_shards_tile_the_image():
+    """n calls of 1 spp == 1 call of n spp; the union of world=3 shards rendered
+    one after the other equals the single-device render bit for bit."""
+    scene, cam = synth.curly_hair_scene(16_000)
+    p = make_params(resolution=96)
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    full = ds.init_state(cam, p)
+    full.trace_samples(4)
+    _, a_full, s_full = full.download()
+    step = ds.init_state(cam, p)
+    for _ in range(4):
+        step.trace_samples(1)
+    _, a_step, s_step = step.download()
+    assert np.array_equal(a_full.view(np.uint32), a_step.view(np.uint32)) and np.array_equal(s_full, s_step)
+    acc = np.zeros_like(a_full)
+    cnt = np.zeros_like(s_full)
+    for rank in range(3):
+        st = ds.init_state(cam, p).set_shard(rank, 3)
+        st.trace_samples(4)
+        _, a, s = st.download()
+        assert not np.any((cnt > 0) & (s > 0))  # disjoint ownership
+        acc += a
+        cnt += s
+        st.close()
+    assert np.array_equal(cnt, s_full)
+    assert np.array_equal(acc.view(np.uint32), a_full.view(np.uint32))
+    full.close(); step.close(); ds.close()
+
+
+def tiny_scene(lines, positions, radius, normals=None, env=(1, 1, 1)):
+    sc = Scene()
+    sc.shapes.append(Shape(positions=positions, normals=normals, radius=radius, lines=lines))
+    sc.materials.append(Material(sigma_a=(0.5, 0.8, 1.2)))
+    sc.objects.append(Object(shape=0, material=0))
+    sc.environments.append(Environment(emission=env))
+    return sc
+
+
+def test_edge_cases(ref):
+    """<= 4 primitives (the tree is one leaf), a zero-length segment (det == 0
+    rejects), segments without tangents (eval_normal falls back to the segment
+    direction, :275), axis-parallel and zero-component directions."""
+    pos = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [1, 1, 0], [0, 1, 0.5], [0.5, 0.5, 1]], np.float32)
+    rad = np.full(6, 0.05, np.float32)
+    for lines in ([[0, 1]], [[0, 1], [1, 2], [2, 3]], [[0, 1], [1, 2], [2, 3], [3, 4], [4, 5], [5, 0]]):
+        sc = tiny_scene(np.array(lines, np.int32), pos, rad)
+        rng = np.random.default_rng(3)
+        o = rng.uniform(-0.5, 1.5, (20000, 3)).astype(np.float32)
+        d = rng.normal(size=(20000, 3)).astype(np.float32)
+        d[:2000] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 2000)] * rng.choice([-1, 1], (2000, 1))
+        d[2000:4000, rng.integers(0, 3)] = 0
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays = make_rays(o, d)
+        rs = ref.scene(sc)
+        ds = DeviceScene(sc).init_bvh().init_lights()
+        assert_hits_identical(rs.intersect(rays.view(np.float32).reshape(-1, 8)), ds.intersect(rays))
+        cam = Camera.from_lookat((0.5, 0.5, 3), (0.5, 0.5, 0))
+        p = make_params(resolution=64)
+        st_r, st_d = rs.state(cam, p), ds.init_state(cam, p)
+        st_r.trace_samples(3)
+        st_d.trace_samples(3)
+        assert np.array_equal(st_r.download()[1].view(np.uint32), st_d.download()[1].view(np.uint32))
+        st_r.close(); rs.close(); st_d.close(); ds.close()
+
+
+def test_empty_shape_and_zero_bounces(ref):
+    sc = tiny_scene(np.zeros((0, 2), np.int32), np.zeros((0, 3), np.float32), np.zeros((0,), np.float32))
+    ds = DeviceScene(sc).init_bvh().init_lights()
+    rays = make_rays(np.zeros((100, 3), np.float32), np.tile(np.array([0, 0, 1], np.float32), (100, 1)))
+    assert not ds.intersect(rays)["hit"].any()
+    cam = Camera.from_lookat((0, 0, 3), (0, 0, 0))
+    st = ds.init_state(cam, make_params(resolution=32))
+    st.trace_samples(2)
+    r, a, s = st.download()
+    assert np.all(s == 2) and np.allclose(r[..., :3], 1.0) and np.all(r[..., 3] == 0)  # sky only, alpha 0
+    st.close()
+    # bounces = 0: the path loop never runs -> black, samples still counted, rng advanced like the reference
+    rs = ref.scene(sc)
+    p0 = make_params(resolution=32, bounces=0)
+    st_d, st_r = ds.init_state(cam, p0), rs.state(cam, p0)
+    st_d.trace_samples(3)
+    st_r.trace_samples(3)
+    _, a_r, s_r, rng_r = st_r.download()
+    _, a_d, s_d = st_d.download()
+    assert np.array_equal(a_r, a_d) and np.array_equal(s_r, s_d) and np.array_equal(rng_r, st_d.rng())
+    st_d.close(); st_r.close(); rs.close(); ds.close()
+
+
+def test_errors_are_loud():
+    lib = capi.load()
+    sc, cam = synth.curly_hair_scene(2_000)
+    ds = DeviceScene(sc)
+    with pytest.raises(capi.YhError) as e:  # trace before init_bvh
+        ds.init_state(cam, make_params(resolution=32))
+    assert e.value.status == capi.YH_ERR_STATE
+    ds.init_bvh().init_lights()
+    with pytest.raises(capi.YhError) as e:  # only trace_path is on the hot path
+        ds.init_state(cam, make_params(resolution=32, shader=0))
+    assert e.value.status == capi.YH_ERR_UNSUPPORTED
+    ds.close()
+    sc.materials[0].specular = 0.5  # microfacet lobes are out of scope: refuse, do not approximate
+    with pytest.raises(capi.YhError) as e:
+        DeviceScene(sc)
+    assert e.value.status == capi.YH_ERR_UNSUPPORTED
+    sc.materials[0].specular = 0
+    sc.environments.clear()  # the reference's sample_lights is undefined without lights
+    ds = DeviceScene(sc).init_bvh().init_lights()
+    with pytest.raises(capi.YhError) as e:
+        ds.init_state(cam, make_params(resolution=32))
+    assert e.value.status == capi.YH_ERR_INVALID
+    assert lib.yh_last_error()
+
+
+def test_full_size_properties(ref):
+    """BASELINE configs[2] geometry (1M curly segments): oracle agreement on a
+    ray subset, and shard-union == whole image at the bench resolution's tile grid."""
+    scene, cam = synth.curly_hair_scene(1_000_000)
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    bs = ds.bvh_stats()
+    assert bs.num_primitives == 1_000_000 and bs.num_references >= bs.num_primitives
+    rays = ray_set(scene, cam, 60_000, 60_000)
+    rs = ref.scene(scene)
+    assert_hits_identical(rs.intersect(rays.view(np.float32).reshape(-1, 8), threads=16), ds.intersect(rays))
+    rs.close()
+    p = make_params(resolution=320)
+    full = ds.init_state(cam, p)
+    full.trace_samples(2)
+    _, a_full, s_full = full.download()
+    acc, cnt = np.zeros_like(a_full), np.zeros_like(s_full)
+    for rank in range(8):
+        st = ds.init_state(cam, p).set_shard(rank, 8)
+        st.trace_samples(2)
+        _, a, s = st.download()
+        acc += a
+        cnt += s
+        st.close()
+    assert np.array_equal(cnt, s_full) and np.array_equal(acc.view(np.uint32), a_full.view(np.uint32))
+    full.close(); ds.close()

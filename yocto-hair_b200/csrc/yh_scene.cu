@@ -164,8 +164,13 @@ __global__ void k_refit(int n, const int* sorted_ref, const ref_bounds* refs, co
     if (atomicAdd(&flags[node], 1) == 0) return;
     __threadfence();
     int        l = left[node], r = right[node];
-    ref_bounds a = l < 0 ? refs[sorted_ref[~l]] : ((volatile ref_bounds*)node_box)[l].lo.x == 0 ? node_box[l] : node_box[l];
-    ref_bounds b = r < 0 ? refs[sorted_ref[~r]] : node_box[r];
+    // child boxes were written by other SMs: read them past L1 (.cg), a line of
+    // node_box may sit there from before its neighbour was written
+    auto       ld = [&](int c) -> ref_bounds {
+      if (c < 0) return refs[sorted_ref[~c]];
+      return {__ldcg(&node_box[c].lo), __ldcg(&node_box[c].hi)};
+    };
+    ref_bounds a = ld(l), b = ld(r);
     ref_bounds m;
     m.lo = make_float4(fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z), 0);
     m.hi = make_float4(fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z), 0);
@@ -232,12 +237,86 @@ __global__ void k_emit_prims(int is_lines, int n_refs, const int* sorted_ref, co
 
 // ------------------------------------------------------------ host driver --
 
+// Topology of the tree the reference would build for this shape (build_bvh /
+// split_middle, yocto_pathtrace.cpp:564-650): spatial-middle split of the
+// centroid bounds along their largest axis with std::partition, median index
+// when that fails, leaves of <= 4 primitives.  Only the ORDER it induces is
+// kept (see yh_scene.cuh "tie order"); our own traversal never walks it.
+struct ref_prim {
+  vec3f center;
+  int   primitive;
+};
+static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos, std::vector<int4>& tie_nodes) {
+  bool lines = sh.is_lines();
+  int  n     = sh.num_elems();
+  auto P     = [&](int v) { return vec3f{sh.positions[3 * v], sh.positions[3 * v + 1], sh.positions[3 * v + 2]}; };
+  std::vector<ref_prim> prims(n);
+  for (int i = 0; i < n; i++) {
+    bbox3f b;
+    if (lines) {
+      int a = sh.lines[2 * i], c = sh.lines[2 * i + 1];
+      b     = line_bounds(P(a), P(c), sh.radius[a], sh.radius[c]);
+    } else {
+      b = triangle_bounds(P(sh.triangles[3 * i]), P(sh.triangles[3 * i + 1]), P(sh.triangles[3 * i + 2]));
+    }
+    prims[i] = {(b.min + b.max) / 2.0f, i};  // center(bbox), yocto_math.h:3008
+  }
+  tie_nodes.clear();
+  struct item { int node, start, end; };
+  std::vector<item> todo;
+  if (n > kLeafMax) {
+    tie_nodes.push_back({0, 0, -1, -1});
+    todo.push_back({0, 0, n});
+  }
+  while (!todo.empty()) {
+    item it = todo.back();
+    todo.pop_back();
+    int axis = 0, mid = (it.start + it.end) / 2;
+    vec3f cmin = {flt_max, flt_max, flt_max}, cmax = {-flt_max, -flt_max, -flt_max};
+    for (int i = it.start; i < it.end; i++) cmin = min3(cmin, prims[i].center), cmax = max3(cmax, prims[i].center);
+    vec3f csize = cmax - cmin;
+    if (!(csize == vec3f{0, 0, 0})) {
+      if (csize.x >= csize.y && csize.x >= csize.z) axis = 0;
+      if (csize.y >= csize.x && csize.y >= csize.z) axis = 1;
+      if (csize.z >= csize.x && csize.z >= csize.y) axis = 2;
+      vec3f cc     = (cmin + cmax) / 2.0f;
+      float middle = axis == 0 ? cc.x : (axis == 1 ? cc.y : cc.z);
+      auto  key    = [axis](const ref_prim& p) { return axis == 0 ? p.center.x : (axis == 1 ? p.center.y : p.center.z); };
+      mid = (int)(std::partition(prims.data() + it.start, prims.data() + it.end,
+                      [&](const ref_prim& p) { return key(p) < middle; }) -
+                  prims.data());
+      if (mid == it.start || mid == it.end) mid = (it.start + it.end) / 2;
+    }
+    int child[2];
+    int range[2][2] = {{it.start, mid}, {mid, it.end}};
+    for (int c = 0; c < 2; c++) {
+      if (range[c][1] - range[c][0] > kLeafMax) {
+        child[c] = (int)tie_nodes.size();
+        tie_nodes.push_back({0, 0, -1, -1});
+        todo.push_back({child[c], range[c][0], range[c][1]});
+      } else {
+        child[c] = -1;
+      }
+    }
+    tie_nodes[it.node] = {mid, axis, child[0], child[1]};
+  }
+  ref_pos.assign(n, 0);
+  for (int i = 0; i < n; i++) ref_pos[prims[i].primitive] = i;
+}
+
 static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   bool lines = sh.is_lines();
   int  n     = sh.num_elems();
   sh.root = 0, sh.num_refs = 0, sh.num_nodes = 0;
   sh.root_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   if (n == 0) return YH_OK;
+  {
+    std::vector<int>  ref_pos;
+    std::vector<int4> tie_nodes;
+    reference_tree_order(sh, ref_pos, tie_nodes);
+    YH_CUDA(sh.d_ref_pos.upload(ref_pos.data(), ref_pos.size()));
+    YH_CUDA(sh.d_tie_nodes.upload(tie_nodes.data(), tie_nodes.size()));
+  }
   if (!lines) max_split = 1;
   const int B = 256;
   auto      G = [&](int c) { return (c + B - 1) / B; };
@@ -393,6 +472,7 @@ static yh_status upload_tables(yh_scene* sc) {
   for (auto s : sc->shapes) {
     dev_shape d{};
     d.nodes = s->d_nodes.ptr, d.prims = s->d_prims.ptr, d.ref_elem = s->d_ref_elem.ptr;
+    d.ref_pos = s->d_ref_pos.ptr, d.tie_nodes = s->d_tie_nodes.ptr, d.num_tie_nodes = (int)s->d_tie_nodes.count;
     d.root = s->root, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0;
     d.has_normals = s->normals.empty() ? 0 : 1;
     d.positions = s->d_positions.ptr, d.normals = s->d_normals.ptr, d.elems = s->d_elems.ptr;

@@ -13,6 +13,14 @@
 //                  a long segment may be referenced by several leaves (each
 //                  reference bounds a sub-span of it) — the test always runs on
 //                  the whole segment, so hit records do not depend on splitting.
+//   tie order    : when two primitives of one shape are hit at EXACTLY the same
+//                  t, the reference keeps the one its own BVH visits last
+//                  (intersect_line accepts t == tmax, yocto_math.h:3450).  So
+//                  the topology of the reference's tree (split_middle,
+//                  yocto_pathtrace.cpp:564-595) is kept beside ours: ref_pos[e] =
+//                  position of element e in the reference's leaf order, and
+//                  tie_nodes[k] = {mid, axis, left, right} of its internal
+//                  nodes (child < 0: leaf).  Only ties read them.
 //   shading data : the reference's own arrays (positions, normals = hair
 //                  tangents, lines / triangles) for eval_position / eval_normal.
 #pragma once
@@ -28,7 +36,10 @@ constexpr int kLeafMax = 4;  // the reference's bvh_max_prims (yocto_pathtrace.c
 struct dev_shape {
   const float4* nodes;
   const float4* prims;
-  const int*    ref_elem;   // lines: element id of each reference
+  const int*    ref_elem;   // element id of each reference
+  const int*    ref_pos;    // element id -> position in the reference's leaf order
+  const int4*   tie_nodes;  // internal nodes of the reference's tree: mid, axis, left, right
+  int           num_tie_nodes;
   int           root;       // child encoding of the whole tree (leaf if < 0); 0 refs -> empty
   int           num_refs;
   int           is_lines;
@@ -94,7 +105,8 @@ struct host_shape {
   dev_buffer<float>  d_positions, d_normals, d_radius;
   dev_buffer<int>    d_elems;
   dev_buffer<float4> d_nodes, d_prims;
-  dev_buffer<int>    d_ref_elem;
+  dev_buffer<int>    d_ref_elem, d_ref_pos;
+  dev_buffer<int4>   d_tie_nodes;
   int                root = 0, num_refs = 0, num_nodes = 0;
   bbox3f             root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   int  num_elems() const { return is_lines() ? (int)lines.size() / 2 : (int)triangles.size() / 3; }

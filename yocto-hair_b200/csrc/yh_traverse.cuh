@@ -45,6 +45,30 @@ struct trav_stack {
 #define YH_STAT(x)
 #endif
 
+// True when the reference's traversal (intersect_shape_bvh,
+// yocto_pathtrace.cpp:866-925) reaches element eb AFTER element ea for a ray
+// with these direction signs.  Its DFS pops the child on the ray's near side
+// of the split axis first (:879-886) and walks a leaf in primitive order, and
+// a hit at t == tmax replaces the stored one, so among exact ties the element
+// visited last is the one it returns.
+__device__ __noinline__ bool reference_visits_later(const dev_shape& sh, int ea, int eb, unsigned dsign) {
+  int pa = __ldg(sh.ref_pos + ea), pb = __ldg(sh.ref_pos + eb);
+  if (pa == pb) return false;
+  int  lo = min(pa, pb), hi = max(pa, pb);
+  bool hi_later = true;  // same leaf: position order
+  int  node     = sh.num_tie_nodes > 0 ? 0 : -1;
+  while (node >= 0) {
+    int4 n = __ldg(sh.tie_nodes + node);
+    if (hi < n.x) node = n.z;
+    else if (lo >= n.x) node = n.w;
+    else {  // lowest common ancestor: lo in child 0, hi in child 1
+      hi_later = ((dsign >> n.y) & 1u) == 0;  // positive direction: child 0 first
+      break;
+    }
+  }
+  return (pb == hi) == hi_later;
+}
+
 // Traverses one shape with an object-space ray.  On a hit updates ray.tmax,
 // ref (leaf-order reference index), uv, and returns true.
 __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref,
@@ -54,6 +78,8 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
   // reciprocal direction and origin pre-multiplied: slab distances become one FMA each
   float idx = 1.0f / ray.d.x, idy = 1.0f / ray.d.y, idz = 1.0f / ray.d.z;
   float ox = -ray.o.x * idx, oy = -ray.o.y * idy, oz = -ray.o.z * idz;
+  // ray_dsign, :862-863
+  unsigned dsign = (idx < 0 ? 1u : 0u) | (idy < 0 ? 2u : 0u) | (idz < 0 ? 4u : 0u);
   const float4* __restrict__ nodes = sh.nodes;
   const float4* __restrict__ prims = sh.prims;
   int base = st.sp;
@@ -95,9 +121,13 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
         for (int k = 0; k < count; k++) {
           const float4 a = __ldg(prims + 2 * (size_t)(first + k)), b = __ldg(prims + 2 * (size_t)(first + k) + 1);
           YH_STAT(if (prims_tested)(*prims_tested)++;)
-          if (intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uv, ray.tmax)) {
-            hit = true;
-            ref = first + k;
+          vec2f uvc;
+          float tc;
+          if (intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uvc, tc)) {
+            if (hit && tc == ray.tmax &&
+                !reference_visits_later(sh, __ldg(sh.ref_elem + ref), __ldg(sh.ref_elem + first + k), dsign))
+              continue;  // exact tie that the reference resolves the other way
+            hit = true, ref = first + k, uv = uvc, ray.tmax = tc;
           }
         }
       } else {
@@ -105,9 +135,13 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
           const float4 a = __ldg(prims + 3 * (size_t)(first + k)), b = __ldg(prims + 3 * (size_t)(first + k) + 1),
                        c = __ldg(prims + 3 * (size_t)(first + k) + 2);
           YH_STAT(if (prims_tested)(*prims_tested)++;)
-          if (intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uv, ray.tmax)) {
-            hit = true;
-            ref = first + k;
+          vec2f uvc;
+          float tc;
+          if (intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uvc, tc)) {
+            if (hit && tc == ray.tmax &&
+                !reference_visits_later(sh, __ldg(sh.ref_elem + ref), __ldg(sh.ref_elem + first + k), dsign))
+              continue;
+            hit = true, ref = first + k, uv = uvc, ray.tmax = tc;
           }
         }
       }
