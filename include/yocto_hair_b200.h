@@ -147,7 +147,8 @@ void      yh_scene_destroy(yh_scene* scene);
  * segment from up to `max_split` boxes (0 = library default).               */
 typedef struct yh_bvh_params {
   int max_split;
-  int reserved[7];
+  int leaf_size; /* references per leaf, 1..8 (0 = library default)        */
+  int reserved[6];
 } yh_bvh_params;
 yh_status yh_scene_init_bvh(yh_scene* scene, const yh_bvh_params* params);
 

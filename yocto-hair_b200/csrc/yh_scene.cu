@@ -46,16 +46,16 @@ __global__ void k_count_refs(int is_lines, const int* elems, const float* pos, c
 // Padding keeps every box conservative with respect to the rounding of the
 // exact primitive test (the hit point of an accepted intersection always lies
 // inside the padded box of the sub-span that contains its segment parameter).
-__device__ __forceinline__ void pad_box(vec3f& lo, vec3f& hi) {
-  float m   = fmaxf(fmaxf(fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y))),
-      fmaxf(fabsf(lo.z), fabsf(hi.z)));
-  float eps = 4e-7f * m + 1e-30f;
+// `scale` = largest |coordinate| of the shape: the traversal's fused slab test
+// needs the pad to dominate 6e-8 |ray origin| (yh_traverse.cuh).
+__device__ __forceinline__ void pad_box(vec3f& lo, vec3f& hi, float scale) {
+  float eps = 4e-7f * scale + 1e-30f;
   lo        = lo - eps;
   hi        = hi + eps;
 }
 
 __global__ void k_make_refs(int is_lines, const int* elems, const float* pos, const float* radius, int n,
-    const int* offsets, const int* counts, ref_bounds* refs, int* ref_prim, vec3f cmin, vec3f cinv,
+    const int* offsets, const int* counts, ref_bounds* refs, int* ref_prim, vec3f cmin, vec3f cinv, float scale,
     unsigned long long* keys, int* ref_ids) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -72,14 +72,14 @@ __global__ void k_make_refs(int is_lines, const int* elems, const float* pos, co
       ra         = ra * 1.000001f;
       rb         = rb * 1.000001f;
       bbox3f box = k == 1 ? line_bounds(p0, p1, r0, r1) : line_bounds(pa, pb, ra, rb);
-      pad_box(box.min, box.max);
+      pad_box(box.min, box.max, scale);
       refs[first + s]     = {make_float4(box.min.x, box.min.y, box.min.z, 0), make_float4(box.max.x, box.max.y, box.max.z, 0)};
       ref_prim[first + s] = i;
     }
   } else {
     int    a = elems[3 * i], b = elems[3 * i + 1], c = elems[3 * i + 2];
     bbox3f box = triangle_bounds(ldv(pos, a), ldv(pos, b), ldv(pos, c));
-    pad_box(box.min, box.max);
+    pad_box(box.min, box.max, scale);
     refs[first]     = {make_float4(box.min.x, box.min.y, box.min.z, 0), make_float4(box.max.x, box.max.y, box.max.z, 0)};
     ref_prim[first] = i;
   }
@@ -179,10 +179,10 @@ __global__ void k_refit(int n, const int* sorted_ref, const ref_bounds* refs, co
   }
 }
 
-__global__ void k_keep_flags(int n_inner, const int* first, const int* last, int* keep) {
+__global__ void k_keep_flags(int n_inner, const int* first, const int* last, int leaf_max, int* keep) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_inner) return;
-  keep[i] = (last[i] - first[i] + 1) > kLeafMax ? 1 : 0;
+  keep[i] = (last[i] - first[i] + 1) > leaf_max ? 1 : 0;
 }
 
 __device__ __forceinline__ int leaf_code(int first_ref, int count) { return ~((first_ref << 3) | (count - 1)); }
@@ -264,7 +264,7 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
   tie_nodes.clear();
   struct item { int node, start, end; };
   std::vector<item> todo;
-  if (n > kLeafMax) {
+  if (n > kRefLeafMax) {
     tie_nodes.push_back({0, 0, -1, -1});
     todo.push_back({0, 0, n});
   }
@@ -290,7 +290,7 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
     int child[2];
     int range[2][2] = {{it.start, mid}, {mid, it.end}};
     for (int c = 0; c < 2; c++) {
-      if (range[c][1] - range[c][0] > kLeafMax) {
+      if (range[c][1] - range[c][0] > kRefLeafMax) {
         child[c] = (int)tie_nodes.size();
         tie_nodes.push_back({0, 0, -1, -1});
         todo.push_back({child[c], range[c][0], range[c][1]});
@@ -304,7 +304,7 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
   for (int i = 0; i < n; i++) ref_pos[prims[i].primitive] = i;
 }
 
-static yh_status build_shape_bvh(host_shape& sh, int max_split) {
+static yh_status build_shape_bvh(host_shape& sh, int max_split, int leaf_max) {
   bool lines = sh.is_lines();
   int  n     = sh.num_elems();
   sh.root = 0, sh.num_refs = 0, sh.num_nodes = 0;
@@ -345,6 +345,10 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
     cmin    = min3(cmin, p);
     cmax    = max3(cmax, p);
   }
+  float rmax = 0;
+  for (float r : sh.radius) rmax = fmax_(rmax, fabs_(r));
+  sh.scale = fmax_(fmax_(fmax_(fabs_(cmin.x), fabs_(cmax.x)), fmax_(fabs_(cmin.y), fabs_(cmax.y))),
+                 fmax_(fabs_(cmin.z), fabs_(cmax.z))) + rmax;
   vec3f ext  = cmax - cmin;
   vec3f cinv = {ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f, ext.z > 0 ? 1.0f / ext.z : 0.0f};
 
@@ -358,7 +362,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   YH_CUDA(keys_in.alloc(R));
   YH_CUDA(keys_out.alloc(R));
   k_make_refs<<<G(n), B>>>(lines, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, n, offsets.ptr,
-      counts.ptr, refs.ptr, ref_prim.ptr, cmin, cinv, keys_in.ptr, ids_in.ptr);
+      counts.ptr, refs.ptr, ref_prim.ptr, cmin, cinv, sh.scale, keys_in.ptr, ids_in.ptr);
   YH_CUDA(cudaGetLastError());
   tmp_bytes = 0;
   YH_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in.ptr, keys_out.ptr, ids_in.ptr, ids_out.ptr, R, 0, 63));
@@ -373,7 +377,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   YH_CUDA(cudaGetLastError());
   sh.num_refs = R;
 
-  if (R <= kLeafMax) {  // the whole shape is one leaf
+  if (R <= leaf_max) {  // the whole shape is one leaf
     sh.root = ~((0 << 3) | (R - 1));
     std::vector<ref_bounds> h(R);
     YH_CUDA(cudaMemcpy(h.data(), refs.ptr, sizeof(ref_bounds) * R, cudaMemcpyDeviceToHost));
@@ -403,7 +407,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   YH_CUDA(cudaGetLastError());
   k_refit<<<G(R), B>>>(R, ids_out.ptr, refs.ptr, left.ptr, right.ptr, parent_inner.ptr, parent_leaf.ptr, flags.ptr, node_box.ptr);
   YH_CUDA(cudaGetLastError());
-  k_keep_flags<<<G(ni), B>>>(ni, first.ptr, last.ptr, keep.ptr);
+  k_keep_flags<<<G(ni), B>>>(ni, first.ptr, last.ptr, leaf_max, keep.ptr);
   YH_CUDA(cudaGetLastError());
   tmp_bytes = 0;
   YH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep.ptr, new_index.ptr, ni));
@@ -412,7 +416,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   int k_last = 0, i_last = 0;
   YH_CUDA(cudaMemcpy(&k_last, keep.ptr + (ni - 1), 4, cudaMemcpyDeviceToHost));
   YH_CUDA(cudaMemcpy(&i_last, new_index.ptr + (ni - 1), 4, cudaMemcpyDeviceToHost));
-  int kept = k_last + i_last;  // node 0 (the root) is kept because R > kLeafMax, and gets index 0
+  int kept = k_last + i_last;  // node 0 (the root) is kept because R > leaf_max, and gets index 0
   YH_CUDA(sh.d_nodes.alloc((size_t)kept * 4));
   k_emit_nodes<<<G(ni), B>>>(ni, keep.ptr, new_index.ptr, left.ptr, right.ptr, first.ptr, last.ptr,
       ids_out.ptr, refs.ptr, node_box.ptr, sh.d_nodes.ptr);
@@ -474,6 +478,7 @@ static yh_status upload_tables(yh_scene* sc) {
     d.nodes = s->d_nodes.ptr, d.prims = s->d_prims.ptr, d.ref_elem = s->d_ref_elem.ptr;
     d.ref_pos = s->d_ref_pos.ptr, d.tie_nodes = s->d_tie_nodes.ptr, d.num_tie_nodes = (int)s->d_tie_nodes.count;
     d.root = s->root, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0;
+    d.scale = s->scale;
     d.has_normals = s->normals.empty() ? 0 : 1;
     d.positions = s->d_positions.ptr, d.normals = s->d_normals.ptr, d.elems = s->d_elems.ptr;
     d.num_elems = s->num_elems();
@@ -596,9 +601,11 @@ yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
   if (!sc) return fail(YH_ERR_INVALID, "yh_scene_init_bvh: scene is null");
   int max_split = params && params->max_split > 0 ? params->max_split : 1;
   if (max_split > 8) max_split = 8;
+  int leaf_max = params && params->leaf_size > 0 ? params->leaf_size : kLeafMax;
+  if (leaf_max > 8) leaf_max = 8;  // 3 bits of the leaf code
   sc->stats = yh_bvh_stats{};
   for (auto s : sc->shapes) {
-    yh_status st = build_shape_bvh(*s, max_split);
+    yh_status st = build_shape_bvh(*s, max_split, leaf_max);
     if (st != YH_OK) return st;
     sc->stats.num_primitives += s->num_elems();
     sc->stats.num_references += s->num_refs;

@@ -31,7 +31,8 @@
 
 namespace yh {
 
-constexpr int kLeafMax = 4;  // the reference's bvh_max_prims (yocto_pathtrace.cpp:598)
+constexpr int kLeafMax    = 4;  // default leaf size of our tree (yh_bvh_params::leaf_size)
+constexpr int kRefLeafMax = 4;  // the reference's bvh_max_prims (yocto_pathtrace.cpp:598)
 
 struct dev_shape {
   const float4* nodes;
@@ -42,6 +43,7 @@ struct dev_shape {
   int           num_tie_nodes;
   int           root;       // child encoding of the whole tree (leaf if < 0); 0 refs -> empty
   int           num_refs;
+  float         scale;      // largest |coordinate| of the shape: boxes are padded by 4e-7 * scale
   int           is_lines;
   int           has_normals;
   const float*  positions;  // xyz
@@ -108,6 +110,7 @@ struct host_shape {
   dev_buffer<int>    d_ref_elem, d_ref_pos;
   dev_buffer<int4>   d_tie_nodes;
   int                root = 0, num_refs = 0, num_nodes = 0;
+  float              scale = 0;
   bbox3f             root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   int  num_elems() const { return is_lines() ? (int)lines.size() / 2 : (int)triangles.size() / 3; }
   bool is_lines() const { return !lines.empty(); }

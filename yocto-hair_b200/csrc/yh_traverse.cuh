@@ -69,35 +69,80 @@ __device__ __noinline__ bool reference_visits_later(const dev_shape& sh, int ea,
   return (pb == hi) == hi_later;
 }
 
+// Certain-miss test for a line primitive, evaluated in fast arithmetic (FMA,
+// approximate sqrt) BEFORE the reference's own test.  intersect_line
+// (yocto_math.h:3426-3469) accepts only when a point of the ray line and a
+// point of the segment line are closer than max(r0, r1); both are at least
+// the line-line distance L = |w . n| / |n|, n = u x v, apart.  So
+//     L > max(r0, r1) + (rounding of either evaluation)
+// proves the reference rejects.  The slack covers the reference's rounding of
+// pr / pl (a few ulp of the coordinates) and this evaluation's own (n is only
+// trusted when the lines are more than ~1.8 degrees apart).  A primitive that is
+// not provably missed takes the exact path, so hit records are unchanged.
+__device__ __forceinline__ bool line_certain_miss(const vec3f& o, const vec3f& u, float uu, float mo,
+    const float4& a, const float4& b) {
+  float vx = b.x - a.x, vy = b.y - a.y, vz = b.z - a.z;
+  float wx = o.x - a.x, wy = o.y - a.y, wz = o.z - a.z;
+  float nx = __fmaf_rn(u.y, vz, -u.z * vy), ny = __fmaf_rn(u.z, vx, -u.x * vz), nz = __fmaf_rn(u.x, vy, -u.y * vx);
+  float nn = __fmaf_rn(nx, nx, __fmaf_rn(ny, ny, nz * nz));
+  float vv = __fmaf_rn(vx, vx, __fmaf_rn(vy, vy, vz * vz));
+  float ww = __fmaf_rn(wx, wx, __fmaf_rn(wy, wy, wz * wz));
+  float wn = __fmaf_rn(wx, nx, __fmaf_rn(wy, ny, wz * nz));
+  float m1  = mo + fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + fabsf(b.x) + fabsf(b.y) + fabsf(b.z);
+  float tol = __fmaf_rn(fmaxf(a.w, b.w), 1.01f, __fmaf_rn(2e-5f, __fsqrt_ru(ww), 4e-6f * m1));
+  return nn > 1e-3f * uu * vv && wn * wn > nn * tol * tol;
+}
+
+constexpr int kTraverseDone = (int)0x80000000;  // never a leaf code: those are ~x with x < 2^31
+
 // Traverses one shape with an object-space ray.  On a hit updates ray.tmax,
-// ref (leaf-order reference index), uv, and returns true.
-__device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref,
+// ref (leaf-order reference index), uv, and returns true.  while-while form:
+// every lane first walks inner nodes until it holds a leaf (or is done), then
+// the warp tests its leaves together, so the long primitive test does not
+// serialise against the short node step.
+//
+// Box test: slab distances as ONE FMA per plane, plane * (1/d) + (-o/d).  The
+// rounding of -o/d displaces a plane by <= 6e-8 |o| in space; the builder pads
+// every box by 4e-7 * (largest coordinate of the shape), which covers it for
+// |o| <= 4 * that scale.  Rays that start farther away (FUSED = false) use the
+// (plane - o) * (1/d) form, exact in the difference like the reference's
+// intersect_bbox (yocto_math.h:3544-3554).  A zero direction component is
+// replaced by +-1e-20 in the fused form (1/0 = inf would turn the FMA into
+// inf - inf); the slab then still rejects origins outside it and passes
+// origins inside, as the reference does.
+template <bool FUSED>
+__device__ __forceinline__ bool intersect_shape_impl(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref,
     vec2f& uv, bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
-  if (sh.num_refs == 0) return false;
   bool  hit  = false;
-  // reciprocal direction and origin pre-multiplied: slab distances become one FMA each
-  float idx = 1.0f / ray.d.x, idy = 1.0f / ray.d.y, idz = 1.0f / ray.d.z;
-  float ox = -ray.o.x * idx, oy = -ray.o.y * idy, oz = -ray.o.z * idz;
   // ray_dsign, :862-863
-  unsigned dsign = (idx < 0 ? 1u : 0u) | (idy < 0 ? 2u : 0u) | (idz < 0 ? 4u : 0u);
+  unsigned dsign = ((1.0f / ray.d.x) < 0 ? 1u : 0u) | ((1.0f / ray.d.y) < 0 ? 2u : 0u) | ((1.0f / ray.d.z) < 0 ? 4u : 0u);
+  auto     safe  = [](float d) { return FUSED && fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; };
+  float idx = 1.0f / safe(ray.d.x), idy = 1.0f / safe(ray.d.y), idz = 1.0f / safe(ray.d.z);
+  float ox = FUSED ? -ray.o.x * idx : ray.o.x, oy = FUSED ? -ray.o.y * idy : ray.o.y,
+        oz = FUSED ? -ray.o.z * idz : ray.o.z;
+  // slab distance of plane p along one axis
+  auto slab = [](float p, float id, float o) { return FUSED ? __fmaf_rn(p, id, o) : (p - o) * id; };
+  float uu = __fmaf_rn(ray.d.x, ray.d.x, __fmaf_rn(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
+  float mo = fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z);
   const float4* __restrict__ nodes = sh.nodes;
   const float4* __restrict__ prims = sh.prims;
+  const bool is_lines = sh.is_lines != 0;
   int base = st.sp;
   int cur  = sh.root;
   while (true) {
-    if (cur >= 0) {
+    while (cur >= 0) {
       const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1),
                    n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
       YH_STAT(if (nodes_visited)(*nodes_visited)++;)
       // child 0: min = n0.xyz, max = n0.w n1.x n1.y ; child 1: min = n1.z n1.w n2.x, max = n2.yzw
-      float a0 = __fmaf_rn(n0.x, idx, ox), b0 = __fmaf_rn(n0.w, idx, ox);
-      float a1 = __fmaf_rn(n0.y, idy, oy), b1 = __fmaf_rn(n1.x, idy, oy);
-      float a2 = __fmaf_rn(n0.z, idz, oz), b2 = __fmaf_rn(n1.y, idz, oz);
+      float a0 = slab(n0.x, idx, ox), b0 = slab(n0.w, idx, ox);
+      float a1 = slab(n0.y, idy, oy), b1 = slab(n1.x, idy, oy);
+      float a2 = slab(n0.z, idz, oz), b2 = slab(n1.y, idz, oz);
       float tn0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), ray.tmin));
       float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), ray.tmax));
-      float c0 = __fmaf_rn(n1.z, idx, ox), d0 = __fmaf_rn(n2.y, idx, ox);
-      float c1 = __fmaf_rn(n1.w, idy, oy), d1 = __fmaf_rn(n2.z, idy, oy);
-      float c2 = __fmaf_rn(n2.x, idz, oz), d2 = __fmaf_rn(n2.w, idz, oz);
+      float c0 = slab(n1.z, idx, ox), d0 = slab(n2.y, idx, ox);
+      float c1 = slab(n1.w, idy, oy), d1 = slab(n2.z, idy, oy);
+      float c2 = slab(n2.x, idz, oz), d2 = slab(n2.w, idz, oz);
       float tn1 = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), ray.tmin));
       float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), ray.tmax));
       // generous slack on both ends (padding + this keep the test conservative)
@@ -107,20 +152,22 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
         bool swap = tn1 < tn0;
         st.push(swap ? ch0 : ch1);
         cur = swap ? ch1 : ch0;
-        continue;
       } else if (h0) {
         cur = ch0;
-        continue;
       } else if (h1) {
         cur = ch1;
-        continue;
+      } else {
+        cur = st.sp == base ? kTraverseDone : st.pop();
       }
-    } else {
+    }
+    if (cur == kTraverseDone) break;
+    {
       int code = ~cur, first = code >> 3, count = (code & 7) + 1;
-      if (sh.is_lines) {
+      if (is_lines) {
         for (int k = 0; k < count; k++) {
           const float4 a = __ldg(prims + 2 * (size_t)(first + k)), b = __ldg(prims + 2 * (size_t)(first + k) + 1);
           YH_STAT(if (prims_tested)(*prims_tested)++;)
+          if (line_certain_miss(ray.o, ray.d, uu, mo, a, b)) continue;
           vec2f uvc;
           float tc;
           if (intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uvc, tc)) {
@@ -150,10 +197,23 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
         return true;
       }
     }
-    if (st.sp == base) break;
-    cur = st.pop();
+    cur = st.sp == base ? kTraverseDone : st.pop();
   }
   return hit;
+}
+
+template <bool FUSED>
+__device__ __noinline__ bool intersect_shape_far(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref, vec2f& uv,
+    bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
+  return intersect_shape_impl<FUSED>(sh, ray, st, ref, uv, find_any, nodes_visited, prims_tested);
+}
+__device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref,
+    vec2f& uv, bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
+  if (sh.num_refs == 0) return false;
+  float mo = fmaxf(fmaxf(fabsf(ray.o.x), fabsf(ray.o.y)), fabsf(ray.o.z));
+  if (!(mo <= 4.0f * sh.scale))  // far origin (or NaN): rare, kept out of line
+    return intersect_shape_far<false>(sh, ray, st, ref, uv, find_any, nodes_visited, prims_tested);
+  return intersect_shape_impl<true>(sh, ray, st, ref, uv, find_any, nodes_visited, prims_tested);
 }
 
 // conservative ray / box test for the object level
