@@ -144,28 +144,42 @@ __global__ void __launch_bounds__(256) k_start(path_state ps, queues q, dev_came
   queue_push(q.active[0], q.count + 0, live, slot);
 }
 
-__global__ void __launch_bounds__(kTraceBlock) k_intersect(dev_scene sc, path_state ps, queues q, int cur) {
-  __shared__ int smem_stack[kStackShared * kTraceBlock];
-  int            n = q.count[cur];
-  unsigned long long nv = 0, pt = 0;
-  for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-    int  idx  = base + threadIdx.x;
-    bool live = idx < n;
-    int  slot = live ? q.active[cur][idx] : 0;
-    int  kind = -1;
-    if (live) {
-      float4     o = ps.ray_o[slot], d = ps.ray_d[slot];
-      trav_stack st;
-      st.smem = smem_stack + threadIdx.x;
-      st.sp   = 0;
-      hit_record h = intersect_scene(sc, {{o.x, o.y, o.z}, {d.x, d.y, d.z}, ray_eps, flt_max}, st, false, &nv, &pt);
-      ps.hit[slot] = make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y));
-      kind = !h.hit ? 0 : (sc.shapes[sc.objects[h.object].shape].is_lines ? 2 : 1);
-    }
+// Ray source / hit sink of the wavefront for trace_persistent().
+struct wavefront_io {
+  const dev_scene& sc;
+  const path_state& ps;
+  const queues&     q;
+  const int*        active;
+  __device__ __forceinline__ bool load(int index, int& slot, ray3f& r) const {
+    slot     = active[index];
+    float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
+    r        = {{o.x, o.y, o.z}, {d.x, d.y, d.z}, ray_eps, flt_max};
+    return true;
+  }
+  __device__ __forceinline__ void reload(int slot, vec3f& o, vec3f& d) const {
+    float4 o4 = ps.ray_o[slot], d4 = ps.ray_d[slot];
+    o = {o4.x, o4.y, o4.z}, d = {d4.x, d4.y, d4.z};
+  }
+  __device__ __forceinline__ void store(int slot, const hit_record& h) const {
+    ps.hit[slot] = make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y));
+    int kind     = !h.hit ? 0 : (sc.shapes[sc.objects[h.object].shape].is_lines ? 2 : 1);
     queue_push(q.miss, q.count + 2, kind == 0, slot);
     queue_push(q.surface, q.count + 3, kind == 1, slot);
     queue_push(q.hair, q.count + 4, kind == 2, slot);
   }
+};
+
+// Closest hit for every slot of the active queue, then the slot id goes to the
+// miss / surface / hair queue.  Persistent warps, q.count[5] is the ray cursor.
+#ifndef YH_INTERSECT_BLOCKS
+#define YH_INTERSECT_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur) {
+  __shared__ int smem_stack[kStackShared * kTraceBlock];
+  int            n = q.count[cur];
+  unsigned long long nv = 0, pt = 0;
+  wavefront_io   io{sc, ps, q, q.active[cur]};
+  trace_persistent(sc, io, n, q.count + 5, smem_stack + threadIdx.x, false, &nv, &pt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.stats + 0, (unsigned long long)n);
 #ifdef YH_TRAVERSAL_STATS
   atomicAdd(q.stats + 3, nv);
@@ -333,7 +347,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_shade(dev_scene sc, path_state 
 
 __global__ void k_reset_counts(int* count, int next) {
   count[next] = 0;
-  count[2] = count[3] = count[4] = 0;
+  count[2] = count[3] = count[4] = count[5] = 0;
 }
 
 // init_state, yocto_pathtrace.cpp:1931-1946: pixel k takes the k-th draw of the
@@ -375,23 +389,41 @@ __global__ void k_resolve(const float4* accum, const int* samples, float4* rende
                     : make_float4(0, 0, 0, 0);
 }
 
-__global__ void __launch_bounds__(kTraceBlock) k_intersect_batch(dev_scene sc, const yh_ray* rays, long long n,
-    int find_any, yh_hit* hits) {
-  __shared__ int smem_stack[kStackShared * kTraceBlock];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    yh_ray     r = rays[i];
-    trav_stack st;
-    st.smem = smem_stack + threadIdx.x;
-    st.sp   = 0;
-    hit_record h = intersect_scene(sc, {{r.o[0], r.o[1], r.o[2]}, {r.d[0], r.d[1], r.d[2]}, r.tmin, r.tmax}, st,
-        find_any != 0);
-    hits[i] = {h.object, h.element, {h.uv.x, h.uv.y}, h.distance, h.hit ? 1 : 0};
+struct batch_io {
+  const yh_ray* rays;
+  yh_hit*       hits;
+  __device__ __forceinline__ bool load(int index, int& handle, ray3f& r) const {
+    yh_ray y = rays[index];
+    handle   = index;
+    r        = {{y.o[0], y.o[1], y.o[2]}, {y.d[0], y.d[1], y.d[2]}, y.tmin, y.tmax};
+    return true;
   }
+  __device__ __forceinline__ void reload(int handle, vec3f& o, vec3f& d) const {
+    const yh_ray& y = rays[handle];
+    o = {y.o[0], y.o[1], y.o[2]}, d = {y.d[0], y.d[1], y.d[2]};
+  }
+  __device__ __forceinline__ void store(int handle, const hit_record& h) const {
+    hits[handle] = {h.object, h.element, {h.uv.x, h.uv.y}, h.distance, h.hit ? 1 : 0};
+  }
+};
+__global__ void __launch_bounds__(kTraceBlock) k_intersect_batch(dev_scene sc, const yh_ray* rays, int n,
+    int find_any, yh_hit* hits, int* cursor) {
+  __shared__ int smem_stack[kStackShared * kTraceBlock];
+  batch_io       io{rays, hits};
+  trace_persistent(sc, io, n, cursor, smem_stack + threadIdx.x, find_any != 0, nullptr, nullptr);
 }
 
 }  // namespace yh
 
 using namespace yh;
+
+// one resident wave of kTraceBlock-thread blocks (persistent kernels)
+static int persistent_grid(const void* kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 4;
+  return per_sm * sm_count();
+}
 
 struct yh_state {
   const yh_scene* scene = nullptr;
@@ -564,6 +596,7 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
   k_start<<<(st->num_slots + 255) / 256, 256, 0, s>>>(ps, q, st->camera, tc, st->num_slots, num_samples);
   int64_t launches = 1, iterations = 0;
   int     grid_t = sms * 8, grid_s = sms * 4;
+  int     grid_i = persistent_grid((const void*)k_intersect);
   int     cur = 0;
   size_t  ev_used = 0;
   auto    ev = [&]() -> cudaEvent_t {
@@ -582,7 +615,7 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
     int next = cur ^ 1;
     k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
     if (prof) ev();
-    k_intersect<<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, cur);
+    k_intersect<<<grid_i, kTraceBlock, 0, s>>>(sc, ps, q, cur);
     if (prof) ev();
     k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
     k_shade<false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
@@ -684,10 +717,19 @@ yh_status yh_intersect_batch_dev(const yh_scene* scene, const yh_ray* rays_dev, 
   cudaEvent_t e0, e1;
   YH_CUDA(cudaEventCreate(&e0));
   YH_CUDA(cudaEventCreate(&e1));
-  int64_t g = (n + kTraceBlock - 1) / kTraceBlock;
-  int64_t cap = (int64_t)sm_count() * 16;
+  const int64_t   chunk = 1ll << 30;  // the ray cursor is a 32-bit counter
+  int64_t         nchunks = (n + chunk - 1) / chunk;
+  dev_buffer<int> cursor;
+  YH_CUDA(cursor.alloc((size_t)nchunks));
+  YH_CUDA(cudaMemset(cursor.ptr, 0, cursor.bytes()));
+  int grid = persistent_grid((const void*)k_intersect_batch);
   YH_CUDA(cudaEventRecord(e0));
-  k_intersect_batch<<<(int)(g < cap ? g : cap), kTraceBlock>>>(scene->view(), rays_dev, n, find_any, hits_dev);
+  for (int64_t c = 0; c < nchunks; c++) {
+    int64_t m = n - c * chunk < chunk ? n - c * chunk : chunk;
+    int64_t g = (m + kTraceBlock - 1) / kTraceBlock;
+    k_intersect_batch<<<(int)(g < grid ? g : grid), kTraceBlock>>>(scene->view(), rays_dev + c * chunk, (int)m, find_any,
+        hits_dev + c * chunk, cursor.ptr + c);
+  }
   YH_CUDA(cudaEventRecord(e1));
   YH_CUDA(cudaEventSynchronize(e1));
   YH_CUDA(cudaGetLastError());

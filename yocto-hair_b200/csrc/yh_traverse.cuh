@@ -260,4 +260,207 @@ __device__ __forceinline__ hit_record intersect_scene(const dev_scene& sc, ray3f
   return h;
 }
 
+
+// --------------------------------------------------------------------------
+// Persistent closest-hit tracer: dynamic ray fetch, one step per iteration,
+// deferred exact tests.
+//
+// Traversal lengths of hair rays are wildly uneven (a ray that leaves the hair
+// volume ends after a handful of nodes, one that grazes a lock visits hundreds),
+// and so is the number of node steps between two leaves.  A warp that takes 32
+// rays and runs "all node steps, then all leaf tests" spends its node loop at
+// ~7 of 32 lanes (ncu, profiles/r01_*).  Here
+//   * a warp keeps running and refills the lanes whose ray has finished from a
+//     global cursor;
+//   * every iteration each lane takes ONE step, a node step or the certain-miss
+//     test of one primitive (comparable cost), so no lane waits for another
+//     lane's run of node steps;
+//   * the reference's exact primitive test (long: two IEEE divisions, a square
+//     root) is deferred: a primitive that survives the certain-miss test is
+//     parked, and the warp runs the exact test when enough lanes have one parked
+//     or a lane cannot go on without it.
+// The exact tests may therefore run in another order than the tree is walked.
+// That is legal because the hit record does not depend on the order: the
+// closest t wins, and an exact tie goes to reference_visits_later().
+//
+// IO supplies rays and consumes hit records:
+//   bool load(int index, int& handle, ray3f& world_ray)
+//   void reload(int handle, vec3f& o, vec3f& d)        (world origin / direction)
+//   void store(int handle, const hit_record&)
+constexpr int kRefillIdle = 8;  // refill once this many lanes of the warp are idle
+constexpr int kExactBatch = 8;  // run the parked exact tests once this many lanes have one
+
+template <class IO>
+__device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, int n, int* cursor, int* smem_stack,
+    bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
+  const unsigned full = 0xffffffffu;
+  const int      lane = threadIdx.x & 31;
+  trav_stack     st;
+  st.smem = smem_stack;
+  st.sp   = 0;
+  bool  have = false, exhausted = false;
+  int   handle = 0, obj = -1, cur = kTraverseDone, leaf_k = 0;
+  int   parked = -1;       // reference index waiting for its exact test
+  bool  blocked = false;   // a second survivor turned up while one is parked
+  // ray in the space of the object being traversed
+  vec3f o = {0, 0, 0}, d = {0, 0, 1};
+  float tmin = 0, tmax = 0;
+  float idx = 0, idy = 0, idz = 0, ox = 0, oy = 0, oz = 0, uu = 0, mo = 0;
+  unsigned dsign = 0;
+  const float4* __restrict__ nodes = nullptr;
+  const float4* __restrict__ prims = nullptr;
+  const dev_shape* shp = nullptr;
+  bool  is_lines = false, shape_hit = false;
+  int   ref = -1;
+  vec2f uv = {0, 0};
+  hit_record best;
+  best.object = -1, best.element = -1, best.uv = {0, 0}, best.distance = 0, best.hit = false;
+
+  while (true) {
+    // ---- 1. refill idle lanes from the global cursor
+    unsigned idle = __ballot_sync(full, !have);
+    if (!exhausted && (__popc(idle) >= kRefillIdle)) {
+      int cnt = __popc(idle), base = 0;
+      if (lane == 0) base = atomicAdd(cursor, cnt);
+      base = __shfl_sync(full, base, 0);
+      if (!have) {
+        int   index = base + __popc(idle & ((1u << lane) - 1));
+        ray3f wr;
+        if (index < n && io.load(index, handle, wr)) {
+          have = true, obj = -1, cur = kTraverseDone, st.sp = 0, shape_hit = false, leaf_k = 0;
+          tmin = wr.tmin, tmax = wr.tmax;
+          best.object = -1, best.element = -1, best.uv = {0, 0}, best.distance = 0, best.hit = false;
+        }
+      }
+      exhausted = base + cnt >= n;
+      idle      = __ballot_sync(full, !have);
+    }
+    if (idle == full) {
+      if (exhausted) break;
+      continue;
+    }
+
+    // ---- 2. parked exact tests (the reference's own arithmetic)
+    {
+      bool     pending = parked >= 0;
+      unsigned pm = __ballot_sync(full, pending);
+      unsigned um = __ballot_sync(full, pending && (blocked || cur == kTraverseDone));
+      if (pending && (um != 0 || __popc(pm) >= kExactBatch)) {
+        ray3f ray = {o, d, tmin, tmax};
+        vec2f uvc;
+        float tc;
+        bool  got;
+        if (is_lines) {
+          const float4 a = __ldg(prims + 2 * (size_t)parked), b = __ldg(prims + 2 * (size_t)parked + 1);
+          got = intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uvc, tc);
+        } else {
+          const float4 a = __ldg(prims + 3 * (size_t)parked), b = __ldg(prims + 3 * (size_t)parked + 1),
+                       c = __ldg(prims + 3 * (size_t)parked + 2);
+          got = intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uvc, tc);
+        }
+        if (got && !(shape_hit && tc == tmax &&
+                       !reference_visits_later(*shp, __ldg(shp->ref_elem + ref), __ldg(shp->ref_elem + parked), dsign))) {
+          shape_hit = true, ref = parked, uv = uvc, tmax = tc;
+          if (find_any) st.sp = 0, cur = kTraverseDone, leaf_k = 0;
+        }
+        parked = -1, blocked = false;
+      }
+    }
+
+    // ---- 3. lanes between shapes: close the finished one, open the next object
+    if (have && cur == kTraverseDone) {
+      if (shape_hit) {
+        best.hit = true, best.object = obj, best.element = __ldg(shp->ref_elem + ref), best.uv = uv, best.distance = tmax;
+        shape_hit = false;
+        if (find_any) obj = sc.num_objects;
+      }
+      vec3f wo, wd;
+      io.reload(handle, wo, wd);
+      bool opened = false;
+      while (++obj < sc.num_objects) {
+        const dev_object& ob = sc.objects[obj];
+        ray3f             wr = {wo, wd, tmin, tmax};
+        if (!hits_box(wr, ob.bbox)) continue;
+        const dev_shape& sh = sc.shapes[ob.shape];
+        if (sh.num_refs == 0) continue;
+        o = transform_point(ob.inv_frame, wo), d = transform_vector(ob.inv_frame, wd);
+        mo = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+        if (!(mo <= 4.0f * sh.scale)) {  // far origin: whole shape at once, out of line (rare)
+          ray3f r = {o, d, tmin, tmax};
+          int   rr = -1;
+          vec2f ruv;
+          if (intersect_shape_far<false>(sh, r, st, rr, ruv, find_any, nodes_visited, prims_tested)) {
+            best.hit = true, best.object = obj, best.element = __ldg(sh.ref_elem + rr), best.uv = ruv;
+            best.distance = tmax = r.tmax;
+            if (find_any) break;
+          }
+          continue;
+        }
+        auto safe = [](float v) { return fabsf(v) < 1e-20f ? copysignf(1e-20f, v) : v; };
+        dsign = ((1.0f / d.x) < 0 ? 1u : 0u) | ((1.0f / d.y) < 0 ? 2u : 0u) | ((1.0f / d.z) < 0 ? 4u : 0u);
+        idx = 1.0f / safe(d.x), idy = 1.0f / safe(d.y), idz = 1.0f / safe(d.z);
+        ox = -o.x * idx, oy = -o.y * idy, oz = -o.z * idz;
+        uu = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
+        mo = fabsf(o.x) + fabsf(o.y) + fabsf(o.z);
+        nodes = sh.nodes, prims = sh.prims, shp = &sh, is_lines = sh.is_lines != 0;
+        cur = sh.root, ref = -1, leaf_k = 0;
+        opened = true;
+        break;
+      }
+      if (!opened) {
+        io.store(handle, best);
+        have = false;
+      }
+    }
+
+    // ---- 4. one step per lane
+    if (cur >= 0) {
+      const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1),
+                   n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
+      YH_STAT(if (nodes_visited)(*nodes_visited)++;)
+      float a0 = __fmaf_rn(n0.x, idx, ox), b0 = __fmaf_rn(n0.w, idx, ox);
+      float a1 = __fmaf_rn(n0.y, idy, oy), b1 = __fmaf_rn(n1.x, idy, oy);
+      float a2 = __fmaf_rn(n0.z, idz, oz), b2 = __fmaf_rn(n1.y, idz, oz);
+      float tn0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));
+      float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));
+      float c0 = __fmaf_rn(n1.z, idx, ox), d0 = __fmaf_rn(n2.y, idx, ox);
+      float c1 = __fmaf_rn(n1.w, idy, oy), d1 = __fmaf_rn(n2.z, idy, oy);
+      float c2 = __fmaf_rn(n2.x, idz, oz), d2 = __fmaf_rn(n2.w, idz, oz);
+      float tn1 = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), tmin));
+      float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), tmax));
+      bool h0 = tn0 * 0.9999995f <= tf0 * 1.0000005f, h1 = tn1 * 0.9999995f <= tf1 * 1.0000005f;
+      int  ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+      if (h0 && h1) {
+        bool swap = tn1 < tn0;
+        st.push(swap ? ch0 : ch1);
+        cur = swap ? ch1 : ch0;
+      } else if (h0) {
+        cur = ch0;
+      } else if (h1) {
+        cur = ch1;
+      } else {
+        cur = st.sp == 0 ? kTraverseDone : st.pop();
+      }
+    } else if (cur != kTraverseDone) {
+      int  code = ~cur, first = code >> 3, count = (code & 7) + 1;
+      int  r    = first + leaf_k;
+      bool survivor = true;
+      if (is_lines) {
+        const float4 a = __ldg(prims + 2 * (size_t)r), b = __ldg(prims + 2 * (size_t)r + 1);
+        survivor = !line_certain_miss(o, d, uu, mo, a, b);
+      }
+      if (survivor && parked >= 0) {
+        blocked = true;  // step 2 empties the slot, then this primitive is looked at again
+      } else {
+        YH_STAT(if (prims_tested)(*prims_tested)++;)
+        if (survivor) parked = r;
+        if (++leaf_k == count) {
+          leaf_k = 0;
+          cur    = st.sp == 0 ? kTraverseDone : st.pop();
+        }
+      }
+    }
+  }
+}
+
 }  // namespace yh
