@@ -599,7 +599,7 @@ void yh_scene_destroy(yh_scene* scene) { delete scene; }
 yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
   YH_REQUIRE_DEVICE();
   if (!sc) return fail(YH_ERR_INVALID, "yh_scene_init_bvh: scene is null");
-  int max_split = params && params->max_split > 0 ? params->max_split : 1;
+  int max_split = params && params->max_split > 0 ? params->max_split : kDefaultSplit;
   if (max_split > 8) max_split = 8;
   int leaf_max = params && params->leaf_size > 0 ? params->leaf_size : kLeafMax;
   if (leaf_max > 8) leaf_max = 8;  // 3 bits of the leaf code

@@ -31,7 +31,9 @@
 
 namespace yh {
 
-constexpr int kLeafMax    = 4;  // default leaf size of our tree (yh_bvh_params::leaf_size)
+constexpr int kLeafMax    = 1;  // default leaf size of our tree (yh_bvh_params::leaf_size): the parent's
+                                 // box test is then the primitive's own box test (yh_traverse.cuh)
+constexpr int kDefaultSplit = 4; // default yh_bvh_params::max_split
 constexpr int kRefLeafMax = 4;  // the reference's bvh_max_prims (yocto_pathtrace.cpp:598)
 
 struct dev_shape {

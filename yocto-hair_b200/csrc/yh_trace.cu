@@ -17,8 +17,12 @@
 // Each shading kernel appends surviving or regenerated slots to the next
 // iteration's active queue.
 #include <cmath>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
+
+#include <cub/cub.cuh>
 
 #include "yh_shade.cuh"
 
@@ -62,6 +66,13 @@ struct trace_consts {
   float clamp;
 };
 
+// Path state is touched once per wavefront iteration and is larger than L2
+// (104 B per pixel): stream it (evict-first) so the BVH stays L2-resident.
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, decltype(T{}) v) { __stcs(p, v); }
+
 // warp-aggregated queue append
 __device__ __forceinline__ void queue_push(int* queue, int* counter, bool pred, int value) {
   unsigned mask = __ballot_sync(__activemask(), pred);
@@ -96,11 +107,11 @@ __device__ __forceinline__ ray3f camera_ray(const dev_camera& cam, const trace_c
 
 __device__ __forceinline__ void start_sample(const path_state& ps, const dev_camera& cam, const trace_consts& tc,
     int slot, rng_state& rng) {
-  ray3f ray       = camera_ray(cam, tc, ps.pixel[slot], rng);
-  ps.ray_o[slot]  = make_float4(ray.o.x, ray.o.y, ray.o.z, 0);
-  ps.ray_d[slot]  = make_float4(ray.d.x, ray.d.y, ray.d.z, 0);
-  ps.weight[slot] = make_float4(1, 1, 1, 0);
-  ps.radiance[slot] = make_float4(0, 0, 0, __int_as_float(0));
+  ray3f ray       = camera_ray(cam, tc, ld_stream(&ps.pixel[slot]), rng);
+  st_stream(&ps.ray_o[slot], make_float4(ray.o.x, ray.o.y, ray.o.z, 0));
+  st_stream(&ps.ray_d[slot], make_float4(ray.d.x, ray.d.y, ray.d.z, 0));
+  st_stream(&ps.weight[slot], make_float4(1, 1, 1, 0));
+  st_stream(&ps.radiance[slot], make_float4(0, 0, 0, __int_as_float(0)));
 }
 
 // trace_sample tail, :1683-1688, then regenerate or retire the slot.
@@ -109,14 +120,14 @@ __device__ __forceinline__ bool finish_sample(const path_state& ps, const dev_ca
   if (!isfinite3(radiance)) radiance = {0, 0, 0};
   float m = max3(radiance);
   if (m > tc.clamp) radiance = radiance * div_(tc.clamp, m);
-  int    px = ps.pixel[slot];
-  float4 a  = ps.accum[px];
+  int    px = ld_stream(&ps.pixel[slot]);
+  float4 a  = ld_stream(&ps.accum[px]);
   a.x += radiance.x, a.y += radiance.y, a.z += radiance.z, a.w += alpha;
-  ps.accum[px] = a;
-  ps.samples[px] += 1;
-  int left = ps.remaining[slot];
+  st_stream(&ps.accum[px], a);
+  st_stream(&ps.samples[px], ld_stream(&ps.samples[px]) + 1);
+  int left = ld_stream(&ps.remaining[slot]);
   if (left > 0) {
-    ps.remaining[slot] = left - 1;
+    st_stream(&ps.remaining[slot], left - 1);
     start_sample(ps, cam, tc, slot, rng);
     return true;
   }
@@ -128,18 +139,18 @@ __global__ void __launch_bounds__(256) k_start(path_state ps, queues q, dev_came
   int  slot = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = slot < num_slots && num_samples > 0;
   if (live) {
-    rng_state rng = {ps.rng_state[slot], ps.rng_inc[slot]};
+    rng_state rng = {ld_stream(&ps.rng_state[slot]), ld_stream(&ps.rng_inc[slot])};
     if (tc.bounces <= 0) {
       // the path loop (:1395) never runs: black sample, alpha 0, camera draws still consumed
-      int px = ps.pixel[slot];
+      int px = ld_stream(&ps.pixel[slot]);
       for (int s = 0; s < num_samples; s++) camera_ray(cam, tc, px, rng);
-      ps.samples[px] += num_samples;
+      st_stream(&ps.samples[px], ld_stream(&ps.samples[px]) + num_samples);
       live = false;
     } else {
-      ps.remaining[slot] = num_samples - 1;
+      st_stream(&ps.remaining[slot], num_samples - 1);
       start_sample(ps, cam, tc, slot, rng);
     }
-    ps.rng_state[slot] = rng.state;
+    st_stream(&ps.rng_state[slot], rng.state);
   }
   queue_push(q.active[0], q.count + 0, live, slot);
 }
@@ -152,16 +163,16 @@ struct wavefront_io {
   const int*        active;
   __device__ __forceinline__ bool load(int index, int& slot, ray3f& r) const {
     slot     = active[index];
-    float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
+    float4 o = ld_stream(&ps.ray_o[slot]), d = ld_stream(&ps.ray_d[slot]);
     r        = {{o.x, o.y, o.z}, {d.x, d.y, d.z}, ray_eps, flt_max};
     return true;
   }
   __device__ __forceinline__ void reload(int slot, vec3f& o, vec3f& d) const {
-    float4 o4 = ps.ray_o[slot], d4 = ps.ray_d[slot];
+    float4 o4 = ld_stream(&ps.ray_o[slot]), d4 = ld_stream(&ps.ray_d[slot]);
     o = {o4.x, o4.y, o4.z}, d = {d4.x, d4.y, d4.z};
   }
   __device__ __forceinline__ void store(int slot, const hit_record& h) const {
-    ps.hit[slot] = make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y));
+    st_stream(&ps.hit[slot], make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y)));
     int kind     = !h.hit ? 0 : (sc.shapes[sc.objects[h.object].shape].is_lines ? 2 : 1);
     queue_push(q.miss, q.count + 2, kind == 0, slot);
     queue_push(q.surface, q.count + 3, kind == 1, slot);
@@ -172,14 +183,17 @@ struct wavefront_io {
 // Closest hit for every slot of the active queue, then the slot id goes to the
 // miss / surface / hair queue.  Persistent warps, q.count[5] is the ray cursor.
 #ifndef YH_INTERSECT_BLOCKS
-#define YH_INTERSECT_BLOCKS 4
+#define YH_INTERSECT_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
   int            n = q.count[cur];
   unsigned long long nv = 0, pt = 0;
+  __shared__ int smem_park[kParkSlots * kTraceBlock];
+  __shared__ int smem_cold[kColdWords * kTraceBlock];
   wavefront_io   io{sc, ps, q, q.active[cur]};
-  trace_persistent(sc, io, n, q.count + 5, smem_stack + threadIdx.x, false, &nv, &pt);
+  trace_persistent(sc, io, n, q.count + 5, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x, false,
+      &nv, &pt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.stats + 0, (unsigned long long)n);
 #ifdef YH_TRAVERSAL_STATS
   atomicAdd(q.stats + 3, nv);
@@ -196,11 +210,11 @@ __global__ void __launch_bounds__(256) k_shade_miss(dev_scene sc, path_state ps,
     bool live = idx < n, again = false;
     int  slot = live ? q.miss[idx] : 0;
     if (live) {
-      float4    d = ps.ray_d[slot], w = ps.weight[slot], r = ps.radiance[slot];
+      float4    d = ld_stream(&ps.ray_d[slot]), w = ld_stream(&ps.weight[slot]), r = ld_stream(&ps.radiance[slot]);
       vec3f     radiance = vec3f{r.x, r.y, r.z} + vec3f{w.x, w.y, w.z} * eval_environment(sc, {d.x, d.y, d.z});
-      rng_state rng      = {ps.rng_state[slot], ps.rng_inc[slot]};
+      rng_state rng      = {ld_stream(&ps.rng_state[slot]), ld_stream(&ps.rng_inc[slot])};
       again              = finish_sample(ps, cam, tc, slot, radiance, w.w, rng);
-      ps.rng_state[slot] = rng.state;
+      st_stream(&ps.rng_state[slot], rng.state);
     }
     queue_push(q.active[next], q.count + next, again, slot);
   }
@@ -211,9 +225,9 @@ __global__ void __launch_bounds__(256) k_shade_miss(dev_scene sc, path_state ps,
 template <bool HAIR>
 __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_state& ps, const dev_camera& cam,
     const trace_consts& tc, int slot, trav_stack& st, unsigned int& light_rays) {
-  float4    o4 = ps.ray_o[slot], d4 = ps.ray_d[slot], w4 = ps.weight[slot], r4 = ps.radiance[slot];
-  int4      h4 = ps.hit[slot];
-  rng_state rng = {ps.rng_state[slot], ps.rng_inc[slot]};
+  float4    o4 = ld_stream(&ps.ray_o[slot]), d4 = ld_stream(&ps.ray_d[slot]), w4 = ld_stream(&ps.weight[slot]), r4 = ld_stream(&ps.radiance[slot]);
+  int4      h4 = ld_stream(&ps.hit[slot]);
+  rng_state rng = {ld_stream(&ps.rng_state[slot]), ld_stream(&ps.rng_inc[slot])};
   vec3f     ray_d = {d4.x, d4.y, d4.z}, weight = {w4.x, w4.y, w4.z}, radiance = {r4.x, r4.y, r4.z};
   int       bounce = __float_as_int(r4.w);
   int       object = h4.x, element = h4.y;
@@ -241,7 +255,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
   bool finished = false;
   if (opacity < 1 && rand1f(rng) >= opacity) {
     vec3f no = position + ray_d * 1e-2f;
-    ps.ray_o[slot] = make_float4(no.x, no.y, no.z, 0);  // same direction, bounce not counted
+    st_stream(&ps.ray_o[slot], make_float4(no.x, no.y, no.z, 0));  // same direction, bounce not counted
   } else {
     float alpha = 1.0f;
     radiance    = radiance + weight * emission;  // :1437
@@ -297,8 +311,8 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     float light_pdf = sample_lights_pdf(sc, position, incoming, st, light_rays);
     weight          = weight * (brdfcos / (0.5f * brdf_pdf + 0.5f * light_pdf));
 
-    ps.ray_o[slot] = make_float4(position.x, position.y, position.z, 0);
-    ps.ray_d[slot] = make_float4(incoming.x, incoming.y, incoming.z, 0);
+    st_stream(&ps.ray_o[slot], make_float4(position.x, position.y, position.z, 0));
+    st_stream(&ps.ray_d[slot], make_float4(incoming.x, incoming.y, incoming.z, 0));
 
     // :1500-1507, then the loop condition bounce < params.bounces
     if ((weight == vec3f{0, 0, 0}) || !isfinite3(weight)) finished = true;
@@ -315,11 +329,11 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
   if (finished) {
     again = finish_sample(ps, cam, tc, slot, radiance, w4.w, rng);
   } else {
-    ps.weight[slot]   = make_float4(weight.x, weight.y, weight.z, w4.w);
-    ps.radiance[slot] = make_float4(radiance.x, radiance.y, radiance.z, __int_as_float(bounce));
+    st_stream(&ps.weight[slot], make_float4(weight.x, weight.y, weight.z, w4.w));
+    st_stream(&ps.radiance[slot], make_float4(radiance.x, radiance.y, radiance.z, __int_as_float(bounce)));
     again             = true;
   }
-  ps.rng_state[slot] = rng.state;
+  st_stream(&ps.rng_state[slot], rng.state);
   return again;
 }
 
@@ -343,6 +357,31 @@ __global__ void __launch_bounds__(kTraceBlock) k_shade(dev_scene sc, path_state 
     queue_push(q.active[next], q.count + next, again, slot);
   }
   if (light_rays) atomicAdd(q.stats + 1, (unsigned long long)light_rays);
+}
+
+// Sort key of one queued ray: 30-bit Morton code of its origin inside the scene
+// bounds (rays that start close together walk the same part of the tree, so a
+// warp's node fetches share cache lines).  Entries past the queue's end get the
+// largest key.
+__device__ __forceinline__ unsigned spread10(unsigned v) {
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+__global__ void k_ray_keys(path_state ps, const int* queue, const int* count, int capacity, vec3f lo, vec3f inv,
+    unsigned* keys) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= capacity) return;
+  unsigned key = 0xffffffffu;
+  if (i < *count) {
+    float4 o = ld_stream(&ps.ray_o[queue[i]]);
+    auto   q = [](float v) { return (unsigned)fminf(fmaxf(v * 1024.0f, 0.0f), 1023.0f); };
+    key = (spread10(q((o.x - lo.x) * inv.x)) << 2) | (spread10(q((o.y - lo.y) * inv.y)) << 1) |
+          spread10(q((o.z - lo.z) * inv.z));
+  }
+  keys[i] = key;
 }
 
 __global__ void k_reset_counts(int* count, int next) {
@@ -373,10 +412,10 @@ __global__ void k_init_slots(path_state ps, const int* slot_pixel, int num_slots
   rng_state master = rng_skip(make_rng(1301081), (unsigned long long)px);
   uint32_t  r      = advance_rng(master) & 0x7fffffffu;  // % (1 << 31)
   rng_state rng    = make_rng(seed, (uint64_t)(r / 2 + 1));
-  ps.rng_state[slot] = rng.state;
-  ps.rng_inc[slot]   = rng.inc;
-  ps.pixel[slot]     = px;
-  ps.remaining[slot] = 0;
+  st_stream(&ps.rng_state[slot], rng.state);
+  st_stream(&ps.rng_inc[slot], rng.inc);
+  st_stream(&ps.pixel[slot], px);
+  st_stream(&ps.remaining[slot], 0);
 }
 
 __global__ void k_resolve(const float4* accum, const int* samples, float4* render, int n) {
@@ -409,8 +448,11 @@ struct batch_io {
 __global__ void __launch_bounds__(kTraceBlock) k_intersect_batch(dev_scene sc, const yh_ray* rays, int n,
     int find_any, yh_hit* hits, int* cursor) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
+  __shared__ int smem_park[kParkSlots * kTraceBlock];
+  __shared__ int smem_cold[kColdWords * kTraceBlock];
   batch_io       io{rays, hits};
-  trace_persistent(sc, io, n, cursor, smem_stack + threadIdx.x, find_any != 0, nullptr, nullptr);
+  trace_persistent(sc, io, n, cursor, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x,
+      find_any != 0, nullptr, nullptr);
 }
 
 }  // namespace yh
@@ -435,6 +477,9 @@ struct yh_state {
   dev_buffer<int4>               hit;
   dev_buffer<unsigned long long> rng_state, rng_inc, stats;
   dev_buffer<int>                remaining, pixel, samples, q_active0, q_active1, q_miss, q_surface, q_hair, q_count;
+  dev_buffer<unsigned> sort_keys0, sort_keys1;
+  dev_buffer<int>      sort_vals;
+  dev_buffer<char>     sort_tmp;
   int*            host_counts = nullptr;  // pinned
   cudaStream_t    stream      = nullptr;
   cudaEvent_t     ev_begin = nullptr, ev_end = nullptr;
@@ -610,6 +655,23 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
     return e;
   };
   bool    prof = st->profile;
+  const char* se = getenv("YH_SORT_RAYS");
+  bool    sort_rays = se && se[0] == '1';
+  vec3f   slo = {0, 0, 0}, sinv = {0, 0, 0};
+  if (sort_rays) {
+    bbox3f b = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+    for (auto& o : st->scene->objects) b.min = min3(b.min, o.bbox.min), b.max = max3(b.max, o.bbox.max);
+    slo  = b.min;
+    sinv = {1.0f / fmax_(b.max.x - b.min.x, 1e-20f), 1.0f / fmax_(b.max.y - b.min.y, 1e-20f), 1.0f / fmax_(b.max.z - b.min.z, 1e-20f)};
+    size_t cap = (size_t)st->num_slots, tb = 0;
+    if (st->sort_vals.count < cap) {
+      YH_CUDA(st->sort_keys0.alloc(cap));
+      YH_CUDA(st->sort_keys1.alloc(cap));
+      YH_CUDA(st->sort_vals.alloc(cap));
+      cub::DeviceRadixSort::SortPairs(nullptr, tb, st->sort_keys0.ptr, st->sort_keys1.ptr, st->q_active0.ptr, st->sort_vals.ptr, (int)cap, 0, 30, s);
+      YH_CUDA(st->sort_tmp.alloc(tb));
+    }
+  }
   int64_t min_iters = num_samples;  // every sample needs at least one iteration
   while (true) {
     int next = cur ^ 1;
@@ -623,6 +685,16 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
     if (prof) ev();
     launches += 5;
     iterations++;
+    if (sort_rays) {
+      // order the next iteration's rays by origin; the sorted ids land in the other queue buffer
+      int cap = st->num_slots;
+      k_ray_keys<<<(cap + 255) / 256, 256, 0, s>>>(ps, q.active[next], q.count + next, cap, slo, sinv, st->sort_keys0.ptr);
+      size_t tb = st->sort_tmp.bytes();
+      cub::DeviceRadixSort::SortPairs(st->sort_tmp.ptr, tb, st->sort_keys0.ptr, st->sort_keys1.ptr, q.active[next],
+          st->sort_vals.ptr, cap, 0, 30, s);
+      cudaMemcpyAsync(q.active[next], st->sort_vals.ptr, sizeof(int) * (size_t)cap, cudaMemcpyDeviceToDevice, s);
+      launches += 3;
+    }
     cur = next;
     if (iterations >= min_iters && (iterations % 4 == 0 || iterations < min_iters + 4)) {
       YH_CUDA(cudaMemcpyAsync(st->host_counts, q.count, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));

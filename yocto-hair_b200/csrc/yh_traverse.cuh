@@ -10,8 +10,11 @@
 
 namespace yh {
 
-constexpr int kStackShared = 24;  // entries per thread kept in shared memory
-constexpr int kStackLocal  = 72;  // overflow (LBVH chains can be deep)
+#ifndef YH_STACK_SHARED
+#define YH_STACK_SHARED 16
+#endif
+constexpr int kStackShared = YH_STACK_SHARED;  // entries per thread kept in shared memory
+constexpr int kStackLocal  = 96 - kStackShared;  // overflow (LBVH chains can be deep)
 constexpr int kTraceBlock  = 128;
 
 struct hit_record {
@@ -262,116 +265,164 @@ __device__ __forceinline__ hit_record intersect_scene(const dev_scene& sc, ray3f
 
 
 // --------------------------------------------------------------------------
-// Persistent closest-hit tracer: dynamic ray fetch, one step per iteration,
-// deferred exact tests.
+// Persistent closest-hit tracer: dynamic ray fetch, a pure node loop, parked
+// leaves.
 //
 // Traversal lengths of hair rays are wildly uneven (a ray that leaves the hair
 // volume ends after a handful of nodes, one that grazes a lock visits hundreds),
 // and so is the number of node steps between two leaves.  A warp that takes 32
-// rays and runs "all node steps, then all leaf tests" spends its node loop at
+// rays and alternates "all node steps / all leaf tests" runs its node loop at
 // ~7 of 32 lanes (ncu, profiles/r01_*).  Here
 //   * a warp keeps running and refills the lanes whose ray has finished from a
-//     global cursor;
-//   * every iteration each lane takes ONE step, a node step or the certain-miss
-//     test of one primitive (comparable cost), so no lane waits for another
-//     lane's run of node steps;
-//   * the reference's exact primitive test (long: two IEEE divisions, a square
-//     root) is deferred: a primitive that survives the certain-miss test is
-//     parked, and the warp runs the exact test when enough lanes have one parked
-//     or a lane cannot go on without it.
-// The exact tests may therefore run in another order than the tree is walked.
-// That is legal because the hit record does not depend on the order: the
-// closest t wins, and an exact tie goes to reference_visits_later().
+//     global cursor (finished lanes also write their hit records together);
+//   * the hot loop is ONE node step per lane per iteration; a leaf child whose
+//     box is hit is not tested on the spot but parked in a small per-lane list;
+//   * when enough lanes hold parked leaves (or too few can still walk), the warp
+//     tests them together: the certain-miss test first, then, for the few
+//     survivors, the reference's exact arithmetic.
+// Primitive tests therefore run later, and in another order, than a plain
+// depth-first walk would run them.  That is legal because the hit record does
+// not depend on the order: the closest t wins and an exact tie goes to
+// reference_visits_later(); a later test only means t_max shrinks later, i.e.
+// some extra node steps.
 //
 // IO supplies rays and consumes hit records:
 //   bool load(int index, int& handle, ray3f& world_ray)
 //   void reload(int handle, vec3f& o, vec3f& d)        (world origin / direction)
 //   void store(int handle, const hit_record&)
-constexpr int kRefillIdle = 8;  // refill once this many lanes of the warp are idle
-constexpr int kExactBatch = 8;  // run the parked exact tests once this many lanes have one
+constexpr int kRefillIdle = 8;   // refill once this many lanes of the warp have no ray
+constexpr int kParkSlots  = 4;   // parked leaves per lane
+constexpr int kParkLanes  = 12;  // test parked leaves once this many lanes hold some
+constexpr int kWalkLanes  = 12;  // ... or once fewer lanes than this can still take a node step
+
+// Per-lane state that the node loop does not touch lives in shared memory
+// (word w of thread t at cold[w * kTraceBlock + t]: conflict-free), so the hot
+// loop fits in few registers and more warps are resident to hide the latency
+// of the dependent node fetches.
+enum cold_word {
+  CW_OX, CW_OY, CW_OZ, CW_DX, CW_DY, CW_DZ,   // object-space ray
+  CW_HANDLE, CW_OBJ, CW_REF, CW_U, CW_V,      // ray handle, object index, best reference of this shape, its uv
+  CW_BOBJ, CW_BELEM, CW_BU, CW_BV, CW_BDIST,  // best hit over the objects closed so far
+  CW_FLAGS,                                    // bit 0 shape_hit, 1 best.hit, 2 is_lines, 4..6 dsign
+  CW_PRIMS_LO, CW_PRIMS_HI, CW_SHAPE_LO, CW_SHAPE_HI,
+  CW_COUNT
+};
+constexpr int kColdWords = CW_COUNT;
 
 template <class IO>
 __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, int n, int* cursor, int* smem_stack,
-    bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
+    int* smem_park, int* smem_cold, bool find_any, unsigned long long* nodes_visited,
+    unsigned long long* prims_tested) {
   const unsigned full = 0xffffffffu;
   const int      lane = threadIdx.x & 31;
   trav_stack     st;
   st.smem = smem_stack;
   st.sp   = 0;
-  bool  have = false, exhausted = false;
-  int   handle = 0, obj = -1, cur = kTraverseDone, leaf_k = 0;
-  int   parked = -1;       // reference index waiting for its exact test
-  bool  blocked = false;   // a second survivor turned up while one is parked
-  // ray in the space of the object being traversed
-  vec3f o = {0, 0, 0}, d = {0, 0, 1};
+  volatile int* cold = smem_cold;
+  auto cw  = [&](int w) -> volatile int& { return cold[w * kTraceBlock]; };
+  auto cwf = [&](int w) -> float { return __int_as_float(cold[w * kTraceBlock]); };
+  auto put = [&](int w, float v) { cold[w * kTraceBlock] = __float_as_int(v); };
+  auto ptr = [&](int w) -> const void* {
+    return (const void*)(((unsigned long long)(unsigned)cold[(w + 1) * kTraceBlock] << 32) | (unsigned)cold[w * kTraceBlock]);
+  };
+  auto put_ptr = [&](int w, const void* p) {
+    cold[w * kTraceBlock]       = (int)(unsigned)((unsigned long long)p);
+    cold[(w + 1) * kTraceBlock] = (int)(unsigned)((unsigned long long)p >> 32);
+  };
+  // registers of the node loop
+  bool  have = false, finished = false, exhausted = false;
+  int   cur = kTraverseDone, npark = 0;
   float tmin = 0, tmax = 0;
-  float idx = 0, idy = 0, idz = 0, ox = 0, oy = 0, oz = 0, uu = 0, mo = 0;
-  unsigned dsign = 0;
+  float idx = 0, idy = 0, idz = 0, ox = 0, oy = 0, oz = 0;
   const float4* __restrict__ nodes = nullptr;
-  const float4* __restrict__ prims = nullptr;
-  const dev_shape* shp = nullptr;
-  bool  is_lines = false, shape_hit = false;
-  int   ref = -1;
-  vec2f uv = {0, 0};
-  hit_record best;
-  best.object = -1, best.element = -1, best.uv = {0, 0}, best.distance = 0, best.hit = false;
 
   while (true) {
-    // ---- 1. refill idle lanes from the global cursor
+    // ---- 1. lanes without a ray: write finished records, fetch new rays
     unsigned idle = __ballot_sync(full, !have);
-    if (!exhausted && (__popc(idle) >= kRefillIdle)) {
-      int cnt = __popc(idle), base = 0;
-      if (lane == 0) base = atomicAdd(cursor, cnt);
-      base = __shfl_sync(full, base, 0);
-      if (!have) {
-        int   index = base + __popc(idle & ((1u << lane) - 1));
-        ray3f wr;
-        if (index < n && io.load(index, handle, wr)) {
-          have = true, obj = -1, cur = kTraverseDone, st.sp = 0, shape_hit = false, leaf_k = 0;
-          tmin = wr.tmin, tmax = wr.tmax;
-          best.object = -1, best.element = -1, best.uv = {0, 0}, best.distance = 0, best.hit = false;
-        }
+    if (__popc(idle) >= kRefillIdle || idle == full) {
+      if (finished) {
+        hit_record best;
+        best.object = cw(CW_BOBJ), best.element = cw(CW_BELEM), best.uv = {cwf(CW_BU), cwf(CW_BV)};
+        best.distance = cwf(CW_BDIST), best.hit = (cw(CW_FLAGS) & 2) != 0;
+        io.store(cw(CW_HANDLE), best);
+        finished = false;
       }
-      exhausted = base + cnt >= n;
-      idle      = __ballot_sync(full, !have);
-    }
-    if (idle == full) {
-      if (exhausted) break;
-      continue;
+      if (!exhausted) {
+        int cnt = __popc(idle), base = 0;
+        if (lane == 0) base = atomicAdd(cursor, cnt);
+        base = __shfl_sync(full, base, 0);
+        if (!have) {
+          int   index = base + __popc(idle & ((1u << lane) - 1));
+          ray3f wr;
+          int   handle;
+          if (index < n && io.load(index, handle, wr)) {
+            have = true, cur = kTraverseDone, st.sp = 0, npark = 0;
+            tmin = wr.tmin, tmax = wr.tmax;
+            cw(CW_HANDLE) = handle, cw(CW_OBJ) = -1, cw(CW_FLAGS) = 0;
+            cw(CW_BOBJ) = -1, cw(CW_BELEM) = -1, put(CW_BU, 0), put(CW_BV, 0), put(CW_BDIST, 0);
+          }
+        }
+        exhausted = base + cnt >= n;
+        idle      = __ballot_sync(full, !have);
+      }
+      if (idle == full) break;  // nothing in flight and nothing left to fetch
     }
 
-    // ---- 2. parked exact tests (the reference's own arithmetic)
+    // ---- 2. parked leaves
     {
-      bool     pending = parked >= 0;
-      unsigned pm = __ballot_sync(full, pending);
-      unsigned um = __ballot_sync(full, pending && (blocked || cur == kTraverseDone));
-      if (pending && (um != 0 || __popc(pm) >= kExactBatch)) {
+      bool     can_walk = have && cur >= 0 && npark <= kParkSlots - 2;
+      unsigned pm = __ballot_sync(full, npark > 0);
+      unsigned wm = __ballot_sync(full, can_walk);
+      if (npark > 0 && (__popc(pm) >= kParkLanes || __popc(wm) < kWalkLanes)) {
+        vec3f o = {cwf(CW_OX), cwf(CW_OY), cwf(CW_OZ)}, d = {cwf(CW_DX), cwf(CW_DY), cwf(CW_DZ)};
+        float uu = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
+        float mo = fabsf(o.x) + fabsf(o.y) + fabsf(o.z);
+        int   flags = cw(CW_FLAGS), ref = cw(CW_REF);
+        bool  shape_hit = flags & 1, is_lines = (flags & 4) != 0;
+        unsigned dsign = (flags >> 4) & 7;
+        vec2f uv = {cwf(CW_U), cwf(CW_V)};
+        const float4* __restrict__ prims = (const float4*)ptr(CW_PRIMS_LO);
+        const dev_shape* shp = (const dev_shape*)ptr(CW_SHAPE_LO);
         ray3f ray = {o, d, tmin, tmax};
-        vec2f uvc;
-        float tc;
-        bool  got;
-        if (is_lines) {
-          const float4 a = __ldg(prims + 2 * (size_t)parked), b = __ldg(prims + 2 * (size_t)parked + 1);
-          got = intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uvc, tc);
-        } else {
-          const float4 a = __ldg(prims + 3 * (size_t)parked), b = __ldg(prims + 3 * (size_t)parked + 1),
-                       c = __ldg(prims + 3 * (size_t)parked + 2);
-          got = intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uvc, tc);
+        for (int e = 0; e < npark; e++) {
+          int code = ~smem_park[e * kTraceBlock], first = code >> 3, count = (code & 7) + 1;
+          for (int k = 0; k < count; k++) {
+            int   r = first + k;
+            vec2f uvc;
+            float tc;
+            bool  got;
+            YH_STAT(if (prims_tested)(*prims_tested)++;)
+            if (is_lines) {
+              const float4 a = __ldg(prims + 2 * (size_t)r), b = __ldg(prims + 2 * (size_t)r + 1);
+              if (line_certain_miss(o, d, uu, mo, a, b)) continue;
+              got = intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uvc, tc);
+            } else {
+              const float4 a = __ldg(prims + 3 * (size_t)r), b = __ldg(prims + 3 * (size_t)r + 1),
+                           c = __ldg(prims + 3 * (size_t)r + 2);
+              got = intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uvc, tc);
+            }
+            if (got && !(shape_hit && tc == ray.tmax &&
+                           !reference_visits_later(*shp, __ldg(shp->ref_elem + ref), __ldg(shp->ref_elem + r), dsign)))
+              shape_hit = true, ref = r, uv = uvc, ray.tmax = tc;
+          }
         }
-        if (got && !(shape_hit && tc == tmax &&
-                       !reference_visits_later(*shp, __ldg(shp->ref_elem + ref), __ldg(shp->ref_elem + parked), dsign))) {
-          shape_hit = true, ref = parked, uv = uvc, tmax = tc;
-          if (find_any) st.sp = 0, cur = kTraverseDone, leaf_k = 0;
+        tmax  = ray.tmax;
+        npark = 0;
+        if (shape_hit) {
+          cw(CW_FLAGS) = flags | 1, cw(CW_REF) = ref, put(CW_U, uv.x), put(CW_V, uv.y);
+          if (find_any) st.sp = 0, cur = kTraverseDone;
         }
-        parked = -1, blocked = false;
       }
     }
 
     // ---- 3. lanes between shapes: close the finished one, open the next object
-    if (have && cur == kTraverseDone) {
-      if (shape_hit) {
-        best.hit = true, best.object = obj, best.element = __ldg(shp->ref_elem + ref), best.uv = uv, best.distance = tmax;
-        shape_hit = false;
+    if (have && cur == kTraverseDone && npark == 0) {
+      int flags = cw(CW_FLAGS), obj = cw(CW_OBJ), handle = cw(CW_HANDLE);
+      if (flags & 1) {
+        const dev_shape* shp = (const dev_shape*)ptr(CW_SHAPE_LO);
+        cw(CW_BOBJ) = obj, cw(CW_BELEM) = __ldg(shp->ref_elem + cw(CW_REF));
+        cw(CW_BU) = cw(CW_U), cw(CW_BV) = cw(CW_V), put(CW_BDIST, tmax);
+        flags = (flags & ~1) | 2;
         if (find_any) obj = sc.num_objects;
       }
       vec3f wo, wd;
@@ -383,38 +434,42 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         if (!hits_box(wr, ob.bbox)) continue;
         const dev_shape& sh = sc.shapes[ob.shape];
         if (sh.num_refs == 0) continue;
-        o = transform_point(ob.inv_frame, wo), d = transform_vector(ob.inv_frame, wd);
-        mo = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
+        vec3f o = transform_point(ob.inv_frame, wo), d = transform_vector(ob.inv_frame, wd);
+        float mo = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
         if (!(mo <= 4.0f * sh.scale)) {  // far origin: whole shape at once, out of line (rare)
           ray3f r = {o, d, tmin, tmax};
           int   rr = -1;
           vec2f ruv;
           if (intersect_shape_far<false>(sh, r, st, rr, ruv, find_any, nodes_visited, prims_tested)) {
-            best.hit = true, best.object = obj, best.element = __ldg(sh.ref_elem + rr), best.uv = ruv;
-            best.distance = tmax = r.tmax;
+            cw(CW_BOBJ) = obj, cw(CW_BELEM) = __ldg(sh.ref_elem + rr), put(CW_BU, ruv.x), put(CW_BV, ruv.y);
+            put(CW_BDIST, r.tmax);
+            tmax = r.tmax, flags |= 2;
             if (find_any) break;
           }
           continue;
         }
         auto safe = [](float v) { return fabsf(v) < 1e-20f ? copysignf(1e-20f, v) : v; };
-        dsign = ((1.0f / d.x) < 0 ? 1u : 0u) | ((1.0f / d.y) < 0 ? 2u : 0u) | ((1.0f / d.z) < 0 ? 4u : 0u);
+        unsigned dsign = ((1.0f / d.x) < 0 ? 1u : 0u) | ((1.0f / d.y) < 0 ? 2u : 0u) | ((1.0f / d.z) < 0 ? 4u : 0u);
         idx = 1.0f / safe(d.x), idy = 1.0f / safe(d.y), idz = 1.0f / safe(d.z);
         ox = -o.x * idx, oy = -o.y * idy, oz = -o.z * idz;
-        uu = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
-        mo = fabsf(o.x) + fabsf(o.y) + fabsf(o.z);
-        nodes = sh.nodes, prims = sh.prims, shp = &sh, is_lines = sh.is_lines != 0;
-        cur = sh.root, ref = -1, leaf_k = 0;
+        put(CW_OX, o.x), put(CW_OY, o.y), put(CW_OZ, o.z), put(CW_DX, d.x), put(CW_DY, d.y), put(CW_DZ, d.z);
+        put_ptr(CW_PRIMS_LO, sh.prims), put_ptr(CW_SHAPE_LO, &sh);
+        flags = (flags & 3) | (sh.is_lines ? 4 : 0) | (int)(dsign << 4);
+        nodes = sh.nodes;
+        cur   = sh.root;
+        cw(CW_REF) = -1;
+        if (cur < 0) {  // the whole shape is one leaf
+          smem_park[0] = cur, npark = 1, cur = kTraverseDone;
+        }
         opened = true;
         break;
       }
-      if (!opened) {
-        io.store(handle, best);
-        have = false;
-      }
+      cw(CW_FLAGS) = flags, cw(CW_OBJ) = obj;
+      if (!opened) have = false, finished = true;
     }
 
-    // ---- 4. one step per lane
-    if (cur >= 0) {
+    // ---- 4. one node step; leaf children whose box is hit are parked
+    if (cur >= 0 && npark <= kParkSlots - 2) {
       const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1),
                    n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
       YH_STAT(if (nodes_visited)(*nodes_visited)++;)
@@ -430,6 +485,8 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), tmax));
       bool h0 = tn0 * 0.9999995f <= tf0 * 1.0000005f, h1 = tn1 * 0.9999995f <= tf1 * 1.0000005f;
       int  ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
+      if (h0 && ch0 < 0) smem_park[npark++ * kTraceBlock] = ch0, h0 = false;
+      if (h1 && ch1 < 0) smem_park[npark++ * kTraceBlock] = ch1, h1 = false;
       if (h0 && h1) {
         bool swap = tn1 < tn0;
         st.push(swap ? ch0 : ch1);
@@ -440,24 +497,6 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         cur = ch1;
       } else {
         cur = st.sp == 0 ? kTraverseDone : st.pop();
-      }
-    } else if (cur != kTraverseDone) {
-      int  code = ~cur, first = code >> 3, count = (code & 7) + 1;
-      int  r    = first + leaf_k;
-      bool survivor = true;
-      if (is_lines) {
-        const float4 a = __ldg(prims + 2 * (size_t)r), b = __ldg(prims + 2 * (size_t)r + 1);
-        survivor = !line_certain_miss(o, d, uu, mo, a, b);
-      }
-      if (survivor && parked >= 0) {
-        blocked = true;  // step 2 empties the slot, then this primitive is looked at again
-      } else {
-        YH_STAT(if (prims_tested)(*prims_tested)++;)
-        if (survivor) parked = r;
-        if (++leaf_k == count) {
-          leaf_k = 0;
-          cur    = st.sp == 0 ? kTraverseDone : st.pop();
-        }
       }
     }
   }
