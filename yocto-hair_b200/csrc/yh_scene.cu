@@ -47,9 +47,10 @@ __global__ void k_count_refs(int is_lines, const int* elems, const float* pos, c
 // exact primitive test (the hit point of an accepted intersection always lies
 // inside the padded box of the sub-span that contains its segment parameter).
 // `scale` = largest |coordinate| of the shape: the traversal's fused slab test
-// needs the pad to dominate 6e-8 |ray origin| (yh_traverse.cuh).
+// needs the pad to dominate ~1e-6 * scale (rounding of -o/d for |o| <= 4 scale, of
+// the grid decode, and of the quantisation itself; yh_traverse.cuh).
 __device__ __forceinline__ void pad_box(vec3f& lo, vec3f& hi, float scale) {
-  float eps = 4e-7f * scale + 1e-30f;
+  float eps = 2e-6f * scale + 1e-30f;
   lo        = lo - eps;
   hi        = hi + eps;
 }
@@ -179,60 +180,66 @@ __global__ void k_refit(int n, const int* sorted_ref, const ref_bounds* refs, co
   }
 }
 
-__global__ void k_keep_flags(int n_inner, const int* first, const int* last, int leaf_max, int* keep) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_inner) return;
-  keep[i] = (last[i] - first[i] + 1) > leaf_max ? 1 : 0;
+// Quantises one box onto the shape's 16-bit grid, outwards.
+__device__ __forceinline__ void quantise(const ref_bounds& b, const vec3f& g, const vec3f& inv_s, unsigned q[6]) {
+  auto dn = [](float v) { return (unsigned)fminf(fmaxf(floorf(v), 0.0f), 65535.0f); };
+  auto up = [](float v) { return (unsigned)fminf(fmaxf(ceilf(v), 0.0f), 65535.0f); };
+  q[0] = dn((b.lo.x - g.x) * inv_s.x), q[1] = dn((b.lo.y - g.y) * inv_s.y), q[2] = dn((b.lo.z - g.z) * inv_s.z);
+  q[3] = up((b.hi.x - g.x) * inv_s.x), q[4] = up((b.hi.y - g.y) * inv_s.y), q[5] = up((b.hi.z - g.z) * inv_s.z);
 }
 
-__device__ __forceinline__ int leaf_code(int first_ref, int count) { return ~((first_ref << 3) | (count - 1)); }
-
-// Writes the final 64-byte nodes (children's boxes inside the parent).
-__global__ void k_emit_nodes(int n_inner, const int* keep, const int* new_index, const int* left,
-    const int* right, const int* first, const int* last, const int* sorted_ref, const ref_bounds* refs,
-    const ref_bounds* node_box, float4* nodes) {
+// Writes the packed tree (yh_scene.cuh "shape BVH"): one thread per inner node
+// of the radix tree emits its own 32-byte record at the slot its parent
+// reserved for it, and the primitive records of its leaf children next to it.
+__global__ void k_emit_packed(int is_lines, int n_inner, const int* left, const int* right, const int* parent_inner,
+    const int* sorted_ref, const ref_bounds* refs, const ref_bounds* node_box, const int* ref_prim, const int* elems,
+    const float* pos, const float* radius, vec3f g, vec3f inv_s, uint4* slots, int* slot_elem) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_inner || !keep[i]) return;
-  int        child[2] = {left[i], right[i]};
-  ref_bounds box[2];
-  int        code[2];
+  if (i >= n_inner) return;
+  int my_slot = 0;
+  if (i > 0) {
+    int p   = parent_inner[i];
+    my_slot = 1 + 2 * p + (right[p] == i ? 1 : 0);
+  }
+  int      child[2] = {left[i], right[i]};
+  unsigned q[2][6];
+  unsigned flags = 0;
   for (int c = 0; c < 2; c++) {
     int ch = child[c];
     if (ch < 0) {
-      box[c]  = refs[sorted_ref[~ch]];
-      code[c] = leaf_code(~ch, 1);
+      int sr = sorted_ref[~ch];
+      quantise(refs[sr], g, inv_s, q[c]);
+      flags |= 1u << c;
+      // the leaf child is the primitive itself
+      int    prim = ref_prim[sr];
+      size_t slot = (size_t)(1 + 2 * i + c);
+      if (is_lines) {
+        int a = elems[2 * prim], b = elems[2 * prim + 1];
+        slots[2 * slot]     = make_uint4(__float_as_uint(pos[3 * a]), __float_as_uint(pos[3 * a + 1]), __float_as_uint(pos[3 * a + 2]), __float_as_uint(radius[a]));
+        slots[2 * slot + 1] = make_uint4(__float_as_uint(pos[3 * b]), __float_as_uint(pos[3 * b + 1]), __float_as_uint(pos[3 * b + 2]), __float_as_uint(radius[b]));
+      } else {
+        slots[2 * slot]     = make_uint4((unsigned)prim, 0, 0, 0);
+        slots[2 * slot + 1] = make_uint4(0, 0, 0, 0);
+      }
+      slot_elem[slot] = prim;
     } else {
-      box[c] = node_box[ch];
-      code[c] = keep[ch] ? new_index[ch] : leaf_code(first[ch], last[ch] - first[ch] + 1);
+      quantise(node_box[ch], g, inv_s, q[c]);
     }
   }
-  float4* o = nodes + 4 * (size_t)new_index[i];
-  o[0]      = make_float4(box[0].lo.x, box[0].lo.y, box[0].lo.z, box[0].hi.x);
-  o[1]      = make_float4(box[0].hi.y, box[0].hi.z, box[1].lo.x, box[1].lo.y);
-  o[2]      = make_float4(box[1].lo.z, box[1].hi.x, box[1].hi.y, box[1].hi.z);
-  o[3]      = make_float4(__int_as_float(code[0]), __int_as_float(code[1]), 0, 0);
+  slots[2 * (size_t)my_slot] = make_uint4(q[0][0] | (q[0][1] << 16), q[0][2] | (q[0][3] << 16), q[0][4] | (q[0][5] << 16),
+      q[1][0] | (q[1][1] << 16));
+  slots[2 * (size_t)my_slot + 1] = make_uint4(q[1][2] | (q[1][3] << 16), q[1][4] | (q[1][5] << 16), (unsigned)(1 + 2 * i), flags);
 }
 
-// Leaf-ordered primitive records.
-__global__ void k_emit_prims(int is_lines, int n_refs, const int* sorted_ref, const int* ref_prim,
-    const int* elems, const float* pos, const float* radius, float4* prims, int* ref_elem) {
+// Triangle vertices by element (48 bytes): leaf slots of triangle shapes hold the element id.
+__global__ void k_emit_triangles(int n, const int* elems, const float* pos, float4* tris) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_refs) return;
-  int prim = ref_prim[sorted_ref[j]];
-  if (is_lines) {
-    int   a = elems[2 * prim], b = elems[2 * prim + 1];
-    vec3f p0 = ldv(pos, a), p1 = ldv(pos, b);
-    prims[2 * (size_t)j]     = make_float4(p0.x, p0.y, p0.z, radius[a]);
-    prims[2 * (size_t)j + 1] = make_float4(p1.x, p1.y, p1.z, radius[b]);
-    ref_elem[j]              = prim;
-  } else {
-    int   a = elems[3 * prim], b = elems[3 * prim + 1], c = elems[3 * prim + 2];
-    vec3f p0 = ldv(pos, a), p1 = ldv(pos, b), p2 = ldv(pos, c);
-    prims[3 * (size_t)j]     = make_float4(p0.x, p0.y, p0.z, __int_as_float(prim));
-    prims[3 * (size_t)j + 1] = make_float4(p1.x, p1.y, p1.z, 0);
-    prims[3 * (size_t)j + 2] = make_float4(p2.x, p2.y, p2.z, 0);
-    ref_elem[j]              = prim;
-  }
+  if (j >= n) return;
+  int   a = elems[3 * j], b = elems[3 * j + 1], c = elems[3 * j + 2];
+  vec3f p0 = ldv(pos, a), p1 = ldv(pos, b), p2 = ldv(pos, c);
+  tris[3 * (size_t)j]     = make_float4(p0.x, p0.y, p0.z, 0);
+  tris[3 * (size_t)j + 1] = make_float4(p1.x, p1.y, p1.z, 0);
+  tris[3 * (size_t)j + 2] = make_float4(p2.x, p2.y, p2.z, 0);
 }
 
 // ------------------------------------------------------------ host driver --
@@ -304,10 +311,10 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
   for (int i = 0; i < n; i++) ref_pos[prims[i].primitive] = i;
 }
 
-static yh_status build_shape_bvh(host_shape& sh, int max_split, int leaf_max) {
+static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   bool lines = sh.is_lines();
   int  n     = sh.num_elems();
-  sh.root = 0, sh.num_refs = 0, sh.num_nodes = 0;
+  sh.root_leaf = 0, sh.num_refs = 0, sh.num_nodes = 0;
   sh.root_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   if (n == 0) return YH_OK;
   {
@@ -369,28 +376,47 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int leaf_max) {
   YH_CUDA(tmp.alloc(tmp_bytes));
   YH_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys_in.ptr, keys_out.ptr, ids_in.ptr, ids_out.ptr, R, 0, 63));
 
-  // leaf-ordered primitive records
-  YH_CUDA(sh.d_prims.alloc((size_t)R * (lines ? 2 : 3)));
-  YH_CUDA(sh.d_ref_elem.alloc(R));
-  k_emit_prims<<<G(R), B>>>(lines, R, ids_out.ptr, ref_prim.ptr, sh.d_elems.ptr, sh.d_positions.ptr,
-      sh.d_radius.ptr, sh.d_prims.ptr, sh.d_ref_elem.ptr);
-  YH_CUDA(cudaGetLastError());
-  sh.num_refs = R;
+  // grid of the packed boxes: 16 bits per axis over the (padded) bounds of the shape
+  float pad  = 2e-6f * sh.scale + 1e-30f;
+  vec3f glo  = cmin - (rmax + pad), ghi = cmax + (rmax + pad);
+  auto  step = [](float lo, float hi) { return fmax_((hi - lo) / 65534.0f, 1e-30f); };
+  sh.grid_origin = glo;
+  sh.grid_step   = {step(glo.x, ghi.x), step(glo.y, ghi.y), step(glo.z, ghi.z)};
+  vec3f inv_step = {1.0f / sh.grid_step.x, 1.0f / sh.grid_step.y, 1.0f / sh.grid_step.z};
+  sh.num_refs    = R;
+  if (!lines) {
+    YH_CUDA(sh.d_prims.alloc((size_t)n * 3));
+    k_emit_triangles<<<G(n), B>>>(n, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_prims.ptr);
+    YH_CUDA(cudaGetLastError());
+  }
+  size_t num_slots = 2 * (size_t)R - 1;
+  YH_CUDA(sh.d_slots.alloc(2 * num_slots));
+  YH_CUDA(sh.d_slot_elem.alloc(num_slots));
+  YH_CUDA(cudaMemset(sh.d_slot_elem.ptr, 0xff, sh.d_slot_elem.bytes()));
+  sh.num_nodes = (int)num_slots;
 
-  if (R <= leaf_max) {  // the whole shape is one leaf
-    sh.root = ~((0 << 3) | (R - 1));
-    std::vector<ref_bounds> h(R);
-    YH_CUDA(cudaMemcpy(h.data(), refs.ptr, sizeof(ref_bounds) * R, cudaMemcpyDeviceToHost));
-    for (auto& r : h) {
-      sh.root_bbox.min = min3(sh.root_bbox.min, vec3f{r.lo.x, r.lo.y, r.lo.z});
-      sh.root_bbox.max = max3(sh.root_bbox.max, vec3f{r.hi.x, r.hi.y, r.hi.z});
+  if (R == 1) {  // the whole shape is one leaf: slot 0 is the primitive
+    std::vector<ref_bounds> h(1);
+    YH_CUDA(cudaMemcpy(h.data(), refs.ptr, sizeof(ref_bounds), cudaMemcpyDeviceToHost));
+    sh.root_bbox = {{h[0].lo.x, h[0].lo.y, h[0].lo.z}, {h[0].hi.x, h[0].hi.y, h[0].hi.z}};
+    sh.root_leaf = 1;
+    uint4 rec[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if (lines) {
+      int a = sh.lines[0], b = sh.lines[1];
+      float v[8] = {sh.positions[3 * a], sh.positions[3 * a + 1], sh.positions[3 * a + 2], sh.radius[a],
+          sh.positions[3 * b], sh.positions[3 * b + 1], sh.positions[3 * b + 2], sh.radius[b]};
+      memcpy(rec, v, 32);
     }
+    int zero = 0;
+    YH_CUDA(cudaMemcpy(sh.d_slots.ptr, rec, 32, cudaMemcpyHostToDevice));
+    YH_CUDA(cudaMemcpy(sh.d_slot_elem.ptr, &zero, 4, cudaMemcpyHostToDevice));
     return YH_OK;
   }
+  sh.root_leaf = 0;
 
   // hierarchy + bounds
   int             ni = R - 1;
-  dev_buffer<int> left, right, first, last, parent_inner, parent_leaf, flags, keep, new_index;
+  dev_buffer<int> left, right, first, last, parent_inner, parent_leaf, flags;
   dev_buffer<ref_bounds> node_box;
   YH_CUDA(left.alloc(ni));
   YH_CUDA(right.alloc(ni));
@@ -399,33 +425,19 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int leaf_max) {
   YH_CUDA(parent_inner.alloc(ni));
   YH_CUDA(parent_leaf.alloc(R));
   YH_CUDA(flags.alloc(ni));
-  YH_CUDA(keep.alloc(ni));
-  YH_CUDA(new_index.alloc(ni));
   YH_CUDA(node_box.alloc(ni));
   YH_CUDA(cudaMemset(flags.ptr, 0, flags.bytes()));
   k_hierarchy<<<G(ni), B>>>(keys_out.ptr, R, left.ptr, right.ptr, first.ptr, last.ptr, parent_inner.ptr, parent_leaf.ptr);
   YH_CUDA(cudaGetLastError());
   k_refit<<<G(R), B>>>(R, ids_out.ptr, refs.ptr, left.ptr, right.ptr, parent_inner.ptr, parent_leaf.ptr, flags.ptr, node_box.ptr);
   YH_CUDA(cudaGetLastError());
-  k_keep_flags<<<G(ni), B>>>(ni, first.ptr, last.ptr, leaf_max, keep.ptr);
-  YH_CUDA(cudaGetLastError());
-  tmp_bytes = 0;
-  YH_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep.ptr, new_index.ptr, ni));
-  YH_CUDA(tmp.alloc(tmp_bytes));
-  YH_CUDA(cub::DeviceScan::ExclusiveSum(tmp.ptr, tmp_bytes, keep.ptr, new_index.ptr, ni));
-  int k_last = 0, i_last = 0;
-  YH_CUDA(cudaMemcpy(&k_last, keep.ptr + (ni - 1), 4, cudaMemcpyDeviceToHost));
-  YH_CUDA(cudaMemcpy(&i_last, new_index.ptr + (ni - 1), 4, cudaMemcpyDeviceToHost));
-  int kept = k_last + i_last;  // node 0 (the root) is kept because R > leaf_max, and gets index 0
-  YH_CUDA(sh.d_nodes.alloc((size_t)kept * 4));
-  k_emit_nodes<<<G(ni), B>>>(ni, keep.ptr, new_index.ptr, left.ptr, right.ptr, first.ptr, last.ptr,
-      ids_out.ptr, refs.ptr, node_box.ptr, sh.d_nodes.ptr);
+  k_emit_packed<<<G(ni), B>>>(lines, ni, left.ptr, right.ptr, parent_inner.ptr, ids_out.ptr, refs.ptr, node_box.ptr,
+      ref_prim.ptr, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, sh.grid_origin, inv_step, sh.d_slots.ptr,
+      sh.d_slot_elem.ptr);
   YH_CUDA(cudaGetLastError());
   ref_bounds rb;
   YH_CUDA(cudaMemcpy(&rb, node_box.ptr, sizeof(rb), cudaMemcpyDeviceToHost));
   sh.root_bbox = {{rb.lo.x, rb.lo.y, rb.lo.z}, {rb.hi.x, rb.hi.y, rb.hi.z}};
-  sh.root      = 0;
-  sh.num_nodes = kept;
   YH_CUDA(cudaDeviceSynchronize());
   return YH_OK;
 }
@@ -475,10 +487,10 @@ static yh_status upload_tables(yh_scene* sc) {
   std::vector<dev_shape> ds;
   for (auto s : sc->shapes) {
     dev_shape d{};
-    d.nodes = s->d_nodes.ptr, d.prims = s->d_prims.ptr, d.ref_elem = s->d_ref_elem.ptr;
+    d.slots = s->d_slots.ptr, d.tris = s->d_prims.ptr, d.slot_elem = s->d_slot_elem.ptr;
     d.ref_pos = s->d_ref_pos.ptr, d.tie_nodes = s->d_tie_nodes.ptr, d.num_tie_nodes = (int)s->d_tie_nodes.count;
-    d.root = s->root, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0;
-    d.scale = s->scale;
+    d.root_leaf = s->root_leaf, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0;
+    d.scale = s->scale, d.grid_origin = s->grid_origin, d.grid_step = s->grid_step;
     d.has_normals = s->normals.empty() ? 0 : 1;
     d.positions = s->d_positions.ptr, d.normals = s->d_normals.ptr, d.elems = s->d_elems.ptr;
     d.num_elems = s->num_elems();
@@ -601,17 +613,15 @@ yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
   if (!sc) return fail(YH_ERR_INVALID, "yh_scene_init_bvh: scene is null");
   int max_split = params && params->max_split > 0 ? params->max_split : kDefaultSplit;
   if (max_split > 8) max_split = 8;
-  int leaf_max = params && params->leaf_size > 0 ? params->leaf_size : kLeafMax;
-  if (leaf_max > 8) leaf_max = 8;  // 3 bits of the leaf code
   sc->stats = yh_bvh_stats{};
   for (auto s : sc->shapes) {
-    yh_status st = build_shape_bvh(*s, max_split, leaf_max);
+    yh_status st = build_shape_bvh(*s, max_split);
     if (st != YH_OK) return st;
     sc->stats.num_primitives += s->num_elems();
     sc->stats.num_references += s->num_refs;
     sc->stats.num_nodes += s->num_nodes;
-    sc->stats.node_bytes += (int64_t)s->d_nodes.bytes();
-    sc->stats.prim_bytes += (int64_t)s->d_prims.bytes() + (int64_t)s->d_ref_elem.bytes();
+    sc->stats.node_bytes += (int64_t)s->d_slots.bytes();
+    sc->stats.prim_bytes += (int64_t)s->d_prims.bytes() + (int64_t)s->d_slot_elem.bytes();
   }
   for (auto& o : sc->objects) {
     auto s = sc->shapes[o.shape];

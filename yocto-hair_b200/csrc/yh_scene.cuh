@@ -1,18 +1,23 @@
 // Device-side scene layout (what lives in HBM) and its host owner.
 //
-//   shape BVH    : binary LBVH, 64-byte nodes that hold BOTH children's boxes
-//                  (4 x float4, one 128-bit load each):
-//                    n0 = c0.min.xyz, c0.max.x     n1 = c0.max.yz, c1.min.xy
-//                    n2 = c1.min.z,  c1.max.xyz    n3 = int child0, child1, -, -
-//                  child >= 0: index of an inner node; child < 0: leaf packed as
-//                  ~((first_ref << 3) | (count - 1)), count <= 8.
-//   references   : leaf-ordered primitive records, so one leaf is one
-//                  contiguous run of 32-byte (line) / 48-byte (triangle) records:
-//                    line     = {p0.xyz, r0}, {p1.xyz, r1}
-//                    triangle = {p0.xyz, element}, {p1.xyz, -}, {p2.xyz, -}
-//                  a long segment may be referenced by several leaves (each
-//                  reference bounds a sub-span of it) — the test always runs on
-//                  the whole segment, so hit records do not depend on splitting.
+//   shape BVH    : binary LBVH packed into 32-byte SLOTS, one 256-bit load each
+//                  (LDG.E.256 on sm_100a).  A slot is either
+//                    an inner node: the boxes of BOTH children on the shape's 16-bit
+//                      grid (box = grid_origin + q * grid_step, rounded outwards)
+//                        w0 = c0.lo.x | c0.lo.y << 16   w1 = c0.lo.z | c0.hi.x << 16
+//                        w2 = c0.hi.y | c0.hi.z << 16   w3 = c1.lo.x | c1.lo.y << 16
+//                        w4 = c1.lo.z | c1.hi.x << 16   w5 = c1.hi.y | c1.hi.z << 16
+//                        w6 = slot of child 0 (child 1 is the next slot)
+//                        w7 = bit 0: child 0 is a leaf, bit 1: child 1 is a leaf
+//                    or a leaf = ONE primitive reference:
+//                        line     : {p0.xyz, r0, p1.xyz, r1}  (the segment itself)
+//                        triangle : w0 = element id (vertices in tris[3 * id ..])
+//                  Siblings share a 64-byte line, a leaf needs no second fetch, and
+//                  the whole tree of 1M segments is 64-106 MB instead of 160 MB.
+//                  slot_elem[slot] = element id of a leaf slot.  A long segment may be
+//                  referenced by several leaves (each reference bounds a sub-span of
+//                  it) — the test always runs on the whole segment, so hit records
+//                  do not depend on splitting.
 //   tie order    : when two primitives of one shape are hit at EXACTLY the same
 //                  t, the reference keeps the one its own BVH visits last
 //                  (intersect_line accepts t == tmax, yocto_math.h:3450).  So
@@ -31,21 +36,20 @@
 
 namespace yh {
 
-constexpr int kLeafMax    = 1;  // default leaf size of our tree (yh_bvh_params::leaf_size): the parent's
-                                 // box test is then the primitive's own box test (yh_traverse.cuh)
-constexpr int kDefaultSplit = 4; // default yh_bvh_params::max_split
+constexpr int kDefaultSplit = 4;  // default yh_bvh_params::max_split
 constexpr int kRefLeafMax = 4;  // the reference's bvh_max_prims (yocto_pathtrace.cpp:598)
 
 struct dev_shape {
-  const float4* nodes;
-  const float4* prims;
-  const int*    ref_elem;   // element id of each reference
+  const uint4*  slots;      // 2 uint4 per slot
+  const float4* tris;       // triangle shapes: 3 float4 per element
+  const int*    slot_elem;  // element id of each leaf slot
   const int*    ref_pos;    // element id -> position in the reference's leaf order
   const int4*   tie_nodes;  // internal nodes of the reference's tree: mid, axis, left, right
   int           num_tie_nodes;
-  int           root;       // child encoding of the whole tree (leaf if < 0); 0 refs -> empty
+  int           root_leaf;  // the tree is a single leaf (slot 0)
+  vec3f         grid_origin, grid_step;
   int           num_refs;
-  float         scale;      // largest |coordinate| of the shape: boxes are padded by 4e-7 * scale
+  float         scale;      // largest |coordinate| of the shape: boxes are padded by 2e-6 * scale
   int           is_lines;
   int           has_normals;
   const float*  positions;  // xyz
@@ -108,11 +112,13 @@ struct host_shape {
   std::vector<int>   lines, triangles;
   dev_buffer<float>  d_positions, d_normals, d_radius;
   dev_buffer<int>    d_elems;
-  dev_buffer<float4> d_nodes, d_prims;
-  dev_buffer<int>    d_ref_elem, d_ref_pos;
+  dev_buffer<uint4>  d_slots;
+  dev_buffer<float4> d_prims;  // triangle vertices by element
+  dev_buffer<int>    d_slot_elem, d_ref_pos;
   dev_buffer<int4>   d_tie_nodes;
-  int                root = 0, num_refs = 0, num_nodes = 0;
+  int                root_leaf = 0, num_refs = 0, num_nodes = 0;
   float              scale = 0;
+  vec3f              grid_origin{0, 0, 0}, grid_step{1, 1, 1};
   bbox3f             root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   int  num_elems() const { return is_lines() ? (int)lines.size() / 2 : (int)triangles.size() / 3; }
   bool is_lines() const { return !lines.empty(); }

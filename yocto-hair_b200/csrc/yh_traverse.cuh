@@ -13,9 +13,22 @@ namespace yh {
 #ifndef YH_STACK_SHARED
 #define YH_STACK_SHARED 16
 #endif
-constexpr int kStackShared = YH_STACK_SHARED;  // entries per thread kept in shared memory
+constexpr int kStackShared = YH_STACK_SHARED;    // entries per thread kept in shared memory
 constexpr int kStackLocal  = 96 - kStackShared;  // overflow (LBVH chains can be deep)
 constexpr int kTraceBlock  = 128;
+
+// One 32-byte slot of the packed tree, fetched with ONE 256-bit load
+// (LDG.E.256.CONSTANT on sm_100a; the data is read-only for the kernel).
+struct slot_words {
+  unsigned w0, w1, w2, w3, w4, w5, w6, w7;
+};
+__device__ __forceinline__ slot_words ld_slot(const uint4* __restrict__ slots, int slot) {
+  slot_words s;
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(s.w0), "=r"(s.w1), "=r"(s.w2), "=r"(s.w3), "=r"(s.w4), "=r"(s.w5), "=r"(s.w6), "=r"(s.w7)
+      : "l"(slots + 2 * (size_t)slot));
+  return s;
+}
 
 struct hit_record {
   int   object, element;
@@ -96,127 +109,158 @@ __device__ __forceinline__ bool line_certain_miss(const vec3f& o, const vec3f& u
   return nn > 1e-3f * uu * vv && wn * wn > nn * tol * tol;
 }
 
-constexpr int kTraverseDone = (int)0x80000000;  // never a leaf code: those are ~x with x < 2^31
+// The primitive in leaf slot `slot` against the ray: certain-miss test, then
+// the reference's exact test.
+__device__ __forceinline__ bool test_leaf_slot(const dev_shape& sh, bool is_lines, const ray3f& ray, float uu, float mo,
+    int slot, vec2f& uv, float& t) {
+  const slot_words s = ld_slot(sh.slots, slot);
+  if (is_lines) {
+    const float4 a = {__uint_as_float(s.w0), __uint_as_float(s.w1), __uint_as_float(s.w2), __uint_as_float(s.w3)};
+    const float4 b = {__uint_as_float(s.w4), __uint_as_float(s.w5), __uint_as_float(s.w6), __uint_as_float(s.w7)};
+    if (line_certain_miss(ray.o, ray.d, uu, mo, a, b)) return false;
+    return intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uv, t);
+  }
+  const float4* tri = sh.tris + 3 * (size_t)s.w0;
+  const float4  a = __ldg(tri), b = __ldg(tri + 1), c = __ldg(tri + 2);
+  return intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uv, t);
+}
 
-// Traverses one shape with an object-space ray.  On a hit updates ray.tmax,
-// ref (leaf-order reference index), uv, and returns true.  while-while form:
-// every lane first walks inner nodes until it holds a leaf (or is done), then
-// the warp tests its leaves together, so the long primitive test does not
-// serialise against the short node step.
-//
-// Box test: slab distances as ONE FMA per plane, plane * (1/d) + (-o/d).  The
-// rounding of -o/d displaces a plane by <= 6e-8 |o| in space; the builder pads
-// every box by 4e-7 * (largest coordinate of the shape), which covers it for
-// |o| <= 4 * that scale.  Rays that start farther away (FUSED = false) use the
-// (plane - o) * (1/d) form, exact in the difference like the reference's
-// intersect_bbox (yocto_math.h:3544-3554).  A zero direction component is
-// replaced by +-1e-20 in the fused form (1/0 = inf would turn the FMA into
-// inf - inf); the slab then still rejects origins outside it and passes
-// origins inside, as the reference does.
-template <bool FUSED>
-__device__ __forceinline__ bool intersect_shape_impl(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref,
-    vec2f& uv, bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
-  bool  hit  = false;
-  // ray_dsign, :862-863
-  unsigned dsign = ((1.0f / ray.d.x) < 0 ? 1u : 0u) | ((1.0f / ray.d.y) < 0 ? 2u : 0u) | ((1.0f / ray.d.z) < 0 ? 4u : 0u);
-  auto     safe  = [](float d) { return FUSED && fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; };
-  float idx = 1.0f / safe(ray.d.x), idy = 1.0f / safe(ray.d.y), idz = 1.0f / safe(ray.d.z);
-  float ox = FUSED ? -ray.o.x * idx : ray.o.x, oy = FUSED ? -ray.o.y * idy : ray.o.y,
-        oz = FUSED ? -ray.o.z * idz : ray.o.z;
-  // slab distance of plane p along one axis
-  auto slab = [](float p, float id, float o) { return FUSED ? __fmaf_rn(p, id, o) : (p - o) * id; };
-  float uu = __fmaf_rn(ray.d.x, ray.d.x, __fmaf_rn(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
-  float mo = fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z);
-  const float4* __restrict__ nodes = sh.nodes;
-  const float4* __restrict__ prims = sh.prims;
-  const bool is_lines = sh.is_lines != 0;
+// Folds a leaf hit into the running closest hit of this shape: the smaller t
+// wins (the exact test already rejected t > tmax), an exact tie goes to the
+// element the reference visits last.
+__device__ __forceinline__ void accept_hit(const dev_shape& sh, unsigned dsign, int slot, const vec2f& uvc, float tc,
+    bool& hit, int& ref, vec2f& uv, float& tmax) {
+  if (hit && tc == tmax &&
+      !reference_visits_later(sh, __ldg(sh.slot_elem + ref), __ldg(sh.slot_elem + slot), dsign))
+    return;
+  hit = true, ref = slot, uv = uvc, tmax = tc;
+}
+
+// Box tests.  Boxes live on the shape's 16-bit grid, plane = grid_origin + q *
+// grid_step, so a slab distance is ONE FMA per plane,
+//     t = q * (step / d) + (grid_origin - o) / d,
+// with both factors per-ray constants.  Their rounding displaces a plane by
+// <~ 1e-6 * scale in space as long as |o| <= ~2 * scale (scale = largest
+// |coordinate| of the shape); the builder pads every box by 2e-6 * scale before
+// quantising outwards, which covers it.  A ray that starts farther away is
+// first moved along itself to its point nearest to the object-space origin
+// (t0 >= 0): if even that point is more than 2 * scale away the ray cannot
+// touch the shape, otherwise box distances are measured from there and compared
+// with [tmin - t0, tmax - t0].  Primitive tests always see the original ray.
+struct slab_consts {
+  float ax, ay, az, bx, by, bz;
+};
+struct shape_ray {
+  slab_consts k;
+  float       t0;     // box distances are measured from o + t0 * d
+  bool        valid;  // false: the ray cannot touch the shape
+};
+// A zero direction component is replaced by +-1e-20 (1/0 = inf would turn the
+// FMA into inf - inf); the slab then still rejects origins outside it and
+// passes origins inside, as the reference's intersect_bbox does.
+__device__ __forceinline__ shape_ray make_shape_ray(const dev_shape& sh, const vec3f& o, const vec3f& d) {
+  shape_ray r;
+  r.t0    = 0;
+  r.valid = true;
+  vec3f bo = o;
+  float lim = 2.0f * sh.scale;
+  if (!(fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z)) <= lim)) {
+    float uu = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
+    r.t0     = fmaxf(0.0f, -(o.x * d.x + o.y * d.y + o.z * d.z) / fmaxf(uu, 1e-30f));
+    bo       = {__fmaf_rn(d.x, r.t0, o.x), __fmaf_rn(d.y, r.t0, o.y), __fmaf_rn(d.z, r.t0, o.z)};
+    // nearest point still outside the ball of radius 2 * scale (> sqrt(3) * scale): no contact
+    r.valid = bo.x * bo.x + bo.y * bo.y + bo.z * bo.z <= 1.0001f * lim * lim;
+  }
+  auto  safe = [](float v) { return fabsf(v) < 1e-20f ? copysignf(1e-20f, v) : v; };
+  float idx = 1.0f / safe(d.x), idy = 1.0f / safe(d.y), idz = 1.0f / safe(d.z);
+  r.k = {sh.grid_step.x * idx, sh.grid_step.y * idy, sh.grid_step.z * idz,
+      __fmaf_rn(sh.grid_origin.x, idx, -bo.x * idx), __fmaf_rn(sh.grid_origin.y, idy, -bo.y * idy),
+      __fmaf_rn(sh.grid_origin.z, idz, -bo.z * idz)};
+  return r;
+}
+// [tmin, tmax] seen from the shifted origin, widened by the rounding of t0
+__device__ __forceinline__ float shifted_tmin(float tmin, float t0) { return tmin - t0 - 4e-6f * t0; }
+__device__ __forceinline__ float shifted_tmax(float tmax, float t0) { return tmax - t0 + 4e-6f * t0; }
+
+// both child boxes of an inner slot against [tlo, thi]
+__device__ __forceinline__ void child_boxes(const slot_words& s, const slab_consts& k, float tlo, float thi,
+    bool& h0, bool& h1, float& tn0, float& tn1) {
+  auto lo16 = [](unsigned w) { return (float)(w & 0xffffu); };
+  auto hi16 = [](unsigned w) { return (float)(w >> 16); };
+  float a0 = __fmaf_rn(lo16(s.w0), k.ax, k.bx), b0 = __fmaf_rn(hi16(s.w1), k.ax, k.bx);
+  float a1 = __fmaf_rn(hi16(s.w0), k.ay, k.by), b1 = __fmaf_rn(lo16(s.w2), k.ay, k.by);
+  float a2 = __fmaf_rn(lo16(s.w1), k.az, k.bz), b2 = __fmaf_rn(hi16(s.w2), k.az, k.bz);
+  tn0       = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tlo));
+  float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), thi));
+  float c0 = __fmaf_rn(lo16(s.w3), k.ax, k.bx), d0 = __fmaf_rn(hi16(s.w4), k.ax, k.bx);
+  float c1 = __fmaf_rn(hi16(s.w3), k.ay, k.by), d1 = __fmaf_rn(lo16(s.w5), k.ay, k.by);
+  float c2 = __fmaf_rn(lo16(s.w4), k.az, k.bz), d2 = __fmaf_rn(hi16(s.w5), k.az, k.bz);
+  tn1       = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), tlo));
+  float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), thi));
+  // slack on both ends; |x| keeps it outward-going for the negative distances of a shifted origin
+  h0 = tn0 - 5e-7f * fabsf(tn0) <= tf0 + 5e-7f * fabsf(tf0);
+  h1 = tn1 - 5e-7f * fabsf(tn1) <= tf1 + 5e-7f * fabsf(tf1);
+}
+
+__device__ __forceinline__ unsigned ray_dsign(const vec3f& d) {  // ray_dsign, :862-863
+  return ((1.0f / d.x) < 0 ? 1u : 0u) | ((1.0f / d.y) < 0 ? 2u : 0u) | ((1.0f / d.z) < 0 ? 4u : 0u);
+}
+
+constexpr int kTraverseDone = (int)0x80000000;
+
+// Traverses one shape with an object-space ray (depth first, leaves tested on
+// the spot).  On a hit updates ray.tmax, ref (leaf slot), uv, and returns true.
+// Used for the light-pdf rays against one object (sample_lights_pdf); the path
+// rays go through trace_persistent() below.
+__device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref, vec2f& uv,
+    bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
+  if (sh.num_refs == 0) return false;
+  shape_ray sr = make_shape_ray(sh, ray.o, ray.d);
+  if (!sr.valid) return false;
+  bool     hit      = false;
+  bool     is_lines = sh.is_lines != 0;
+  unsigned dsign    = ray_dsign(ray.d);
+  float    uu = __fmaf_rn(ray.d.x, ray.d.x, __fmaf_rn(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
+  float    mo = fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z);
+  auto leaf = [&](int slot) {
+    vec2f uvc;
+    float tc;
+    YH_STAT(if (prims_tested)(*prims_tested)++;)
+    if (test_leaf_slot(sh, is_lines, ray, uu, mo, slot, uvc, tc)) accept_hit(sh, dsign, slot, uvc, tc, hit, ref, uv, ray.tmax);
+  };
+  if (sh.root_leaf) {
+    leaf(0);
+    return hit;
+  }
   int base = st.sp;
-  int cur  = sh.root;
+  int cur  = 0;
   while (true) {
-    while (cur >= 0) {
-      const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1),
-                   n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
-      YH_STAT(if (nodes_visited)(*nodes_visited)++;)
-      // child 0: min = n0.xyz, max = n0.w n1.x n1.y ; child 1: min = n1.z n1.w n2.x, max = n2.yzw
-      float a0 = slab(n0.x, idx, ox), b0 = slab(n0.w, idx, ox);
-      float a1 = slab(n0.y, idy, oy), b1 = slab(n1.x, idy, oy);
-      float a2 = slab(n0.z, idz, oz), b2 = slab(n1.y, idz, oz);
-      float tn0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), ray.tmin));
-      float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), ray.tmax));
-      float c0 = slab(n1.z, idx, ox), d0 = slab(n2.y, idx, ox);
-      float c1 = slab(n1.w, idy, oy), d1 = slab(n2.z, idy, oy);
-      float c2 = slab(n2.x, idz, oz), d2 = slab(n2.w, idz, oz);
-      float tn1 = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), ray.tmin));
-      float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), ray.tmax));
-      // generous slack on both ends (padding + this keep the test conservative)
-      bool h0 = tn0 * 0.9999995f <= tf0 * 1.0000005f, h1 = tn1 * 0.9999995f <= tf1 * 1.0000005f;
-      int  ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
-      if (h0 && h1) {
-        bool swap = tn1 < tn0;
-        st.push(swap ? ch0 : ch1);
-        cur = swap ? ch1 : ch0;
-      } else if (h0) {
-        cur = ch0;
-      } else if (h1) {
-        cur = ch1;
-      } else {
-        cur = st.sp == base ? kTraverseDone : st.pop();
-      }
+    const slot_words s = ld_slot(sh.slots, cur);
+    YH_STAT(if (nodes_visited)(*nodes_visited)++;)
+    bool  h0, h1;
+    float tn0, tn1;
+    child_boxes(s, sr.k, shifted_tmin(ray.tmin, sr.t0), shifted_tmax(ray.tmax, sr.t0), h0, h1, tn0, tn1);
+    int ch0 = (int)s.w6, ch1 = (int)s.w6 + 1;
+    if (h0 && (s.w7 & 1u)) leaf(ch0), h0 = false;
+    if (h1 && (s.w7 & 2u)) leaf(ch1), h1 = false;
+    if (find_any && hit) {
+      st.sp = base;
+      return true;
     }
-    if (cur == kTraverseDone) break;
-    {
-      int code = ~cur, first = code >> 3, count = (code & 7) + 1;
-      if (is_lines) {
-        for (int k = 0; k < count; k++) {
-          const float4 a = __ldg(prims + 2 * (size_t)(first + k)), b = __ldg(prims + 2 * (size_t)(first + k) + 1);
-          YH_STAT(if (prims_tested)(*prims_tested)++;)
-          if (line_certain_miss(ray.o, ray.d, uu, mo, a, b)) continue;
-          vec2f uvc;
-          float tc;
-          if (intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uvc, tc)) {
-            if (hit && tc == ray.tmax &&
-                !reference_visits_later(sh, __ldg(sh.ref_elem + ref), __ldg(sh.ref_elem + first + k), dsign))
-              continue;  // exact tie that the reference resolves the other way
-            hit = true, ref = first + k, uv = uvc, ray.tmax = tc;
-          }
-        }
-      } else {
-        for (int k = 0; k < count; k++) {
-          const float4 a = __ldg(prims + 3 * (size_t)(first + k)), b = __ldg(prims + 3 * (size_t)(first + k) + 1),
-                       c = __ldg(prims + 3 * (size_t)(first + k) + 2);
-          YH_STAT(if (prims_tested)(*prims_tested)++;)
-          vec2f uvc;
-          float tc;
-          if (intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uvc, tc)) {
-            if (hit && tc == ray.tmax &&
-                !reference_visits_later(sh, __ldg(sh.ref_elem + ref), __ldg(sh.ref_elem + first + k), dsign))
-              continue;
-            hit = true, ref = first + k, uv = uvc, ray.tmax = tc;
-          }
-        }
-      }
-      if (find_any && hit) {
-        st.sp = base;
-        return true;
-      }
+    if (h0 && h1) {
+      bool swap = tn1 < tn0;
+      st.push(swap ? ch0 : ch1);
+      cur = swap ? ch1 : ch0;
+    } else if (h0) {
+      cur = ch0;
+    } else if (h1) {
+      cur = ch1;
+    } else {
+      if (st.sp == base) break;
+      cur = st.pop();
     }
-    cur = st.sp == base ? kTraverseDone : st.pop();
   }
   return hit;
-}
-
-template <bool FUSED>
-__device__ __noinline__ bool intersect_shape_far(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref, vec2f& uv,
-    bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
-  return intersect_shape_impl<FUSED>(sh, ray, st, ref, uv, find_any, nodes_visited, prims_tested);
-}
-__device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref,
-    vec2f& uv, bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
-  if (sh.num_refs == 0) return false;
-  float mo = fmaxf(fmaxf(fabsf(ray.o.x), fabsf(ray.o.y)), fabsf(ray.o.z));
-  if (!(mo <= 4.0f * sh.scale))  // far origin (or NaN): rare, kept out of line
-    return intersect_shape_far<false>(sh, ray, st, ref, uv, find_any, nodes_visited, prims_tested);
-  return intersect_shape_impl<true>(sh, ray, st, ref, uv, find_any, nodes_visited, prims_tested);
 }
 
 // conservative ray / box test for the object level
@@ -240,29 +284,9 @@ __device__ __forceinline__ bool intersect_instance(const dev_scene& sc, int obje
   int               ref = -1;
   if (!intersect_shape(sh, r, st, ref, uv, find_any, nv, pt)) return false;
   distance = r.tmax;
-  element  = __ldg(sh.ref_elem + ref);
+  element  = __ldg(sh.slot_elem + ref);
   return true;
 }
-
-// intersect_scene_bvh, yocto_pathtrace.cpp:934-1028
-__device__ __forceinline__ hit_record intersect_scene(const dev_scene& sc, ray3f ray, trav_stack& st,
-    bool find_any, unsigned long long* nv = nullptr, unsigned long long* pt = nullptr) {
-  hit_record h;
-  h.object = -1, h.element = -1, h.uv = {0, 0}, h.distance = 0, h.hit = false;
-  for (int o = 0; o < sc.num_objects; o++) {
-    if (!hits_box(ray, sc.objects[o].bbox)) continue;
-    int   element;
-    vec2f uv;
-    float dist;
-    if (intersect_instance(sc, o, ray, st, element, uv, dist, find_any, nv, pt)) {
-      h.hit = true, h.object = o, h.element = element, h.uv = uv, h.distance = dist;
-      ray.tmax = dist;
-      if (find_any) return h;
-    }
-  }
-  return h;
-}
-
 
 // --------------------------------------------------------------------------
 // Persistent closest-hit tracer: dynamic ray fetch, a pure node loop, parked
@@ -275,8 +299,9 @@ __device__ __forceinline__ hit_record intersect_scene(const dev_scene& sc, ray3f
 // ~7 of 32 lanes (ncu, profiles/r01_*).  Here
 //   * a warp keeps running and refills the lanes whose ray has finished from a
 //     global cursor (finished lanes also write their hit records together);
-//   * the hot loop is ONE node step per lane per iteration; a leaf child whose
-//     box is hit is not tested on the spot but parked in a small per-lane list;
+//   * the hot loop is ONE node step per lane per iteration: one 256-bit load,
+//     two box tests; a leaf child whose box is hit is not tested on the spot
+//     but parked in a small per-lane list;
 //   * when enough lanes hold parked leaves (or too few can still walk), the warp
 //     tests them together: the certain-miss test first, then, for the few
 //     survivors, the reference's exact arithmetic.
@@ -301,10 +326,11 @@ constexpr int kWalkLanes  = 12;  // ... or once fewer lanes than this can still 
 // of the dependent node fetches.
 enum cold_word {
   CW_OX, CW_OY, CW_OZ, CW_DX, CW_DY, CW_DZ,   // object-space ray
-  CW_HANDLE, CW_OBJ, CW_REF, CW_U, CW_V,      // ray handle, object index, best reference of this shape, its uv
+  CW_TMIN, CW_TMAX, CW_T0,                    // its range; box distances are measured from o + t0 d
+  CW_HANDLE, CW_OBJ, CW_REF, CW_U, CW_V,      // ray handle, object index, best leaf slot of this shape, its uv
   CW_BOBJ, CW_BELEM, CW_BU, CW_BV, CW_BDIST,  // best hit over the objects closed so far
   CW_FLAGS,                                    // bit 0 shape_hit, 1 best.hit, 2 is_lines, 4..6 dsign
-  CW_PRIMS_LO, CW_PRIMS_HI, CW_SHAPE_LO, CW_SHAPE_HI,
+  CW_SHAPE_LO, CW_SHAPE_HI,
   CW_COUNT
 };
 constexpr int kColdWords = CW_COUNT;
@@ -322,19 +348,16 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
   auto cw  = [&](int w) -> volatile int& { return cold[w * kTraceBlock]; };
   auto cwf = [&](int w) -> float { return __int_as_float(cold[w * kTraceBlock]); };
   auto put = [&](int w, float v) { cold[w * kTraceBlock] = __float_as_int(v); };
-  auto ptr = [&](int w) -> const void* {
-    return (const void*)(((unsigned long long)(unsigned)cold[(w + 1) * kTraceBlock] << 32) | (unsigned)cold[w * kTraceBlock]);
-  };
-  auto put_ptr = [&](int w, const void* p) {
-    cold[w * kTraceBlock]       = (int)(unsigned)((unsigned long long)p);
-    cold[(w + 1) * kTraceBlock] = (int)(unsigned)((unsigned long long)p >> 32);
+  auto shape_ptr = [&]() -> const dev_shape* {
+    return (const dev_shape*)(((unsigned long long)(unsigned)cold[CW_SHAPE_HI * kTraceBlock] << 32) |
+                              (unsigned)cold[CW_SHAPE_LO * kTraceBlock]);
   };
   // registers of the node loop
   bool  have = false, finished = false, exhausted = false;
   int   cur = kTraverseDone, npark = 0;
-  float tmin = 0, tmax = 0;
-  float idx = 0, idy = 0, idz = 0, ox = 0, oy = 0, oz = 0;
-  const float4* __restrict__ nodes = nullptr;
+  float tlo = 0, thi = 0;  // [tmin, tmax] as seen from the (possibly shifted) box origin
+  slab_consts k = {0, 0, 0, 0, 0, 0};
+  const uint4* __restrict__ slots = nullptr;
 
   while (true) {
     // ---- 1. lanes without a ray: write finished records, fetch new rays
@@ -357,7 +380,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
           int   handle;
           if (index < n && io.load(index, handle, wr)) {
             have = true, cur = kTraverseDone, st.sp = 0, npark = 0;
-            tmin = wr.tmin, tmax = wr.tmax;
+            put(CW_TMIN, wr.tmin), put(CW_TMAX, wr.tmax);
             cw(CW_HANDLE) = handle, cw(CW_OBJ) = -1, cw(CW_FLAGS) = 0;
             cw(CW_BOBJ) = -1, cw(CW_BELEM) = -1, put(CW_BU, 0), put(CW_BV, 0), put(CW_BDIST, 0);
           }
@@ -374,41 +397,27 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       unsigned pm = __ballot_sync(full, npark > 0);
       unsigned wm = __ballot_sync(full, can_walk);
       if (npark > 0 && (__popc(pm) >= kParkLanes || __popc(wm) < kWalkLanes)) {
-        vec3f o = {cwf(CW_OX), cwf(CW_OY), cwf(CW_OZ)}, d = {cwf(CW_DX), cwf(CW_DY), cwf(CW_DZ)};
-        float uu = __fmaf_rn(d.x, d.x, __fmaf_rn(d.y, d.y, d.z * d.z));
-        float mo = fabsf(o.x) + fabsf(o.y) + fabsf(o.z);
+        ray3f ray = {{cwf(CW_OX), cwf(CW_OY), cwf(CW_OZ)}, {cwf(CW_DX), cwf(CW_DY), cwf(CW_DZ)}, cwf(CW_TMIN),
+            cwf(CW_TMAX)};
+        float uu = __fmaf_rn(ray.d.x, ray.d.x, __fmaf_rn(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
+        float mo = fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z);
         int   flags = cw(CW_FLAGS), ref = cw(CW_REF);
         bool  shape_hit = flags & 1, is_lines = (flags & 4) != 0;
         unsigned dsign = (flags >> 4) & 7;
         vec2f uv = {cwf(CW_U), cwf(CW_V)};
-        const float4* __restrict__ prims = (const float4*)ptr(CW_PRIMS_LO);
-        const dev_shape* shp = (const dev_shape*)ptr(CW_SHAPE_LO);
-        ray3f ray = {o, d, tmin, tmax};
+        const dev_shape& sh = *shape_ptr();
         for (int e = 0; e < npark; e++) {
-          int code = ~smem_park[e * kTraceBlock], first = code >> 3, count = (code & 7) + 1;
-          for (int k = 0; k < count; k++) {
-            int   r = first + k;
-            vec2f uvc;
-            float tc;
-            bool  got;
-            YH_STAT(if (prims_tested)(*prims_tested)++;)
-            if (is_lines) {
-              const float4 a = __ldg(prims + 2 * (size_t)r), b = __ldg(prims + 2 * (size_t)r + 1);
-              if (line_certain_miss(o, d, uu, mo, a, b)) continue;
-              got = intersect_line(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, a.w, b.w, uvc, tc);
-            } else {
-              const float4 a = __ldg(prims + 3 * (size_t)r), b = __ldg(prims + 3 * (size_t)r + 1),
-                           c = __ldg(prims + 3 * (size_t)r + 2);
-              got = intersect_triangle(ray, {a.x, a.y, a.z}, {b.x, b.y, b.z}, {c.x, c.y, c.z}, uvc, tc);
-            }
-            if (got && !(shape_hit && tc == ray.tmax &&
-                           !reference_visits_later(*shp, __ldg(shp->ref_elem + ref), __ldg(shp->ref_elem + r), dsign)))
-              shape_hit = true, ref = r, uv = uvc, ray.tmax = tc;
-          }
+          int   slot = smem_park[e * kTraceBlock];
+          vec2f uvc;
+          float tc;
+          YH_STAT(if (prims_tested)(*prims_tested)++;)
+          if (test_leaf_slot(sh, is_lines, ray, uu, mo, slot, uvc, tc))
+            accept_hit(sh, dsign, slot, uvc, tc, shape_hit, ref, uv, ray.tmax);
         }
-        tmax  = ray.tmax;
         npark = 0;
         if (shape_hit) {
+          put(CW_TMAX, ray.tmax);
+          thi = shifted_tmax(ray.tmax, cwf(CW_T0));
           cw(CW_FLAGS) = flags | 1, cw(CW_REF) = ref, put(CW_U, uv.x), put(CW_V, uv.y);
           if (find_any) st.sp = 0, cur = kTraverseDone;
         }
@@ -417,10 +426,10 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
 
     // ---- 3. lanes between shapes: close the finished one, open the next object
     if (have && cur == kTraverseDone && npark == 0) {
-      int flags = cw(CW_FLAGS), obj = cw(CW_OBJ), handle = cw(CW_HANDLE);
+      int   flags = cw(CW_FLAGS), obj = cw(CW_OBJ), handle = cw(CW_HANDLE);
+      float tmin = cwf(CW_TMIN), tmax = cwf(CW_TMAX);
       if (flags & 1) {
-        const dev_shape* shp = (const dev_shape*)ptr(CW_SHAPE_LO);
-        cw(CW_BOBJ) = obj, cw(CW_BELEM) = __ldg(shp->ref_elem + cw(CW_REF));
+        cw(CW_BOBJ) = obj, cw(CW_BELEM) = __ldg(shape_ptr()->slot_elem + cw(CW_REF));
         cw(CW_BU) = cw(CW_U), cw(CW_BV) = cw(CW_V), put(CW_BDIST, tmax);
         flags = (flags & ~1) | 2;
         if (find_any) obj = sc.num_objects;
@@ -434,33 +443,20 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         if (!hits_box(wr, ob.bbox)) continue;
         const dev_shape& sh = sc.shapes[ob.shape];
         if (sh.num_refs == 0) continue;
-        vec3f o = transform_point(ob.inv_frame, wo), d = transform_vector(ob.inv_frame, wd);
-        float mo = fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fabsf(o.z));
-        if (!(mo <= 4.0f * sh.scale)) {  // far origin: whole shape at once, out of line (rare)
-          ray3f r = {o, d, tmin, tmax};
-          int   rr = -1;
-          vec2f ruv;
-          if (intersect_shape_far<false>(sh, r, st, rr, ruv, find_any, nodes_visited, prims_tested)) {
-            cw(CW_BOBJ) = obj, cw(CW_BELEM) = __ldg(sh.ref_elem + rr), put(CW_BU, ruv.x), put(CW_BV, ruv.y);
-            put(CW_BDIST, r.tmax);
-            tmax = r.tmax, flags |= 2;
-            if (find_any) break;
-          }
-          continue;
-        }
-        auto safe = [](float v) { return fabsf(v) < 1e-20f ? copysignf(1e-20f, v) : v; };
-        unsigned dsign = ((1.0f / d.x) < 0 ? 1u : 0u) | ((1.0f / d.y) < 0 ? 2u : 0u) | ((1.0f / d.z) < 0 ? 4u : 0u);
-        idx = 1.0f / safe(d.x), idy = 1.0f / safe(d.y), idz = 1.0f / safe(d.z);
-        ox = -o.x * idx, oy = -o.y * idy, oz = -o.z * idz;
+        vec3f     o = transform_point(ob.inv_frame, wo), d = transform_vector(ob.inv_frame, wd);
+        shape_ray sr = make_shape_ray(sh, o, d);
+        if (!sr.valid) continue;
+        k = sr.k;
+        tlo = shifted_tmin(tmin, sr.t0), thi = shifted_tmax(tmax, sr.t0);
         put(CW_OX, o.x), put(CW_OY, o.y), put(CW_OZ, o.z), put(CW_DX, d.x), put(CW_DY, d.y), put(CW_DZ, d.z);
-        put_ptr(CW_PRIMS_LO, sh.prims), put_ptr(CW_SHAPE_LO, &sh);
-        flags = (flags & 3) | (sh.is_lines ? 4 : 0) | (int)(dsign << 4);
-        nodes = sh.nodes;
-        cur   = sh.root;
+        put(CW_T0, sr.t0);
+        cw(CW_SHAPE_LO) = (int)(unsigned)((unsigned long long)&sh);
+        cw(CW_SHAPE_HI) = (int)(unsigned)((unsigned long long)&sh >> 32);
+        flags = (flags & 3) | (sh.is_lines ? 4 : 0) | (int)(ray_dsign(d) << 4);
+        slots = sh.slots;
         cw(CW_REF) = -1;
-        if (cur < 0) {  // the whole shape is one leaf
-          smem_park[0] = cur, npark = 1, cur = kTraverseDone;
-        }
+        if (sh.root_leaf) smem_park[0] = 0, npark = 1, cur = kTraverseDone;  // the whole shape is one leaf
+        else cur = 0;
         opened = true;
         break;
       }
@@ -470,23 +466,14 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
 
     // ---- 4. one node step; leaf children whose box is hit are parked
     if (cur >= 0 && npark <= kParkSlots - 2) {
-      const float4 n0 = __ldg(nodes + 4 * (size_t)cur), n1 = __ldg(nodes + 4 * (size_t)cur + 1),
-                   n2 = __ldg(nodes + 4 * (size_t)cur + 2), n3 = __ldg(nodes + 4 * (size_t)cur + 3);
+      const slot_words s = ld_slot(slots, cur);
       YH_STAT(if (nodes_visited)(*nodes_visited)++;)
-      float a0 = __fmaf_rn(n0.x, idx, ox), b0 = __fmaf_rn(n0.w, idx, ox);
-      float a1 = __fmaf_rn(n0.y, idy, oy), b1 = __fmaf_rn(n1.x, idy, oy);
-      float a2 = __fmaf_rn(n0.z, idz, oz), b2 = __fmaf_rn(n1.y, idz, oz);
-      float tn0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tmin));
-      float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), tmax));
-      float c0 = __fmaf_rn(n1.z, idx, ox), d0 = __fmaf_rn(n2.y, idx, ox);
-      float c1 = __fmaf_rn(n1.w, idy, oy), d1 = __fmaf_rn(n2.z, idy, oy);
-      float c2 = __fmaf_rn(n2.x, idz, oz), d2 = __fmaf_rn(n2.w, idz, oz);
-      float tn1 = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), tmin));
-      float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), tmax));
-      bool h0 = tn0 * 0.9999995f <= tf0 * 1.0000005f, h1 = tn1 * 0.9999995f <= tf1 * 1.0000005f;
-      int  ch0 = __float_as_int(n3.x), ch1 = __float_as_int(n3.y);
-      if (h0 && ch0 < 0) smem_park[npark++ * kTraceBlock] = ch0, h0 = false;
-      if (h1 && ch1 < 0) smem_park[npark++ * kTraceBlock] = ch1, h1 = false;
+      bool  h0, h1;
+      float tn0, tn1;
+      child_boxes(s, k, tlo, thi, h0, h1, tn0, tn1);
+      int ch0 = (int)s.w6, ch1 = (int)s.w6 + 1;
+      if (h0 && (s.w7 & 1u)) smem_park[npark++ * kTraceBlock] = ch0, h0 = false;
+      if (h1 && (s.w7 & 2u)) smem_park[npark++ * kTraceBlock] = ch1, h1 = false;
       if (h0 && h1) {
         bool swap = tn1 < tn0;
         st.push(swap ? ch0 : ch1);
