@@ -110,7 +110,7 @@ YH_HD float log_i0(float x) {
     return logf_(i0(x));
 }
 // :201-207.  The v > 0.1 branch mixes in a double sinh: float / (double*int*float).
-YH_HD float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v) {
+YH_HD_CALL float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v) {
   float a = div_(cos_theta_i * cos_theta_o, v);
   float b = div_(sin_theta_i * sin_theta_o, v);
   if (v <= 0.1f)
@@ -156,7 +156,7 @@ YH_HD float logistic_cdf(float x, float s) { return div_(1.0f, (1 + expf_(div_(-
 YH_HD float trimmed_logistic(float x, float s, float a, float b) {  // :243-245
   return div_(logistic(x, s), (logistic_cdf(b, s) - logistic_cdf(a, s)));
 }
-YH_HD float np(float phi, int p, float s, float gamma_o, float gamma_t) {  // :247-253
+YH_HD_CALL float np(float phi, int p, float s, float gamma_o, float gamma_t) {  // :247-253
   float dphi = phi - phi_p(p, gamma_o, gamma_t);
   while (dphi > pif) dphi -= 2 * pif;
   while (dphi < -pif) dphi += 2 * pif;
@@ -181,32 +181,6 @@ YH_HD void tilt(const hair_brdf& brdf, int p, float sin_theta_o, float cos_theta
   }
 }
 
-// Terms that depend on the outgoing direction only; eval, pdf and sample of
-// one shading point share them (the reference recomputes them per call with
-// identical arithmetic, so sharing does not change any bit).
-struct hair_wo_terms {
-  float sin_theta_o, cos_theta_o, phi_o;
-  float gamma_t;
-  vec3f ap[p_max + 1];
-};
-YH_HD hair_wo_terms hair_prepare_wo(const hair_brdf& brdf, const vec3f& outgoing_) {
-  hair_wo_terms t;
-  vec3f outgoing = transform_direction(brdf.world_to_brdf, outgoing_);
-  t.sin_theta_o  = outgoing.x;
-  t.cos_theta_o  = safe_sqrt(1 - sqr(t.sin_theta_o));
-  t.phi_o        = atan2f_(outgoing.z, outgoing.y);
-  // :281-291 — eval derives sin_theta_t from sin_theta_o; compute_ap_pdf (:365-397)
-  // re-derives sin_theta_o from cos_theta_o: see hair_ap_for_pdf below.
-  float sin_theta_t = div_(t.sin_theta_o, brdf.eta);
-  float cos_theta_t = safe_sqrt(1 - sqr(sin_theta_t));
-  float etap        = div_(sqrt_(brdf.eta * brdf.eta - sqr(t.sin_theta_o)), t.cos_theta_o);
-  float sin_gamma_t = div_(brdf.h, etap);
-  float cos_gamma_t = safe_sqrt(1 - sqr(sin_gamma_t));
-  t.gamma_t         = safe_asin(sin_gamma_t);
-  vec3f T           = exp3(-brdf.sigma_a * div_(2 * cos_gamma_t, cos_theta_t));
-  ap(t.cos_theta_o, brdf.eta, brdf.h, T, t.ap);
-  return t;
-}
 // compute_ap_pdf, :365-397: note sin_theta_o = safe_sqrt(1 - cos^2) here, which
 // is |sin_theta_o| up to rounding, so Ap is evaluated again for the pdf.
 YH_HD void hair_ap_pdf(const hair_brdf& brdf, float cos_theta_o, float ap_pdf[p_max + 1]) {
@@ -224,6 +198,34 @@ YH_HD void hair_ap_pdf(const hair_brdf& brdf, float cos_theta_o, float ap_pdf[p_
   for (int i = 0; i <= p_max; i++) ap_pdf[i] = div_(luminance(a[i]), sum_y);
 }
 
+// Terms that depend on the outgoing direction only; eval, pdf and sample of
+// one shading point share them (the reference recomputes them per call with
+// identical arithmetic, so sharing does not change any bit).
+struct hair_wo_terms {
+  float sin_theta_o, cos_theta_o, phi_o;
+  float gamma_t;
+  vec3f ap[p_max + 1];
+  float ap_pdf[p_max + 1];  // compute_ap_pdf(brdf, cos_theta_o), :365-397
+};
+YH_HD hair_wo_terms hair_prepare_wo(const hair_brdf& brdf, const vec3f& outgoing_) {
+  hair_wo_terms t;
+  vec3f outgoing = transform_direction(brdf.world_to_brdf, outgoing_);
+  t.sin_theta_o  = outgoing.x;
+  t.cos_theta_o  = safe_sqrt(1 - sqr(t.sin_theta_o));
+  t.phi_o        = atan2f_(outgoing.z, outgoing.y);
+  // :281-291 — eval derives sin_theta_t from sin_theta_o; compute_ap_pdf (:365-397)
+  // re-derives sin_theta_o from cos_theta_o: see hair_ap_for_pdf below.
+  float sin_theta_t = div_(t.sin_theta_o, brdf.eta);
+  float cos_theta_t = safe_sqrt(1 - sqr(sin_theta_t));
+  float etap        = div_(sqrt_(brdf.eta * brdf.eta - sqr(t.sin_theta_o)), t.cos_theta_o);
+  float sin_gamma_t = div_(brdf.h, etap);
+  float cos_gamma_t = safe_sqrt(1 - sqr(sin_gamma_t));
+  t.gamma_t         = safe_asin(sin_gamma_t);
+  vec3f T           = exp3(-brdf.sigma_a * div_(2 * cos_gamma_t, cos_theta_t));
+  ap(t.cos_theta_o, brdf.eta, brdf.h, T, t.ap);
+  hair_ap_pdf(brdf, t.cos_theta_o, t.ap_pdf);
+  return t;
+}
 // eval_hair_scattering, :255-336
 YH_HD vec3f eval_hair_scattering(const hair_brdf& brdf, const hair_wo_terms& t, const vec3f& incoming_) {
   vec3f incoming    = transform_direction(brdf.world_to_brdf, incoming_);
@@ -270,8 +272,7 @@ YH_HD float sample_trimmed_logistic(float u, float s, float a, float b) {  // :3
 // sample_hair_scattering, :399-479
 YH_HD vec3f sample_hair_scattering(const hair_brdf& brdf, const hair_wo_terms& t, const vec2f& rn) {
   vec2f u0 = demux_float(rn.x), u1 = demux_float(rn.y);
-  float ap_pdf[p_max + 1];
-  hair_ap_pdf(brdf, t.cos_theta_o, ap_pdf);
+  const float* ap_pdf = t.ap_pdf;
   int p = 0;
   for (p = 0; p < p_max; p++) {
     if (u0.x < ap_pdf[p]) break;
@@ -306,8 +307,7 @@ YH_HD float sample_hair_scattering_pdf(const hair_brdf& brdf, const hair_wo_term
   float sin_theta_i = incoming.x;
   float cos_theta_i = safe_sqrt(1 - sqr(sin_theta_i));
   float phi_i       = atan2f_(incoming.z, incoming.y);
-  float ap_pdf[p_max + 1];
-  hair_ap_pdf(brdf, t.cos_theta_o, ap_pdf);
+  const float* ap_pdf = t.ap_pdf;
   float phi = phi_i - t.phi_o;
   float pdf = 0.0f;
   for (int p = 0; p < p_max; p++) {
@@ -320,6 +320,33 @@ YH_HD float sample_hair_scattering_pdf(const hair_brdf& brdf, const hair_wo_term
   pdf += mp(cos_theta_i, t.cos_theta_o, sin_theta_i, t.sin_theta_o, brdf.v[p_max]) * ap_pdf[p_max] *
          div_(1.0f, (2 * pif));
   return pdf;
+}
+// eval_hair_scattering (:255-336) and sample_hair_scattering_pdf (:481-551) at
+// the SAME incoming direction, as trace_path asks for them (:1449-1451).  Both
+// sums run over the same Mp / Np factors; each factor is formed once, with the
+// reference's arithmetic, and feeds both sums in the reference's order, so f
+// and pdf carry the bits the two separate calls produce.
+YH_HD void eval_hair_scattering_and_pdf(const hair_brdf& brdf, const hair_wo_terms& t, const vec3f& incoming_,
+    vec3f& f, float& pdf) {
+  vec3f incoming    = transform_direction(brdf.world_to_brdf, incoming_);
+  float sin_theta_i = incoming.x;
+  float cos_theta_i = safe_sqrt(1 - sqr(sin_theta_i));
+  float phi_i       = atan2f_(incoming.z, incoming.y);
+  float phi         = phi_i - t.phi_o;
+  f   = {0, 0, 0};
+  pdf = 0.0f;
+  for (int p = 0; p < p_max; p++) {
+    float sin_theta_op, cos_theta_op;
+    tilt(brdf, p, t.sin_theta_o, t.cos_theta_o, sin_theta_op, cos_theta_op);
+    cos_theta_op = fabs_(cos_theta_op);
+    float m = mp(cos_theta_i, cos_theta_op, sin_theta_i, sin_theta_op, brdf.v[p]);
+    float n = np(phi, p, brdf.s, brdf.gamma_o, t.gamma_t);
+    f = f + m * t.ap[p] * n;
+    pdf += m * t.ap_pdf[p] * n;
+  }
+  float m = mp(cos_theta_i, t.cos_theta_o, sin_theta_i, t.sin_theta_o, brdf.v[p_max]);
+  f = f + m * t.ap[p_max] / (2 * pif);
+  pdf += m * t.ap_pdf[p_max] * div_(1.0f, (2 * pif));
 }
 YH_HD float sample_hair_scattering_pdf(const hair_brdf& brdf, const vec3f& outgoing, const vec3f& incoming) {
   return sample_hair_scattering_pdf(brdf, hair_prepare_wo(brdf, outgoing), incoming);

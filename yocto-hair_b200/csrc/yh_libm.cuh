@@ -94,7 +94,7 @@ YH_HD double dfma(double a, double b, double c) {
 }
 
 // glibc e_expf.c (__expf)
-YH_HD float expf_(float x) {
+YH_HD_CALL float expf_(float x) {
   uint32_t abstop = (f2u(x) >> 20) & 0x7ff;
   if (abstop >= 0x42b) {  // top12(88.0f): |x| >= 88 or NaN
     if (f2u(x) == 0xff800000u) return 0.0f;
@@ -119,7 +119,7 @@ YH_HD float expf_(float x) {
 }
 
 // glibc e_logf.c (__logf)
-YH_HD float logf_(float x) {
+YH_HD_CALL float logf_(float x) {
   uint32_t ix = f2u(x);
   if (ix == 0x3f800000u) return 0.0f;
   if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
@@ -201,7 +201,7 @@ YH_HD double reduce_large(uint32_t xi, int* np) {
   return dmul(x, 0x1.921FB54442D18p-62);
 }
 // sinf (which = 0) / cosf (which = 1): glibc s_sinf.c / s_cosf.c
-YH_HD float sincosf_(float y, int which) {
+YH_HD_CALL float sincosf_(float y, int which) {
   double     x = (double)y;
   int        n;
   sincos_tab p{&YH_TAB(yh_sincosf_tab)[0]};
@@ -277,7 +277,7 @@ YH_HD float atanf_(float x) {
 }
 
 // fdlibm e_atan2f.c (__ieee754_atan2f)
-YH_HD float atan2f_(float y, float x) {
+YH_HD_CALL float atan2f_(float y, float x) {
   const float tiny = 1.0e-30f, pi_o_4 = u2f(0x3f490fdbu), pi_o_2 = u2f(0x3fc90fdbu),
               pi = u2f(0x40490fdbu), pi_lo = u2f(0xb3bbbd2eu);
   int32_t hx = (int32_t)f2u(x), hy = (int32_t)f2u(y);
@@ -326,7 +326,7 @@ YH_HD float atan2f_(float y, float x) {
 }
 
 // fdlibm e_acosf.c (__ieee754_acosf)
-YH_HD float acosf_(float x) {
+YH_HD_CALL float acosf_(float x) {
   const float pi = u2f(0x40490fdau), pio2_hi = u2f(0x3fc90fdau), pio2_lo = u2f(0x33a22168u),
               pS0 = u2f(0x3e2aaaabu), pS1 = u2f(0xbea6b090u), pS2 = u2f(0x3e4e0aa8u),
               pS3 = u2f(0xbd241146u), pS4 = u2f(0x3a4f7f04u), pS5 = u2f(0x3811ef08u),

@@ -7,8 +7,13 @@
 
 #if defined(__CUDACC__)
 #define YH_HD __host__ __device__ __forceinline__
+// out of line on the device: the shading kernel would otherwise inline ~270 KB
+// of code (8 copies of mp(), dozens of expf_/logf_) and stall on instruction
+// fetch (ncu: stall_no_inst was its top stall reason)
+#define YH_HD_CALL __host__ __device__ inline __noinline__
 #else
 #define YH_HD inline
+#define YH_HD_CALL inline
 #endif
 
 namespace yh {

@@ -476,6 +476,7 @@ yh_scene::~yh_scene() {
   for (auto s : shapes) delete s;
   for (auto t : tex_dev) delete t;
   for (auto c : light_cdfs) delete c;
+  for (auto g : light_guides) delete g;
 }
 
 static frame3f to_frame(const float* f) {
@@ -647,7 +648,9 @@ yh_status yh_scene_init_lights(yh_scene* sc) {
   YH_REQUIRE_DEVICE();
   if (!sc) return fail(YH_ERR_INVALID, "yh_scene_init_lights: scene is null");
   for (auto c : sc->light_cdfs) delete c;
+  for (auto g : sc->light_guides) delete g;
   sc->light_cdfs.clear();
+  sc->light_guides.clear();
   sc->lights.clear();
   for (int oi = 0; oi < (int)sc->objects.size(); oi++) {
     auto& o = sc->objects[oi];
@@ -666,12 +669,12 @@ yh_status yh_scene_init_lights(yh_scene* sc) {
     auto buf = new dev_buffer<float>{};
     sc->light_cdfs.push_back(buf);
     YH_CUDA(buf->upload(cdf.data(), cdf.size()));
-    sc->lights.push_back({oi, -1, buf->ptr, nt});
+    sc->lights.push_back({oi, -1, buf->ptr, nt, nullptr, 0, 0.0f, 0.0f});
   }
   for (int ei = 0; ei < (int)sc->environments.size(); ei++) {
     auto& e = sc->environments[ei];
     if (e.emission == vec3f{0, 0, 0}) continue;
-    dev_light l{-1, ei, nullptr, 0};
+    dev_light l{-1, ei, nullptr, 0, nullptr, 0, 0.0f, 0.0f};
     if (e.tex >= 0) {
       int                w = sc->textures[e.tex].width, h = sc->textures[e.tex].height;
       auto&              px = sc->tex_host[e.tex];
@@ -687,6 +690,23 @@ yh_status yh_scene_init_lights(yh_scene* sc) {
       sc->light_cdfs.push_back(buf);
       YH_CUDA(buf->upload(cdf.data(), cdf.size()));
       l.cdf = buf->ptr, l.cdf_size = (int)cdf.size();
+      // guide table (one bucket per texel)
+      float back = cdf.back();
+      int   G    = (int)cdf.size();
+      if (back > 0 && std::isfinite(back)) {
+        float            gw = back / (float)G;
+        std::vector<int> guide((size_t)G + 1);
+        size_t           j = 0;
+        for (int b = 0; b <= G; b++) {  // thresholds grow with b: one sweep = upper_bound per bucket
+          float t = (float)b * gw;
+          while (j < cdf.size() && !(t < cdf[j])) j++;
+          guide[b] = (int)j;
+        }
+        auto gbuf = new dev_buffer<int>{};
+        sc->light_guides.push_back(gbuf);
+        YH_CUDA(gbuf->upload(guide.data(), guide.size()));
+        l.guide = gbuf->ptr, l.guide_size = G, l.guide_w = gw, l.guide_inv_w = 1.0f / gw;
+      }
     }
     sc->lights.push_back(l);
   }

@@ -94,6 +94,11 @@ struct dev_light {
   int          environment;  // -1 when this is an object light
   const float* cdf;
   int          cdf_size;
+  // guide table of the cdf: guide[b] = first index with cdf > b * guide_w (b = 0 .. guide_size);
+  // narrows the reference's std::upper_bound to a few elements, same result
+  const int*   guide;
+  int          guide_size;
+  float        guide_w, guide_inv_w;
 };
 
 struct dev_scene {
@@ -136,6 +141,7 @@ struct yh_scene {
   std::vector<yh::dev_buffer<float>*> tex_dev;
   std::vector<yh::dev_light>        lights;
   std::vector<yh::dev_buffer<float>*> light_cdfs;
+  std::vector<yh::dev_buffer<int>*>   light_guides;
   yh::dev_buffer<yh::dev_shape>       d_shapes;
   yh::dev_buffer<yh::dev_material>    d_materials;
   yh::dev_buffer<yh::dev_object>      d_objects;

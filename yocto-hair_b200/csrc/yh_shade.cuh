@@ -89,11 +89,26 @@ __device__ __forceinline__ vec3f eval_environment(const dev_scene& sc, const vec
   return emission;
 }
 
-// sample_discrete_cdf, yocto_math.h:4953-4958 (std::upper_bound)
-__device__ __forceinline__ int sample_discrete_cdf(const float* cdf, int n, float r) {
+// sample_discrete_cdf, yocto_math.h:4953-4958 (std::upper_bound).  With a guide
+// table the search runs over the few elements between guide[b - 1] and
+// guide[b + 2] (b = bucket of r): every element before the window is <= r and
+// the element at its end is > r, so the first element > r is the same one the
+// full search finds.
+__device__ __forceinline__ int sample_discrete_cdf(const dev_light& light, float r) {
+  const float* cdf = light.cdf;
+  int   n    = light.cdf_size;
   float back = __ldg(cdf + n - 1);
   r          = clampf(r * back, 0.0f, back - 0.00001f);
   int lo = 0, len = n;
+  if (light.guide) {
+    int b  = clampi((int)(r * light.guide_inv_w), 0, light.guide_size - 1);
+    int b0 = b > 0 ? b - 1 : 0, b1 = b + 2 < light.guide_size ? b + 2 : light.guide_size;
+    // the margins of one bucket absorb the rounding of r * guide_inv_w; checked anyway
+    if ((float)b0 * light.guide_w <= r && r <= (float)b1 * light.guide_w) {
+      lo  = __ldg(light.guide + b0);
+      len = __ldg(light.guide + b1) - lo;
+    }
+  }
   while (len > 0) {  // first element > r
     int half = len >> 1;
     if (!(r < __ldg(cdf + lo + half))) {
@@ -112,7 +127,7 @@ __device__ __forceinline__ vec3f sample_lights(const dev_scene& sc, const vec3f&
   int              light_id = clampi((int)(rl * sc.num_lights), 0, sc.num_lights - 1);  // sample_uniform
   const dev_light& light    = sc.lights[light_id];
   if (light.object >= 0) {
-    int   element = sample_discrete_cdf(light.cdf, light.cdf_size, rel);
+    int   element = sample_discrete_cdf(light, rel);
     vec2f uv      = {1 - sqrt_(ruv.x), ruv.y * sqrt_(ruv.x)};  // sample_triangle, yocto_math.h:4911
     vec3f lpos    = eval_position(sc, light.object, element, uv);
     return normalize(lpos - position);
@@ -120,7 +135,7 @@ __device__ __forceinline__ vec3f sample_lights(const dev_scene& sc, const vec3f&
   const dev_environment& env = sc.environments[light.environment];
   if (env.tex >= 0) {
     const dev_texture& t = sc.textures[env.tex];
-    int   idx = sample_discrete_cdf(light.cdf, light.cdf_size, rel);
+    int   idx = sample_discrete_cdf(light, rel);
     vec2f uv  = {div_((idx % t.width + 0.5f), (float)t.width), div_((idx / t.width + 0.5f), (float)t.height)};
     return transform_direction(env.frame, {cosf_(uv.x * 2 * pif) * sinf_(uv.y * pif), cosf_(uv.y * pif),
                                               sinf_(uv.x * 2 * pif) * sinf_(uv.y * pif)});

@@ -183,7 +183,7 @@ struct wavefront_io {
 // Closest hit for every slot of the active queue, then the slot id goes to the
 // miss / surface / hair queue.  Persistent warps, q.count[5] is the ray cursor.
 #ifndef YH_INTERSECT_BLOCKS
-#define YH_INTERSECT_BLOCKS 5
+#define YH_INTERSECT_BLOCKS 6
 #endif
 __global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
@@ -295,8 +295,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       incoming  = sample_lights(sc, position, rl, rel, ruv);
     }
     if (HAIR) {
-      brdfcos  = eval_hair_scattering(hb, ht, incoming);        // :1071-1073
-      brdf_pdf = sample_hair_scattering_pdf(hb, ht, incoming);  // :1219-1221
+      eval_hair_scattering_and_pdf(hb, ht, incoming, brdfcos, brdf_pdf);  // :1071-1073, :1219-1221
     } else {
       // eval_diffuse_reflection / sample_diffuse_reflection_pdf, yocto_math.h:4427, :4572
       brdfcos  = {0, 0, 0};
@@ -338,7 +337,10 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
 }
 
 template <bool HAIR>
-__global__ void __launch_bounds__(kTraceBlock) k_shade(dev_scene sc, path_state ps, queues q, dev_camera cam,
+#ifndef YH_SHADE_BLOCKS
+#define YH_SHADE_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kTraceBlock, YH_SHADE_BLOCKS) k_shade(dev_scene sc, path_state ps, queues q, dev_camera cam,
     trace_consts tc, int next) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
   int            n     = q.count[HAIR ? 4 : 3];

@@ -67,7 +67,7 @@ struct trav_stack {
 // of the split axis first (:879-886) and walks a leaf in primitive order, and
 // a hit at t == tmax replaces the stored one, so among exact ties the element
 // visited last is the one it returns.
-__device__ __noinline__ bool reference_visits_later(const dev_shape& sh, int ea, int eb, unsigned dsign) {
+__device__ __forceinline__ bool reference_visits_later(const dev_shape& sh, int ea, int eb, unsigned dsign) {
   int pa = __ldg(sh.ref_pos + ea), pb = __ldg(sh.ref_pos + eb);
   if (pa == pb) return false;
   int  lo = min(pa, pb), hi = max(pa, pb);
