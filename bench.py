@@ -289,7 +289,8 @@ def run_cuda(args):
             probe = traversal_stats_probe(args.workload, args.sky, 2, args.max_split)
             nodes_per_ray = probe["nodes"] / probe["rays"]
             prims_per_ray = probe["prims"] / probe["rays"]
-            bytes_per_ray = 64.0 * nodes_per_ray + 32.0 * prims_per_ray + 56.0
+            # one 32-byte slot per node step and per primitive test (yh_scene.cuh), + ray in (32 B) and hit out (24 B)
+            bytes_per_ray = 32.0 * nodes_per_ray + 32.0 * prims_per_ray + 56.0
             # rank 0's own launches: one k_intersect launch per wavefront iteration
             bytes_per_launch = bytes_per_ray * local_rays / max(1, local_iters)
             ms_per_launch = local_trav_ms / max(1, local_iters)

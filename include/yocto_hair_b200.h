@@ -196,6 +196,12 @@ yh_status yh_state_size(const yh_state* state, int* width, int* height);
  * `world` (32x32 tiles, round-robin).  Every pixel keeps its own RNG stream,
  * so the union over ranks is bit-identical to a single-device render.       */
 yh_status yh_state_set_shard(yh_state* state, int rank, int world);
+/* The ownership map behind yh_state_set_shard, host only (needs no device):
+ * writes the image pixel indices (j * width + i) owned by `rank` of `world`,
+ * in slot order, to `pixels` (may be null) and their number to `count`.
+ * Replaces the row scheduler of parallel_for, yocto_pathtrace.cpp:1954-1989. */
+yh_status yh_shard_pixels(int width, int height, int rank, int world,
+    int* pixels, int64_t* count);
 
 /* Replaces `num_samples` consecutive calls of trace_samples(state, scene,
  * camera, params), yocto_pathtrace.cpp:1992-2026: every owned pixel gains

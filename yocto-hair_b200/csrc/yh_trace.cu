@@ -620,6 +620,15 @@ yh_status yh_state_set_shard(yh_state* st, int rank, int world) {
   return assign_slots(st);
 }
 
+yh_status yh_shard_pixels(int width, int height, int rank, int world, int* pixels, int64_t* count) {
+  if (width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world || !count)
+    return fail(YH_ERR_INVALID, "yh_shard_pixels: bad argument");
+  std::vector<int> px = owned_pixels(width, height, rank, world);
+  if (pixels) memcpy(pixels, px.data(), px.size() * sizeof(int));
+  *count = (int64_t)px.size();
+  return YH_OK;
+}
+
 yh_status yh_state_set_profiling(yh_state* st, int enabled) {
   if (!st) return fail(YH_ERR_INVALID, "yh_state_set_profiling: state is null");
   st->profile = enabled != 0;
