@@ -184,6 +184,7 @@ def run_cuda(args):
     import torch
     import torch.distributed as dist
     from yocto_hair_b200 import _capi as capi
+    from yocto_hair_b200 import parallel
     from yocto_hair_b200.pathtrace import DeviceScene
     from yocto_hair_b200.scene import make_params
 
@@ -209,10 +210,6 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    class DevArray:  # view of a library-owned device buffer for torch.distributed
-        def __init__(self, ptr, shape, typestr):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
-
     # ---------------- resident arm: scene + state in HBM, device-timed -------------
     ds = DeviceScene(scene).init_bvh(args.max_split).init_lights()
     bvh = ds.bvh_stats()
@@ -236,13 +233,10 @@ def run_cuda(args):
         rays += s.rays; light_rays += s.light_rays; launches += s.launches; iters += s.iterations
     reduce_ms = 0.0
     if world > 1:  # one NCCL reduce of the fp32 accumulation buffers over NVLink, at the end
-        a_ptr, s_ptr = st.buffers_dev()
-        accum = torch.as_tensor(DevArray(a_ptr, (height, width, 4), "<f4"), device=f"cuda:{local}")
-        nsamp = torch.as_tensor(DevArray(s_ptr, (height, width), "<i4"), device=f"cuda:{local}")
+        accum, nsamp = parallel.state_tensors(st, f"cuda:{local}")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.reduce(accum, 0, op=dist.ReduceOp.SUM)
-        dist.reduce(nsamp, 0, op=dist.ReduceOp.SUM)
+        parallel.reduce_image(accum, nsamp, 0)
         e1.record()
         torch.cuda.synchronize()
         reduce_ms = e0.elapsed_time(e1)
