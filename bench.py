@@ -231,7 +231,7 @@ def run_cuda(args):
         s = st.trace_samples(spp)
         dev_ms += s.device_ms; trav_ms += s.traverse_ms; shade_ms += s.shade_ms
         rays += s.rays; light_rays += s.light_rays; launches += s.launches; iters += s.iterations
-    reduce_ms = 0.0
+    reduce_ms, reduce_ok = 0.0, None
     if world > 1:  # one NCCL reduce of the fp32 accumulation buffers over NVLink, at the end
         accum, nsamp = parallel.state_tensors(st, f"cuda:{local}")
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -240,6 +240,9 @@ def run_cuda(args):
         e1.record()
         torch.cuda.synchronize()
         reduce_ms = e0.elapsed_time(e1)
+        if rank == 0:  # after the reduce rank 0 holds the whole image: every pixel has all its samples
+            want = spp * (args.warmup + args.steps)
+            reduce_ok = bool((nsamp == want).all().item()) and bool(torch.isfinite(accum).all().item())
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - t_wall)
     clocks = sampler.stop() if rank == 0 else None
@@ -312,7 +315,7 @@ def run_cuda(args):
                                "node_bytes": bvh.node_bytes, "prim_bytes": bvh.prim_bytes, "max_split": args.max_split}},
             "mrays_per_sec": rays_all / (total_ms * 1e-3) / 1e6, "light_mrays_per_sec": light_rays_all / (total_ms * 1e-3) / 1e6,
             "rays_per_sample": rays_all / samples, "wall_ms_per_step": wall_max_ms / args.steps,
-            "traverse_ms": trav_max_ms, "shade_ms": shade_max_ms, "reduce_ms": reduce_ms,
+            "traverse_ms": trav_max_ms, "shade_ms": shade_max_ms, "reduce_ms": reduce_ms, "reduce_complete": reduce_ok,
             "gpu_launches": int(launches_all), "clocks": clocks, "render_mean": checksum,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": scene_bytes(scene) // args.steps,
                     "d2h_bytes_per_step": width * height * 16, "setup_ms": setup_ms,

@@ -1,0 +1,182 @@
+// yscenetrace on the B200 path: the reference's offline renderer command line
+// (apps/yscenetrace/yscenetrace.cpp:199-278: same flags, same JSON + PLY loading
+// through the reference's own yocto_sceneio, same image writers) with the
+// per-sample hot path running in the CUDA library behind include/yocto_hair_b200.h.
+//
+//   yscenetrace_b200 [--backend cuda|cpu] [--spp-batch N] [--seed S] [--device D]
+//                    [--camera NAME] [-r RES] [-s SAMPLES] [-t path] [-b BOUNCES]
+//                    [--clamp C] [--save-batch] [-o out.pfm] scene.json
+//
+// `--backend cpu` runs the reference's own functions on the same scene, for an
+// A/B comparison of the two backends on identical inputs (tests/test_dropin_gpu.py).
+#include <yocto/yocto_commonio.h>
+#include <yocto/yocto_image.h>
+#include <yocto/yocto_sceneio.h>
+#include <yocto/yocto_shape.h>
+#include <yocto_pathtrace/yocto_pathtrace.h>
+
+#include <chrono>
+#include <map>
+#include <memory>
+
+#include "yocto_pathtrace_b200.h"
+
+using namespace std::string_literals;
+namespace cli = yocto::commonio;
+namespace ptr = yocto::pathtrace;
+namespace gpu = yocto::pathtrace_b200;
+namespace sio = yocto::sceneio;
+namespace shp = yocto::shape;
+
+// sceneio::model -> pathtrace::scene through the reference's public setters
+// (the role of init_scene in apps/yscenetrace/yscenetrace.cpp:49-197).
+static ptr::camera* build_trace_scene(ptr::scene* scene, const sio::model* io, const sio::camera* wanted) {
+  std::map<const void*, ptr::texture*>  textures{{nullptr, nullptr}};
+  std::map<const void*, ptr::material*> materials{{nullptr, nullptr}};
+  std::map<const void*, ptr::shape*>    shapes{{nullptr, nullptr}};
+  ptr::camera* chosen = nullptr;
+  for (auto c : io->cameras) {
+    auto camera = ptr::add_camera(scene);
+    ptr::set_frame(camera, c->frame);
+    ptr::set_lens(camera, c->lens, c->aspect, c->film);
+    ptr::set_focus(camera, c->aperture, c->focus);
+    if (c == wanted) chosen = camera;
+  }
+  for (auto t : io->textures) {
+    auto texture = textures[t] = ptr::add_texture(scene);
+    if (!t->colorf.empty()) ptr::set_texture(texture, t->colorf);
+    else if (!t->colorb.empty()) ptr::set_texture(texture, t->colorb);
+    else if (!t->scalarf.empty()) ptr::set_texture(texture, t->scalarf);
+    else if (!t->scalarb.empty()) ptr::set_texture(texture, t->scalarb);
+  }
+  for (auto m : io->materials) {
+    auto material = materials[m] = ptr::add_material(scene);
+    ptr::set_emission(material, m->emission, textures.at(m->emission_tex));
+    ptr::set_color(material, m->color, textures.at(m->color_tex));
+    ptr::set_specular(material, m->specular, textures.at(m->specular_tex));
+    ptr::set_metallic(material, m->metallic, textures.at(m->metallic_tex));
+    ptr::set_roughness(material, m->roughness, textures.at(m->roughness_tex));
+    ptr::set_transmission(material, m->transmission, m->thin, m->trdepth, textures.at(m->transmission_tex));
+    ptr::set_scattering(material, m->scattering, m->scanisotropy, textures.at(m->scattering_tex));
+    ptr::set_opacity(material, m->opacity, textures.at(m->opacity_tex));
+    ptr::set_normalmap(material, textures.at(m->normal_tex));
+    ptr::set_ior(material, m->ior);
+    ptr::set_thin(material, m->thin);
+    ptr::set_sigma_a(material, m->sigma_a);
+    ptr::set_eumelanin(material, m->eumelanin);
+    ptr::set_pheomelanin(material, m->pheomelanin);
+    ptr::set_beta_m(material, m->beta_m);
+    ptr::set_beta_n(material, m->beta_n);
+    ptr::set_alpha(material, m->alpha);
+    ptr::set_eta(material, m->eta);
+  }
+  for (auto s : io->shapes) {
+    auto shape = shapes[s] = ptr::add_shape(scene);
+    ptr::set_positions(shape, s->positions);
+    ptr::set_normals(shape, s->normals);
+    ptr::set_texcoords(shape, s->texcoords);
+    ptr::set_radius(shape, s->radius);
+    ptr::set_points(shape, s->points);
+    ptr::set_lines(shape, s->lines);
+    ptr::set_triangles(shape, s->quads.empty() ? s->triangles : shp::quads_to_triangles(s->quads));
+  }
+  for (auto o : io->objects) {
+    if (o->subdiv) cli::print_fatal("subdivision surfaces are outside the hair hot path (object " + o->name + ")");
+    auto frames = o->instance ? o->instance->frames : std::vector<yocto::math::frame3f>{yocto::math::identity3x4f};
+    for (auto& f : frames) {
+      auto object = ptr::add_object(scene);
+      ptr::set_frame(object, o->instance ? f * o->frame : o->frame);
+      ptr::set_shape(object, shapes.at(o->shape));
+      ptr::set_material(object, materials.at(o->material));
+    }
+  }
+  for (auto e : io->environments) {
+    auto environment = ptr::add_environment(scene);
+    ptr::set_frame(environment, e->frame);
+    ptr::set_emission(environment, e->emission, textures.at(e->emission_tex));
+  }
+  return chosen;
+}
+
+int main(int argc, const char* argv[]) {
+  auto params      = ptr::trace_params{};
+  auto save_batch  = false;
+  auto camera_name = ""s;
+  auto imfilename  = "out.hdr"s;
+  auto filename    = "scene.json"s;
+  auto backend     = "cuda"s;
+  auto spp_batch   = 16;
+  auto device      = 0;
+  auto seed        = (int)ptr::default_seed;
+
+  auto cli = cli::make_cli("yscenetrace_b200", "Offline hair path tracing on B200");
+  add_option(cli, "--backend", backend, "cuda (B200 library) or cpu (the reference's own code).");
+  add_option(cli, "--spp-batch", spp_batch, "Samples per pixel per device call.");
+  add_option(cli, "--device", device, "CUDA device.");
+  add_option(cli, "--seed", seed, "Render seed (trace_params::seed).");
+  add_option(cli, "--camera", camera_name, "Camera name.");
+  add_option(cli, "--resolution,-r", params.resolution, "Image resolution.");
+  add_option(cli, "--samples,-s", params.samples, "Number of samples.");
+  add_option(cli, "--shader,-t", params.shader, "Shader type.", ptr::shader_names);
+  add_option(cli, "--bounces,-b", params.bounces, "Maximum number of bounces.");
+  add_option(cli, "--clamp", params.clamp, "Final pixel clamping.");
+  add_option(cli, "--save-batch", save_batch, "Save images progressively");
+  add_option(cli, "--output-image,-o", imfilename, "Image filename");
+  add_option(cli, "scene", filename, "Scene filename", true);
+  parse_cli(cli, argc, argv);
+  params.seed = (uint64_t)(unsigned)seed;
+  if (backend != "cuda" && backend != "cpu") cli::print_fatal("unknown backend " + backend);
+  const bool on_gpu = backend == "cuda";
+
+  auto ioscene = std::make_unique<sio::model>();
+  auto ioerror = ""s;
+  if (!load_scene(filename, ioscene.get(), ioerror, cli::print_progress)) cli::print_fatal(ioerror);
+  auto scene  = std::make_unique<ptr::scene>();
+  auto camera = build_trace_scene(scene.get(), ioscene.get(), get_camera(ioscene.get(), camera_name));
+  ioscene.reset();
+
+  auto clock = [] { return std::chrono::steady_clock::now(); };
+  auto secs  = [](auto a, auto b) { return std::chrono::duration<double>(b - a).count(); };
+  auto state = std::make_unique<ptr::state>();
+  auto t0    = clock();
+  try {
+    if (on_gpu) {
+      auto opts   = gpu::device_options{};
+      opts.device = device;
+      gpu::set_device_options(opts);
+      gpu::init_bvh(scene.get(), params, cli::print_progress);
+      gpu::init_lights(scene.get(), params, cli::print_progress);
+      gpu::init_state(state.get(), scene.get(), camera, params);
+    } else {
+      ptr::init_subdivs(scene.get(), params, cli::print_progress);
+      ptr::init_bvh(scene.get(), params, cli::print_progress);
+      ptr::init_lights(scene.get(), params, cli::print_progress);
+      ptr::init_state(state.get(), scene.get(), camera, params);
+    }
+    auto t1 = clock();
+    if (save_batch || !on_gpu) spp_batch = 1;
+    for (auto sample = 0; sample < params.samples;) {
+      cli::print_progress("render image", sample, params.samples);
+      auto n = std::min(spp_batch, params.samples - sample);
+      if (on_gpu) gpu::trace_samples(state.get(), scene.get(), camera, params, n);
+      else ptr::trace_samples(state.get(), scene.get(), camera, params);
+      sample += n;
+      if (save_batch) {
+        auto dot  = imfilename.rfind('.');  // <name>-s<k>.<ext>, as the reference names its batches
+        auto stem = dot == std::string::npos ? imfilename : imfilename.substr(0, dot);
+        auto ext  = dot == std::string::npos ? ""s : imfilename.substr(dot);
+        if (!save_image(stem + "-s" + std::to_string(sample - 1) + ext, state->render, ioerror)) cli::print_fatal(ioerror);
+      }
+    }
+    cli::print_progress("render image", params.samples, params.samples);
+    auto   t2      = clock();
+    double samples = (double)state->render.count() * params.samples;
+    printf("backend %s: setup %.3f s, render %.3f s, %.3f Msamples/s\n", backend.c_str(), secs(t0, t1), secs(t1, t2),
+        samples / secs(t1, t2) / 1e6);
+  } catch (const std::exception& e) {
+    cli::print_fatal(e.what());
+  }
+  if (!save_image(imfilename, state->render, ioerror)) cli::print_fatal(ioerror);
+  if (on_gpu) gpu::release(scene.get());
+  return 0;
+}

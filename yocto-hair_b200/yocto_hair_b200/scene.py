@@ -120,6 +120,8 @@ class Camera:
     film: tuple = (0.036, 0.024)
     focus: float = 10000
     aperture: float = 0
+    aspect: float = 1.5      # the (aspect, film) pair `film` was derived from (scene JSON keys)
+    film_size: float = 0.036
 
     @staticmethod
     def from_lookat(eye, center, up=(0, 1, 0), lens=0.05, aspect=1.0, film=0.036, aperture=0.0):
@@ -131,7 +133,8 @@ class Camera:
         focus = float(np.sqrt(np.float32(d[0] * d[0] + d[1] * d[1]) + np.float32(d[2] * d[2])))
         filmv = (film, np.float32(film) / np.float32(aspect)) if aspect >= 1 else (np.float32(film) * np.float32(aspect), film)
         return Camera(frame=lookat_frame(eye, center, up), lens=lens,
-                      film=(float(filmv[0]), float(filmv[1])), focus=focus, aperture=aperture)
+                      film=(float(filmv[0]), float(filmv[1])), focus=focus, aperture=aperture,
+                      aspect=float(aspect), film_size=float(film))
 
     def to_desc(self) -> capi.CameraDesc:
         d = capi.CameraDesc()
