@@ -191,6 +191,9 @@ def run_cuda(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL's version banner) write to fd 1: keep the real stdout for the ONE JSON line
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
@@ -202,7 +205,21 @@ def run_cuda(args):
     scene, cam, res, text = build_workload(args.workload, args.sky)
     params = make_params(resolution=res)
     spp = args.spp_step
-    n_steps = args.warmup + args.steps
+    # sharding: image tiles keep the reference's one-stream-per-pixel RNG (bit-identical images) but a pixel's
+    # samples are sequential, so the wavefront narrows with 1/N; sample-range sharding keeps it full width
+    # (counter-mode streams).  auto = tiles on one GPU, samples on several.
+    shard = args.shard if args.shard != "auto" else ("tiles" if world == 1 else "samples")
+    if shard == "samples" and spp % world:
+        raise SystemExit(f"--spp-step {spp} must be a multiple of the number of GPUs for sample sharding")
+    spp_rank = spp // world if shard == "samples" else spp
+
+    def make_state(ds):
+        st = ds.init_state(cam, params)
+        if shard == "samples":
+            st.set_sample_shard(rank, world)
+        elif world > 1:
+            st.set_shard(rank, world)
+        return st
 
     def barrier():
         torch.cuda.synchronize()
@@ -213,13 +230,11 @@ def run_cuda(args):
     # ---------------- resident arm: scene + state in HBM, device-timed -------------
     ds = DeviceScene(scene).init_bvh(args.max_split).init_lights()
     bvh = ds.bvh_stats()
-    st = ds.init_state(cam, params)
-    if world > 1:
-        st.set_shard(rank, world)
+    st = make_state(ds)
     st.set_profiling(True)
     width, height = st.width, st.height
     for _ in range(args.warmup):
-        st.trace_samples(spp)
+        st.trace_samples(spp_rank)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -228,7 +243,7 @@ def run_cuda(args):
     rays = light_rays = launches = iters = 0
     t_wall = time.perf_counter()
     for _ in range(args.steps):
-        s = st.trace_samples(spp)
+        s = st.trace_samples(spp_rank)
         dev_ms += s.device_ms; trav_ms += s.traverse_ms; shade_ms += s.shade_ms
         rays += s.rays; light_rays += s.light_rays; launches += s.launches; iters += s.iterations
     reduce_ms, reduce_ok = 0.0, None
@@ -263,12 +278,10 @@ def run_cuda(args):
     barrier()
     t0 = time.perf_counter()
     ds2 = DeviceScene(scene).init_bvh(args.max_split).init_lights()
-    st2 = ds2.init_state(cam, params)
-    if world > 1:
-        st2.set_shard(rank, world)
+    st2 = make_state(ds2)
     setup_ms = 1e3 * (time.perf_counter() - t0)
     for _ in range(args.steps):
-        st2.trace_samples(spp)
+        st2.trace_samples(spp_rank)
         st2.download_into(render_host)
     barrier()
     e2e_ms = torch.tensor([1e3 * (time.perf_counter() - t0)], dtype=torch.float64, device=f"cuda:{local}")
@@ -308,7 +321,8 @@ def run_cuda(args):
             "metric": "samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": text, "spp_per_step": spp, "sky_texture": args.sky, "parallelism": f"tiles{world}",
+            "config": {"workload": text, "spp_per_step": spp, "sky_texture": args.sky, "parallelism": f"{shard}{world}",
+                       "rng": "counter (per-sample PCG32 streams)" if shard == "samples" else "reference (one PCG32 stream per pixel)",
                        "l2_policy": "working set larger than L2 is not guaranteed; rays are regenerated every step "
                                     "(no input is re-read), see DESIGN.md",
                        "bvh": {"prims": bvh.num_primitives, "refs": bvh.num_references, "nodes": bvh.num_nodes,
@@ -323,7 +337,8 @@ def run_cuda(args):
                             "yh_state_create + K x (yh_trace_samples + yh_state_download into pinned host memory)"},
             "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
@@ -338,6 +353,8 @@ def main():
     ap.add_argument("--spp-step", type=int, default=16, help="samples per pixel per step (CUDA arm)")
     ap.add_argument("--ref-spp-step", type=int, default=2, help="samples per pixel per step (reference arm)")
     ap.add_argument("--max-split", type=int, default=0)
+    ap.add_argument("--shard", default="auto", choices=["auto", "tiles", "samples"],
+                    help="multi-GPU sharding: image tiles (reference RNG streams) or sample ranges (counter-mode streams)")
     ap.add_argument("--no-sky", dest="sky", action="store_false", help="uniform environment instead of the sky texture")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -196,6 +196,19 @@ yh_status yh_state_size(const yh_state* state, int* width, int* height);
  * `world` (32x32 tiles, round-robin).  Every pixel keeps its own RNG stream,
  * so the union over ranks is bit-identical to a single-device render.       */
 yh_status yh_state_set_shard(yh_state* state, int rank, int world);
+/* Sample-range sharding (the alternative north_star names): this state renders
+ * EVERY pixel but only the samples with index s = rank, rank + world, ... of each
+ * pixel.  Needs per-sample random streams, so it switches the state to COUNTER
+ * MODE: sample s of a pixel draws from its own PCG32 stream
+ *     make_rng(params.seed, seq_pixel + (s << 31))      (yocto_math.h:1419-1427)
+ * where seq_pixel is the reference's per-pixel sequence of init_state (:1943).
+ * Sample 0 therefore equals the reference's first sample bit for bit; later
+ * samples are statistically equivalent (the reference continues ONE stream per
+ * pixel, which makes a pixel's samples strictly sequential).  The per-rank
+ * accumulation / count buffers add up (yh_state_buffers_dev + one reduce) to the
+ * world = 1 counter-mode image up to fp32 summation order.  world = 1 is valid
+ * (counter mode on one device).  Resets the accumulation.                     */
+yh_status yh_state_set_sample_shard(yh_state* state, int rank, int world);
 /* The ownership map behind yh_state_set_shard, host only (needs no device):
  * writes the image pixel indices (j * width + i) owned by `rank` of `world`,
  * in slot order, to `pixels` (may be null) and their number to `count`.

@@ -78,6 +78,9 @@ class _Oracle:
         ]:
             f = self._fn(name)
             f.restype, f.argtypes = res, args
+        if self.kind == "port":  # the library's own counter mode, restated in the port only
+            f = self._fn("state_set_sample_shard")
+            f.restype, f.argtypes = None, [_P, C.c_int, C.c_int]
 
     # ---- hair BSDF ----------------------------------------------------------
     def hair_brdf(self, materials, v, normals, tangents):
@@ -160,6 +163,11 @@ class _OracleState:
         w, h = C.c_int(), C.c_int()
         self.o._fn("state_size")(self.handle, C.byref(w), C.byref(h))
         self.width, self.height = w.value, h.value
+
+    def set_sample_shard(self, rank: int, world: int):
+        """Counter-mode streams (port only; not a reference feature)."""
+        self.o._fn("state_set_sample_shard")(self.handle, rank, world)
+        return self
 
     def trace_samples(self, n: int) -> float:
         """Runs n passes of trace_samples; returns seconds inside the loop."""

@@ -1014,7 +1014,7 @@ static float sample_lights_pdf(const scene_t* sc, v3 position, v3 direction) { /
 }
 
 /* ================================================================ renderer == */
-typedef struct { float accum[4]; int samples; rng_t rng; } pixel_t; /* pt header :419-423 */
+typedef struct { float accum[4]; int samples; rng_t rng; uint64_t seq; } pixel_t; /* pt header :419-423 (+ seq: init_state's sequence id) */
 typedef struct {
   const scene_t* sc;
   fr3 cam_frame; float lens, film[2], focus, aperture;
@@ -1023,6 +1023,11 @@ typedef struct {
   pixel_t* px;
   float*   render;
   volatile int next_row;
+  /* NOT in the reference: the sample-sharded "counter mode" of the CUDA library
+   * (include/yocto_hair_b200.h, yh_state_set_sample_shard), restated here so the
+   * device path can be checked bit for bit.  Sample s of a pixel draws from
+   * make_rng(seed, seq_pixel + (s << 31)); this state renders s = srank + k * sworld. */
+  int counter, srank, sworld;
 } state_t;
 
 static ray_t camera_ray(const state_t* st, int i, int j, v2 puv, v2 luv) { /* pt:211-229 */
@@ -1126,6 +1131,10 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
 
 static void trace_pixel(state_t* st, int i, int j) { /* trace_sample, pt:1676-1689 */
   pixel_t* px = &st->px[(size_t)j * st->w + i];
+  if (st->counter) {
+    uint64_t s = (uint64_t)st->srank + (uint64_t)st->sworld * (uint64_t)px->samples;
+    px->rng = rng_make(st->params.seed, px->seq + (s << 31));
+  }
   v2 luv = rng_2f(&px->rng); /* right-to-left argument evaluation: lens sample first */
   v2 puv = rng_2f(&px->rng);
   ray_t ray = camera_ray(st, i, j, puv, luv);
@@ -1161,13 +1170,28 @@ void* yho_state_create(void* scene, const yh_camera_desc* c, const yh_trace_para
   st->px = (pixel_t*)calloc(n ? n : 1, sizeof(pixel_t));
   st->render = (float*)calloc(n ? n : 1, 16);
   rng_t master = rng_make(1301081, 1);
-  for (size_t i = 0; i < n; i++) st->px[i].rng = rng_make(p->seed, (uint64_t)(rng_1i(&master, 1 << 31) / 2 + 1));
+  for (size_t i = 0; i < n; i++) {
+    st->px[i].seq = (uint64_t)(rng_1i(&master, 1 << 31) / 2 + 1);
+    st->px[i].rng = rng_make(p->seed, st->px[i].seq);
+  }
+  st->counter = 0, st->srank = 0, st->sworld = 1;
   return st;
 }
 void yho_state_destroy(void* h) {
   state_t* st = (state_t*)h;
   if (!st) return;
   free(st->px), free(st->render), free(st);
+}
+void yho_state_set_sample_shard(void* h, int rank, int world) { /* counter mode, see state_t */
+  state_t* st = (state_t*)h;
+  st->counter = 1, st->srank = rank, st->sworld = world;
+  size_t n = (size_t)st->w * st->h;
+  for (size_t i = 0; i < n; i++) {
+    memset(st->px[i].accum, 0, 16);
+    st->px[i].samples = 0;
+    st->px[i].rng = rng_make(st->params.seed, st->px[i].seq);
+  }
+  memset(st->render, 0, 16 * n);
 }
 void yho_state_size(void* h, int* w, int* hgt) { *w = ((state_t*)h)->w, *hgt = ((state_t*)h)->h; }
 double yho_trace_samples(void* h, int nsamples) { /* trace_samples, pt:1992-2007, nsamples passes */

@@ -247,3 +247,65 @@ def test_full_size_properties(ref):
         st.close()
     assert np.array_equal(cnt, s_full) and np.array_equal(acc.view(np.uint32), a_full.view(np.uint32))
     full.close(); ds.close()
+
+
+def test_counter_mode_bit_identical_to_port_and_shards_add_up(port, ref):
+    """yh_state_set_sample_shard: per-sample streams make_rng(seed, seq_pixel + (s << 31)).
+    world = 1 must equal the port's restatement of the same rule bit for bit (and the
+    reference itself at 1 spp); the sample shards of world = 4 must add up to it."""
+    scene, cam = synth.curly_hair_scene(30_000)
+    p = make_params(resolution=128)
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    rp = port.scene(scene)
+    sd, sp = ds.init_state(cam, p).set_sample_shard(0, 1), rp.state(cam, p).set_sample_shard(0, 1)
+    sd.trace_samples(1), sp.trace_samples(1)
+    if ref.kind == "reference":
+        rr = ref.scene(scene)
+        sr = rr.state(cam, p)
+        sr.trace_samples(1)
+        assert np.array_equal(sr.download()[1].view(np.uint32), sd.download()[1].view(np.uint32))
+        sr.close(); rr.close()
+    sd.trace_samples(7), sp.trace_samples(7)
+    _, a_d, s_d = sd.download()
+    _, a_p, s_p, rng_p = sp.download()
+    assert np.array_equal(s_d, s_p) and (s_d == 8).all()
+    assert np.array_equal(a_d.view(np.uint32), a_p.view(np.uint32))
+    assert np.array_equal(sd.rng(), rng_p)
+    acc, cnt = np.zeros_like(a_d, dtype=np.float64), np.zeros_like(s_d)
+    for rank in range(4):
+        st = ds.init_state(cam, p).set_sample_shard(rank, 4)
+        st.trace_samples(2)
+        _, a, s = st.download()
+        acc += a
+        cnt += s
+        # shard `rank` alone == the port's shard `rank`
+        spr = rp.state(cam, p).set_sample_shard(rank, 4)
+        spr.trace_samples(2)
+        assert np.array_equal(a.view(np.uint32), spr.download()[1].view(np.uint32))
+        spr.close(); st.close()
+    assert np.array_equal(cnt, s_d)
+    assert np.allclose(acc, a_d, rtol=2e-6, atol=1e-6)
+    sd.close(); sp.close(); rp.close(); ds.close()
+
+
+def test_counter_mode_converges_to_the_reference_image(ref):
+    """Same rel-MSE criterion as test_converged_image_rel_mse, for counter-mode streams."""
+    scene, cam = synth.curly_hair_scene(40_000)
+    spp, res = 96, 128
+    rs = ref.scene(scene)
+    imgs = {}
+    for tag, seed in (("A", 961748941), ("B", 20240229)):
+        st = rs.state(cam, make_params(resolution=res, seed=seed))
+        st.trace_samples(spp)
+        imgs[tag] = st.download()[0]
+        st.close()
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    st = ds.init_state(cam, make_params(resolution=res, seed=4242)).set_sample_shard(0, 1)
+    st.trace_samples(spp)
+    gpu = st.render()
+    floor, err = rel_mse(imgs["B"], imgs["A"]), rel_mse(gpu, imgs["A"])
+    lum = lambda im: float((im[..., :3] @ np.array([0.2126, 0.7152, 0.0722])).mean())  # noqa: E731
+    print("counter mode: relMSE gpu-vs-A %.4g, B-vs-A %.4g, mean lum gpu %.5f A %.5f" % (err, floor, lum(gpu), lum(imgs["A"])))
+    assert err <= 1.5 * floor
+    assert abs(lum(gpu) / lum(imgs["A"]) - 1) <= 5e-3
+    st.close(); ds.close(); rs.close()

@@ -44,6 +44,7 @@ struct path_state {
   int4*               hit;       // object, element, u bits, v bits
   unsigned long long* rng_state;
   unsigned long long* rng_inc;
+  unsigned long long* rng_base;   // increment of the pixel's reference stream (counter mode re-seeds from it)
   int*                remaining;  // samples still to start for this slot in this call
   int*                pixel;      // image pixel index j * width + i
   float4*             accum;      // image layout, pixel.accumulated
@@ -64,6 +65,10 @@ struct queues {
 struct trace_consts {
   int   width, height, bounces;
   float clamp;
+  // counter mode (yh_state_set_sample_shard): sample s of a pixel draws from its own PCG32
+  // stream make_rng(seed, seq_pixel + (s << 31)); this state renders s = srank, srank + sworld, ...
+  int                counter, srank, sworld;
+  unsigned long long seed;
 };
 
 // Path state is touched once per wavefront iteration and is larger than L2
@@ -106,7 +111,15 @@ __device__ __forceinline__ ray3f camera_ray(const dev_camera& cam, const trace_c
 }
 
 __device__ __forceinline__ void start_sample(const path_state& ps, const dev_camera& cam, const trace_consts& tc,
-    int slot, rng_state& rng) {
+    int slot, rng_state& rng, int samples_done) {
+  if (tc.counter) {
+    // make_rng(seed, seq) (yocto_math.h:1419-1427) in closed form: inc = (seq << 1) | 1,
+    // state = (inc + seed) * mult + inc; seq = seq_pixel + (s << 31) shifts inc by s << 32
+    unsigned long long sidx = (unsigned long long)tc.srank + (unsigned long long)tc.sworld * (unsigned long long)samples_done;
+    rng.inc   = ld_stream(&ps.rng_base[slot]) + (sidx << 32);
+    rng.state = (rng.inc + tc.seed) * 6364136223846793005ULL + rng.inc;
+    st_stream(&ps.rng_inc[slot], rng.inc);
+  }
   ray3f ray       = camera_ray(cam, tc, ld_stream(&ps.pixel[slot]), rng);
   st_stream(&ps.ray_o[slot], make_float4(ray.o.x, ray.o.y, ray.o.z, 0));
   st_stream(&ps.ray_d[slot], make_float4(ray.d.x, ray.d.y, ray.d.z, 0));
@@ -124,11 +137,12 @@ __device__ __forceinline__ bool finish_sample(const path_state& ps, const dev_ca
   float4 a  = ld_stream(&ps.accum[px]);
   a.x += radiance.x, a.y += radiance.y, a.z += radiance.z, a.w += alpha;
   st_stream(&ps.accum[px], a);
-  st_stream(&ps.samples[px], ld_stream(&ps.samples[px]) + 1);
+  int done = ld_stream(&ps.samples[px]) + 1;
+  st_stream(&ps.samples[px], done);
   int left = ld_stream(&ps.remaining[slot]);
   if (left > 0) {
     st_stream(&ps.remaining[slot], left - 1);
-    start_sample(ps, cam, tc, slot, rng);
+    start_sample(ps, cam, tc, slot, rng, done);
     return true;
   }
   return false;
@@ -142,13 +156,21 @@ __global__ void __launch_bounds__(256) k_start(path_state ps, queues q, dev_came
     rng_state rng = {ld_stream(&ps.rng_state[slot]), ld_stream(&ps.rng_inc[slot])};
     if (tc.bounces <= 0) {
       // the path loop (:1395) never runs: black sample, alpha 0, camera draws still consumed
-      int px = ld_stream(&ps.pixel[slot]);
-      for (int s = 0; s < num_samples; s++) camera_ray(cam, tc, px, rng);
-      st_stream(&ps.samples[px], ld_stream(&ps.samples[px]) + num_samples);
+      int px = ld_stream(&ps.pixel[slot]), done = ld_stream(&ps.samples[px]);
+      for (int s = 0; s < num_samples; s++) {
+        if (tc.counter) {  // same re-seed as start_sample
+          unsigned long long sidx = (unsigned long long)tc.srank + (unsigned long long)tc.sworld * (unsigned long long)(done + s);
+          rng.inc   = ld_stream(&ps.rng_base[slot]) + (sidx << 32);
+          rng.state = (rng.inc + tc.seed) * 6364136223846793005ULL + rng.inc;
+          st_stream(&ps.rng_inc[slot], rng.inc);
+        }
+        camera_ray(cam, tc, px, rng);
+      }
+      st_stream(&ps.samples[px], done + num_samples);
       live = false;
     } else {
       st_stream(&ps.remaining[slot], num_samples - 1);
-      start_sample(ps, cam, tc, slot, rng);
+      start_sample(ps, cam, tc, slot, rng, ld_stream(&ps.samples[ld_stream(&ps.pixel[slot])]));
     }
     st_stream(&ps.rng_state[slot], rng.state);
   }
@@ -416,6 +438,7 @@ __global__ void k_init_slots(path_state ps, const int* slot_pixel, int num_slots
   rng_state rng    = make_rng(seed, (uint64_t)(r / 2 + 1));
   st_stream(&ps.rng_state[slot], rng.state);
   st_stream(&ps.rng_inc[slot], rng.inc);
+  st_stream(&ps.rng_base[slot], rng.inc);
   st_stream(&ps.pixel[slot], px);
   st_stream(&ps.remaining[slot], 0);
 }
@@ -475,9 +498,11 @@ struct yh_state {
   yh_trace_params params{};
   int             width = 0, height = 0, num_slots = 0;
   int             rank = 0, world = 1;
+  bool            counter = false;          // per-sample streams (yh_state_set_sample_shard)
+  int             srank = 0, sworld = 1;    // sample indices srank, srank + sworld, ... are rendered here
   dev_buffer<float4>             ray_o, ray_d, weight, radiance, accum, render;
   dev_buffer<int4>               hit;
-  dev_buffer<unsigned long long> rng_state, rng_inc, stats;
+  dev_buffer<unsigned long long> rng_state, rng_inc, rng_base, stats;
   dev_buffer<int>                remaining, pixel, samples, q_active0, q_active1, q_miss, q_surface, q_hair, q_count;
   dev_buffer<unsigned> sort_keys0, sort_keys1;
   dev_buffer<int>      sort_vals;
@@ -489,8 +514,8 @@ struct yh_state {
   bool            profile = false;
   yh_trace_stats  last{};
   path_state      ps() {
-    return {ray_o.ptr, ray_d.ptr, weight.ptr, radiance.ptr, hit.ptr, rng_state.ptr, rng_inc.ptr, remaining.ptr,
-        pixel.ptr, accum.ptr, samples.ptr};
+    return {ray_o.ptr, ray_d.ptr, weight.ptr, radiance.ptr, hit.ptr, rng_state.ptr, rng_inc.ptr, rng_base.ptr,
+        remaining.ptr, pixel.ptr, accum.ptr, samples.ptr};
   }
   queues qs() { return {{q_active0.ptr, q_active1.ptr}, q_miss.ptr, q_surface.ptr, q_hair.ptr, q_count.ptr, stats.ptr}; }
   ~yh_state() {
@@ -533,6 +558,7 @@ static yh_status assign_slots(yh_state* st) {
   YH_CUDA(st->hit.alloc(n));
   YH_CUDA(st->rng_state.alloc(n));
   YH_CUDA(st->rng_inc.alloc(n));
+  YH_CUDA(st->rng_base.alloc(n));
   YH_CUDA(st->remaining.alloc(n));
   YH_CUDA(st->pixel.alloc(n));
   YH_CUDA(st->q_active0.alloc(n));
@@ -615,6 +641,17 @@ yh_status yh_state_set_shard(yh_state* st, int rank, int world) {
   YH_REQUIRE_DEVICE();
   if (!st || world <= 0 || rank < 0 || rank >= world) return fail(YH_ERR_INVALID, "yh_state_set_shard: bad rank/world");
   st->rank = rank, st->world = world;
+  st->counter = false, st->srank = 0, st->sworld = 1;
+  cudaMemset(st->accum.ptr, 0, st->accum.bytes());
+  cudaMemset(st->samples.ptr, 0, st->samples.bytes());
+  return assign_slots(st);
+}
+
+yh_status yh_state_set_sample_shard(yh_state* st, int rank, int world) {
+  YH_REQUIRE_DEVICE();
+  if (!st || world <= 0 || rank < 0 || rank >= world) return fail(YH_ERR_INVALID, "yh_state_set_sample_shard: bad rank/world");
+  st->rank = 0, st->world = 1;  // every pixel is rendered here ...
+  st->counter = true, st->srank = rank, st->sworld = world;  // ... for the sample indices of this rank
   cudaMemset(st->accum.ptr, 0, st->accum.bytes());
   cudaMemset(st->samples.ptr, 0, st->samples.bytes());
   return assign_slots(st);
@@ -643,7 +680,8 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
   dev_scene    sc = st->scene->view();
   path_state   ps = st->ps();
   queues       q  = st->qs();
-  trace_consts tc = {st->width, st->height, st->params.bounces, st->params.clamp};
+  trace_consts tc = {st->width, st->height, st->params.bounces, st->params.clamp, st->counter ? 1 : 0, st->srank, st->sworld,
+      (unsigned long long)st->params.seed};
   cudaStream_t s  = st->stream;
   int          sms = sm_count();
   YH_CUDA(cudaMemsetAsync(q.count, 0, 8 * sizeof(int), s));

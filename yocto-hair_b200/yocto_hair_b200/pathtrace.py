@@ -130,6 +130,11 @@ class DeviceState:
         capi.check(self.lib.yh_state_set_shard(self.handle, rank, world))
         return self
 
+    def set_sample_shard(self, rank: int, world: int) -> "DeviceState":
+        """Counter-mode streams + sample-range sharding (yh_state_set_sample_shard)."""
+        capi.check(self.lib.yh_state_set_sample_shard(self.handle, rank, world))
+        return self
+
     def set_profiling(self, enabled: bool = True) -> "DeviceState":
         capi.check(self.lib.yh_state_set_profiling(self.handle, int(enabled)))
         return self
