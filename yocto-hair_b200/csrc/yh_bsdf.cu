@@ -36,6 +36,17 @@ bool require_device() {
   }
   return true;
 }
+void pool_keep_memory() {
+  static thread_local int done_for = -1;
+  int                     dev      = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    unsigned long long keep = ~0ull;  // never trim on synchronise: the pool is the allocator's cache
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done_for = dev;
+}
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int                     dev        = 0;

@@ -28,6 +28,9 @@ bool         require_device();
     if (!yh::require_device()) return YH_ERR_NO_DEVICE; \
   } while (0)
 
+// raises the release threshold of the current device's default memory pool (once per device)
+void pool_keep_memory();
+
 // device buffer with RAII (host-side owner)
 template <typename T>
 struct dev_buffer {
@@ -37,8 +40,12 @@ struct dev_buffer {
   dev_buffer(const dev_buffer&)            = delete;
   dev_buffer& operator=(const dev_buffer&) = delete;
   ~dev_buffer() { release(); }
+  // Allocations come from the device's default memory pool (stream-ordered allocator on the
+  // legacy stream, followed by a synchronise so that any stream may use the memory); the pool
+  // keeps freed blocks (see pool_keep_memory()), so re-creating a scene or state does not pay
+  // cudaMalloc / cudaFree's map / unmap cost again (they were seen to take 100s of ms).
   void release() {
-    if (ptr) cudaFree(ptr);
+    if (ptr) cudaFreeAsync(ptr, 0);
     ptr   = nullptr;
     count = 0;
   }
@@ -46,7 +53,10 @@ struct dev_buffer {
     release();
     count = n;
     if (n == 0) return cudaSuccess;
-    return cudaMalloc((void**)&ptr, n * sizeof(T));
+    pool_keep_memory();
+    cudaError_t e = cudaMallocAsync((void**)&ptr, n * sizeof(T), 0);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(0);
   }
   cudaError_t upload(const T* host, size_t n) {
     cudaError_t e = alloc(n);

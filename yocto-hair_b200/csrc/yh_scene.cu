@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <future>
 
 #include "yh_scene.cuh"
 
@@ -253,6 +254,73 @@ struct ref_prim {
   vec3f center;
   int   primitive;
 };
+// one split of split_middle (yocto_pathtrace.cpp:564-595) on prims[start, end)
+static void reference_split(ref_prim* prims, int start, int end, int& mid, int& axis) {
+  axis = 0, mid = (start + end) / 2;
+  vec3f cmin = {flt_max, flt_max, flt_max}, cmax = {-flt_max, -flt_max, -flt_max};
+  for (int i = start; i < end; i++) cmin = min3(cmin, prims[i].center), cmax = max3(cmax, prims[i].center);
+  vec3f csize = cmax - cmin;
+  if (csize == vec3f{0, 0, 0}) return;
+  if (csize.x >= csize.y && csize.x >= csize.z) axis = 0;
+  if (csize.y >= csize.x && csize.y >= csize.z) axis = 1;
+  if (csize.z >= csize.x && csize.z >= csize.y) axis = 2;
+  vec3f cc     = (cmin + cmax) / 2.0f;
+  float middle = axis == 0 ? cc.x : (axis == 1 ? cc.y : cc.z);
+  int   ax     = axis;
+  auto  key    = [ax](const ref_prim& p) { return ax == 0 ? p.center.x : (ax == 1 ? p.center.y : p.center.z); };
+  mid = (int)(std::partition(prims + start, prims + end, [&](const ref_prim& p) { return key(p) < middle; }) - prims);
+  if (mid == start || mid == end) mid = (start + end) / 2;
+}
+// the subtree over prims[start, end) as a node list, root first, child indices local to the list
+// (child < 0: leaf of <= 4 primitives).  Iterative: split chains can be long for degenerate inputs.
+static void reference_subtree(ref_prim* prims, int start, int end, std::vector<int4>& nodes) {
+  nodes.clear();
+  if (end - start <= kRefLeafMax) return;
+  struct item { int node, start, end; };
+  std::vector<item> todo;
+  nodes.push_back({0, 0, -1, -1});
+  todo.push_back({0, start, end});
+  while (!todo.empty()) {
+    item it = todo.back();
+    todo.pop_back();
+    int axis, mid;
+    reference_split(prims, it.start, it.end, mid, axis);
+    int child[2];
+    int range[2][2] = {{it.start, mid}, {mid, it.end}};
+    for (int c = 0; c < 2; c++) {
+      if (range[c][1] - range[c][0] > kRefLeafMax) {
+        child[c] = (int)nodes.size();
+        nodes.push_back({0, 0, -1, -1});
+        todo.push_back({child[c], range[c][0], range[c][1]});
+      } else {
+        child[c] = -1;
+      }
+    }
+    nodes[it.node] = {mid, axis, child[0], child[1]};
+  }
+}
+// top levels in parallel: the two halves of a split are independent (disjoint ranges of prims)
+static std::vector<int4> reference_tree(ref_prim* prims, int start, int end, int depth) {
+  std::vector<int4> nodes;
+  if (depth >= 4 || end - start < (1 << 15)) {
+    reference_subtree(prims, start, end, nodes);
+    return nodes;
+  }
+  int axis, mid;
+  reference_split(prims, start, end, mid, axis);
+  auto left_future = std::async(std::launch::async, reference_tree, prims, start, mid, depth + 1);
+  std::vector<int4> right = reference_tree(prims, mid, end, depth + 1);
+  std::vector<int4> left  = left_future.get();
+  int lofs = 1, rofs = 1 + (int)left.size();
+  nodes.reserve(1 + left.size() + right.size());
+  nodes.push_back({mid, axis, left.empty() ? -1 : lofs, right.empty() ? -1 : rofs});
+  auto append = [&](const std::vector<int4>& sub, int ofs) {
+    for (int4 n : sub) nodes.push_back({n.x, n.y, n.z < 0 ? -1 : n.z + ofs, n.w < 0 ? -1 : n.w + ofs});
+  };
+  append(left, lofs);
+  append(right, rofs);
+  return nodes;
+}
 static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos, std::vector<int4>& tie_nodes) {
   bool lines = sh.is_lines();
   int  n     = sh.num_elems();
@@ -268,45 +336,7 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
     }
     prims[i] = {(b.min + b.max) / 2.0f, i};  // center(bbox), yocto_math.h:3008
   }
-  tie_nodes.clear();
-  struct item { int node, start, end; };
-  std::vector<item> todo;
-  if (n > kRefLeafMax) {
-    tie_nodes.push_back({0, 0, -1, -1});
-    todo.push_back({0, 0, n});
-  }
-  while (!todo.empty()) {
-    item it = todo.back();
-    todo.pop_back();
-    int axis = 0, mid = (it.start + it.end) / 2;
-    vec3f cmin = {flt_max, flt_max, flt_max}, cmax = {-flt_max, -flt_max, -flt_max};
-    for (int i = it.start; i < it.end; i++) cmin = min3(cmin, prims[i].center), cmax = max3(cmax, prims[i].center);
-    vec3f csize = cmax - cmin;
-    if (!(csize == vec3f{0, 0, 0})) {
-      if (csize.x >= csize.y && csize.x >= csize.z) axis = 0;
-      if (csize.y >= csize.x && csize.y >= csize.z) axis = 1;
-      if (csize.z >= csize.x && csize.z >= csize.y) axis = 2;
-      vec3f cc     = (cmin + cmax) / 2.0f;
-      float middle = axis == 0 ? cc.x : (axis == 1 ? cc.y : cc.z);
-      auto  key    = [axis](const ref_prim& p) { return axis == 0 ? p.center.x : (axis == 1 ? p.center.y : p.center.z); };
-      mid = (int)(std::partition(prims.data() + it.start, prims.data() + it.end,
-                      [&](const ref_prim& p) { return key(p) < middle; }) -
-                  prims.data());
-      if (mid == it.start || mid == it.end) mid = (it.start + it.end) / 2;
-    }
-    int child[2];
-    int range[2][2] = {{it.start, mid}, {mid, it.end}};
-    for (int c = 0; c < 2; c++) {
-      if (range[c][1] - range[c][0] > kRefLeafMax) {
-        child[c] = (int)tie_nodes.size();
-        tie_nodes.push_back({0, 0, -1, -1});
-        todo.push_back({child[c], range[c][0], range[c][1]});
-      } else {
-        child[c] = -1;
-      }
-    }
-    tie_nodes[it.node] = {mid, axis, child[0], child[1]};
-  }
+  tie_nodes = reference_tree(prims.data(), 0, n, 0);
   ref_pos.assign(n, 0);
   for (int i = 0; i < n; i++) ref_pos[prims[i].primitive] = i;
 }
@@ -317,13 +347,24 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   sh.root_leaf = 0, sh.num_refs = 0, sh.num_nodes = 0;
   sh.root_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   if (n == 0) return YH_OK;
-  {
-    std::vector<int>  ref_pos;
-    std::vector<int4> tie_nodes;
-    reference_tree_order(sh, ref_pos, tie_nodes);
-    YH_CUDA(sh.d_ref_pos.upload(ref_pos.data(), ref_pos.size()));
-    YH_CUDA(sh.d_tie_nodes.upload(tie_nodes.data(), tie_nodes.size()));
-  }
+  // the reference's leaf order is a host computation (it depends on std::partition); it runs in
+  // host threads while the device builds the LBVH below, and is uploaded at the end
+  struct tie_tables { std::vector<int> ref_pos; std::vector<int4> tie_nodes; };
+  auto tie_future = std::async(std::launch::async, [&sh]() {
+    tie_tables t;
+    reference_tree_order(sh, t.ref_pos, t.tie_nodes);
+    return t;
+  });
+  auto upload_ties = [&]() -> yh_status {
+    tie_tables t = tie_future.get();
+    YH_CUDA(sh.d_ref_pos.upload(t.ref_pos.data(), t.ref_pos.size()));
+    YH_CUDA(sh.d_tie_nodes.upload(t.tie_nodes.data(), t.tie_nodes.size()));
+    return YH_OK;
+  };
+  struct tie_guard {  // an early return must still join the host thread before `sh` can go away
+    std::future<tie_tables>& f;
+    ~tie_guard() { if (f.valid()) f.wait(); }
+  } guard{tie_future};
   if (!lines) max_split = 1;
   const int B = 256;
   auto      G = [&](int c) { return (c + B - 1) / B; };
@@ -410,7 +451,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
     int zero = 0;
     YH_CUDA(cudaMemcpy(sh.d_slots.ptr, rec, 32, cudaMemcpyHostToDevice));
     YH_CUDA(cudaMemcpy(sh.d_slot_elem.ptr, &zero, 4, cudaMemcpyHostToDevice));
-    return YH_OK;
+    return upload_ties();
   }
   sh.root_leaf = 0;
 
@@ -439,7 +480,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   YH_CUDA(cudaMemcpy(&rb, node_box.ptr, sizeof(rb), cudaMemcpyDeviceToHost));
   sh.root_bbox = {{rb.lo.x, rb.lo.y, rb.lo.z}, {rb.hi.x, rb.hi.y, rb.hi.z}};
   YH_CUDA(cudaDeviceSynchronize());
-  return YH_OK;
+  return upload_ties();
 }
 
 // transform_bbox(frame, bbox), yocto_math.h:3172-3182, plus padding

@@ -20,9 +20,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
-
-#include <cub/cub.cuh>
 
 #include "yh_shade.cuh"
 
@@ -383,31 +382,6 @@ __global__ void __launch_bounds__(kTraceBlock, YH_SHADE_BLOCKS) k_shade(dev_scen
   if (light_rays) atomicAdd(q.stats + 1, (unsigned long long)light_rays);
 }
 
-// Sort key of one queued ray: 30-bit Morton code of its origin inside the scene
-// bounds (rays that start close together walk the same part of the tree, so a
-// warp's node fetches share cache lines).  Entries past the queue's end get the
-// largest key.
-__device__ __forceinline__ unsigned spread10(unsigned v) {
-  v = (v | (v << 16)) & 0x030000ffu;
-  v = (v | (v << 8)) & 0x0300f00fu;
-  v = (v | (v << 4)) & 0x030c30c3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
-}
-__global__ void k_ray_keys(path_state ps, const int* queue, const int* count, int capacity, vec3f lo, vec3f inv,
-    unsigned* keys) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= capacity) return;
-  unsigned key = 0xffffffffu;
-  if (i < *count) {
-    float4 o = ld_stream(&ps.ray_o[queue[i]]);
-    auto   q = [](float v) { return (unsigned)fminf(fmaxf(v * 1024.0f, 0.0f), 1023.0f); };
-    key = (spread10(q((o.x - lo.x) * inv.x)) << 2) | (spread10(q((o.y - lo.y) * inv.y)) << 1) |
-          spread10(q((o.z - lo.z) * inv.z));
-  }
-  keys[i] = key;
-}
-
 __global__ void k_reset_counts(int* count, int next) {
   count[next] = 0;
   count[2] = count[3] = count[4] = count[5] = 0;
@@ -487,10 +461,57 @@ using namespace yh;
 // one resident wave of kTraceBlock-thread blocks (persistent kernels)
 static int persistent_grid(const void* kernel) {
   int per_sm = 0;
+  // Shared memory and L1 share 228 KB per SM.  The node fetches of the traversal hit L1 about
+  // half of the time, so the carve-out is a trade between resident blocks and L1 capacity
+  // (measured: the largest carve-out costs 30 % of the traversal rate).  YH_CARVEOUT (percent)
+  // overrides the driver's choice for experiments.
+  if (const char* c = getenv("YH_CARVEOUT")) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTraceBlock, 0) != cudaSuccess || per_sm < 1)
     per_sm = 4;
   return per_sm * sm_count();
 }
+
+// One wavefront group: a contiguous range of path slots with its own queues, counters and
+// stream.  The traversal kernel of one group ends with a tail (a few long rays keep a few
+// warps busy while most SMs idle: ncu showed SMs active 74 % of the kernel's duration), so the
+// slots are split into groups whose kernel sequences run on separate streams: the tail of one
+// group's traversal overlaps the bulk of another group's work.  Groups own disjoint pixels.
+// Pinned 64-byte read-back buffers are pooled for the life of the process: cudaMallocHost /
+// cudaFreeHost synchronise the device and were seen to take up to a second on a busy context.
+static std::mutex        pinned_mutex;
+static std::vector<int*> pinned_free;
+static int* pinned_acquire() {
+  std::lock_guard<std::mutex> lock(pinned_mutex);
+  if (!pinned_free.empty()) {
+    int* p = pinned_free.back();
+    pinned_free.pop_back();
+    return p;
+  }
+  int* p = nullptr;
+  if (cudaMallocHost((void**)&p, 64) != cudaSuccess) return nullptr;
+  return p;
+}
+static void pinned_release(int* p) {
+  std::lock_guard<std::mutex> lock(pinned_mutex);
+  pinned_free.push_back(p);
+}
+
+struct wave_group {
+  int                            first_slot = 0, num_slots = 0;
+  dev_buffer<int>                q_active0, q_active1, q_miss, q_surface, q_hair, q_count;
+  dev_buffer<unsigned long long> stats;
+  cudaStream_t                   stream      = nullptr;
+  cudaEvent_t                    ev_done     = nullptr;
+  int*                           host_counts = nullptr;  // pinned
+  int                            cur = 0;
+  bool                           done = false;
+  queues qs() { return {{q_active0.ptr, q_active1.ptr}, q_miss.ptr, q_surface.ptr, q_hair.ptr, q_count.ptr, stats.ptr}; }
+  ~wave_group() {
+    if (host_counts) pinned_release(host_counts);
+    if (ev_done) cudaEventDestroy(ev_done);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
 
 struct yh_state {
   const yh_scene* scene = nullptr;
@@ -502,24 +523,26 @@ struct yh_state {
   int             srank = 0, sworld = 1;    // sample indices srank, srank + sworld, ... are rendered here
   dev_buffer<float4>             ray_o, ray_d, weight, radiance, accum, render;
   dev_buffer<int4>               hit;
-  dev_buffer<unsigned long long> rng_state, rng_inc, rng_base, stats;
-  dev_buffer<int>                remaining, pixel, samples, q_active0, q_active1, q_miss, q_surface, q_hair, q_count;
-  dev_buffer<unsigned> sort_keys0, sort_keys1;
-  dev_buffer<int>      sort_vals;
-  dev_buffer<char>     sort_tmp;
-  int*            host_counts = nullptr;  // pinned
-  cudaStream_t    stream      = nullptr;
+  dev_buffer<unsigned long long> rng_state, rng_inc, rng_base;
+  dev_buffer<int>                remaining, pixel, samples;
+  std::vector<wave_group*>       groups;
+  cudaStream_t    stream      = nullptr;  // set-up, download
   cudaEvent_t     ev_begin = nullptr, ev_end = nullptr;
   std::vector<cudaEvent_t> ev_pool;
   bool            profile = false;
   yh_trace_stats  last{};
-  path_state      ps() {
-    return {ray_o.ptr, ray_d.ptr, weight.ptr, radiance.ptr, hit.ptr, rng_state.ptr, rng_inc.ptr, rng_base.ptr,
-        remaining.ptr, pixel.ptr, accum.ptr, samples.ptr};
+  // path state of the slots [first, ...): kernels index it with group-local slot ids
+  path_state      ps(int first = 0) {
+    return {ray_o.ptr + first, ray_d.ptr + first, weight.ptr + first, radiance.ptr + first, hit.ptr + first,
+        rng_state.ptr + first, rng_inc.ptr + first, rng_base.ptr + first, remaining.ptr + first, pixel.ptr + first,
+        accum.ptr, samples.ptr};
   }
-  queues qs() { return {{q_active0.ptr, q_active1.ptr}, q_miss.ptr, q_surface.ptr, q_hair.ptr, q_count.ptr, stats.ptr}; }
+  void clear_groups() {
+    for (auto g : groups) delete g;
+    groups.clear();
+  }
   ~yh_state() {
-    if (host_counts) cudaFreeHost(host_counts);
+    clear_groups();
     for (auto e : ev_pool) cudaEventDestroy(e);
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
@@ -528,27 +551,45 @@ struct yh_state {
 };
 
 // Slot order: 32x32 tiles round-robin over ranks; inside a tile 8x4 pixel
-// blocks, so one warp starts with a compact bundle of camera rays.
-static std::vector<int> owned_pixels(int w, int h, int rank, int world) {
+// blocks, so one warp starts with a compact bundle of camera rays.  The owned tiles are
+// dealt round-robin to `ngroups` wavefront groups (group g = slots [first[g], first[g + 1])),
+// which interleaves the groups over the image and balances their load.
+static std::vector<int> owned_pixels(int w, int h, int rank, int world, int ngroups = 1, std::vector<int>* first = nullptr) {
   std::vector<int> px;
   const int        T   = 32;
   int              tx  = (w + T - 1) / T, ty = (h + T - 1) / T;
-  for (int t = 0; t < tx * ty; t++) {
-    if (t % world != rank) continue;
-    int x0 = (t % tx) * T, y0 = (t / tx) * T;
-    for (int by = 0; by < T; by += 4)
-      for (int bx = 0; bx < T; bx += 8)
-        for (int y = 0; y < 4; y++)
-          for (int x = 0; x < 8; x++) {
-            int i = x0 + bx + x, j = y0 + by + y;
-            if (i < w && j < h) px.push_back(j * w + i);
-          }
+  if (first) first->assign(1, 0);
+  for (int g = 0; g < ngroups; g++) {
+    int owned = 0;
+    for (int t = 0; t < tx * ty; t++) {
+      if (t % world != rank) continue;
+      if (owned++ % ngroups != g) continue;
+      int x0 = (t % tx) * T, y0 = (t / tx) * T;
+      for (int by = 0; by < T; by += 4)
+        for (int bx = 0; bx < T; bx += 8)
+          for (int y = 0; y < 4; y++)
+            for (int x = 0; x < 8; x++) {
+              int i = x0 + bx + x, j = y0 + by + y;
+              if (i < w && j < h) px.push_back(j * w + i);
+            }
+    }
+    if (first) first->push_back((int)px.size());
   }
   return px;
 }
 
+#ifndef YH_WAVE_GROUPS
+#define YH_WAVE_GROUPS 2
+#endif
 static yh_status assign_slots(yh_state* st) {
-  std::vector<int> px = owned_pixels(st->width, st->height, st->rank, st->world);
+  int ngroups = YH_WAVE_GROUPS;
+  if (const char* e = getenv("YH_WAVE_GROUPS")) ngroups = atoi(e);
+  long long owned_estimate = (long long)st->width * st->height / st->world;
+  if (owned_estimate < 4 * 65536) ngroups = 1;  // small images: one group already under-fills the device
+  if (ngroups < 1) ngroups = 1;
+  if (ngroups > 8) ngroups = 8;
+  std::vector<int> first;
+  std::vector<int> px = owned_pixels(st->width, st->height, st->rank, st->world, ngroups, &first);
   st->num_slots       = (int)px.size();
   size_t n            = px.size() ? px.size() : 1;
   YH_CUDA(st->ray_o.alloc(n));
@@ -561,11 +602,24 @@ static yh_status assign_slots(yh_state* st) {
   YH_CUDA(st->rng_base.alloc(n));
   YH_CUDA(st->remaining.alloc(n));
   YH_CUDA(st->pixel.alloc(n));
-  YH_CUDA(st->q_active0.alloc(n));
-  YH_CUDA(st->q_active1.alloc(n));
-  YH_CUDA(st->q_miss.alloc(n));
-  YH_CUDA(st->q_surface.alloc(n));
-  YH_CUDA(st->q_hair.alloc(n));
+  st->clear_groups();
+  for (int g = 0; g < ngroups; g++) {
+    auto grp = new wave_group{};
+    st->groups.push_back(grp);
+    grp->first_slot = first[g], grp->num_slots = first[g + 1] - first[g];
+    size_t m        = grp->num_slots ? grp->num_slots : 1;
+    YH_CUDA(grp->q_active0.alloc(m));
+    YH_CUDA(grp->q_active1.alloc(m));
+    YH_CUDA(grp->q_miss.alloc(m));
+    YH_CUDA(grp->q_surface.alloc(m));
+    YH_CUDA(grp->q_hair.alloc(m));
+    YH_CUDA(grp->q_count.alloc(8));
+    YH_CUDA(grp->stats.alloc(8));
+    YH_CUDA(cudaStreamCreateWithFlags(&grp->stream, cudaStreamNonBlocking));
+    YH_CUDA(cudaEventCreateWithFlags(&grp->ev_done, cudaEventDisableTiming));
+    grp->host_counts = pinned_acquire();
+    if (!grp->host_counts) return fail(YH_ERR_CUDA, "pinned host allocation failed");
+  }
   if (st->num_slots) {
     dev_buffer<int> d_px;
     YH_CUDA(d_px.upload(px.data(), px.size()));
@@ -611,16 +665,15 @@ yh_status yh_state_create(const yh_scene* scene, const yh_camera_desc* camera, c
   };
   if (st->width <= 0 || st->height <= 0) return bail(fail(YH_ERR_INVALID, "empty image"));
   size_t np = (size_t)st->width * st->height;
-  if (cudaStreamCreate(&st->stream) != cudaSuccess || cudaEventCreate(&st->ev_begin) != cudaSuccess ||
-      cudaEventCreate(&st->ev_end) != cudaSuccess || cudaMallocHost((void**)&st->host_counts, 64) != cudaSuccess)
+  if (cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&st->ev_begin) != cudaSuccess ||
+      cudaEventCreate(&st->ev_end) != cudaSuccess)
     return bail(fail(YH_ERR_CUDA, "stream/event creation failed"));
-  if (st->accum.alloc(np) != cudaSuccess || st->render.alloc(np) != cudaSuccess || st->samples.alloc(np) != cudaSuccess ||
-      st->q_count.alloc(8) != cudaSuccess || st->stats.alloc(8) != cudaSuccess)
+  if (st->accum.alloc(np) != cudaSuccess || st->render.alloc(np) != cudaSuccess || st->samples.alloc(np) != cudaSuccess)
     return bail(fail(YH_ERR_CUDA, "device allocation failed"));
   cudaMemset(st->accum.ptr, 0, st->accum.bytes());
   cudaMemset(st->render.ptr, 0, st->render.bytes());
   cudaMemset(st->samples.ptr, 0, st->samples.bytes());
-  cudaMemset(st->stats.ptr, 0, st->stats.bytes());
+  cudaDeviceSynchronize();  // the state's streams do not synchronise with the legacy default stream
   yh_status s = assign_slots(st);
   if (s != YH_OK) return bail(s);
   const char* prof = getenv("YH_PROFILE_KERNELS");
@@ -644,6 +697,7 @@ yh_status yh_state_set_shard(yh_state* st, int rank, int world) {
   st->counter = false, st->srank = 0, st->sworld = 1;
   cudaMemset(st->accum.ptr, 0, st->accum.bytes());
   cudaMemset(st->samples.ptr, 0, st->samples.bytes());
+  cudaDeviceSynchronize();
   return assign_slots(st);
 }
 
@@ -654,6 +708,7 @@ yh_status yh_state_set_sample_shard(yh_state* st, int rank, int world) {
   st->counter = true, st->srank = rank, st->sworld = world;  // ... for the sample indices of this rank
   cudaMemset(st->accum.ptr, 0, st->accum.bytes());
   cudaMemset(st->samples.ptr, 0, st->samples.bytes());
+  cudaDeviceSynchronize();
   return assign_slots(st);
 }
 
@@ -678,22 +733,20 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
   st->last = yh_trace_stats{};
   if (num_samples == 0 || st->num_slots == 0) return YH_OK;
   dev_scene    sc = st->scene->view();
-  path_state   ps = st->ps();
-  queues       q  = st->qs();
   trace_consts tc = {st->width, st->height, st->params.bounces, st->params.clamp, st->counter ? 1 : 0, st->srank, st->sworld,
       (unsigned long long)st->params.seed};
-  cudaStream_t s  = st->stream;
-  int          sms = sm_count();
-  YH_CUDA(cudaMemsetAsync(q.count, 0, 8 * sizeof(int), s));
-  YH_CUDA(cudaMemsetAsync(q.stats, 0, 8 * sizeof(unsigned long long), s));
-  YH_CUDA(cudaEventRecord(st->ev_begin, s));
-  k_start<<<(st->num_slots + 255) / 256, 256, 0, s>>>(ps, q, st->camera, tc, st->num_slots, num_samples);
-  int64_t launches = 1, iterations = 0;
-  int     grid_t = sms * 8, grid_s = sms * 4;
-  int     grid_i = persistent_grid((const void*)k_intersect);
-  int     cur = 0;
-  size_t  ev_used = 0;
-  auto    ev = [&]() -> cudaEvent_t {
+  int  sms    = sm_count();
+  bool prof   = st->profile;  // per-kernel timing: every group runs on ONE stream, nothing overlaps
+  int  grid_t = sms * 8, grid_s = sms * 4;
+  int  grid_i = persistent_grid((const void*)k_intersect);
+  // the groups share the device: each group's persistent traversal grid takes its share of the resident blocks
+  int  ngroups = (int)st->groups.size();
+  int  grid_div = 1;
+  if (const char* e = getenv("YH_GROUP_GRID_DIV")) grid_div = std::max(1, atoi(e));
+  int  grid_ig = prof ? grid_i : std::max(sms, grid_i / std::min(grid_div, ngroups));
+  auto stream_of = [&](wave_group* g) { return prof ? st->groups[0]->stream : g->stream; };
+  size_t ev_used = 0;
+  auto   ev = [&](cudaStream_t s) -> cudaEvent_t {
     if (ev_used == st->ev_pool.size()) {
       cudaEvent_t e;
       cudaEventCreate(&e);
@@ -703,75 +756,93 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
     cudaEventRecord(e, s);
     return e;
   };
-  bool    prof = st->profile;
-  const char* se = getenv("YH_SORT_RAYS");
-  bool    sort_rays = se && se[0] == '1';
-  vec3f   slo = {0, 0, 0}, sinv = {0, 0, 0};
-  if (sort_rays) {
-    bbox3f b = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
-    for (auto& o : st->scene->objects) b.min = min3(b.min, o.bbox.min), b.max = max3(b.max, o.bbox.max);
-    slo  = b.min;
-    sinv = {1.0f / fmax_(b.max.x - b.min.x, 1e-20f), 1.0f / fmax_(b.max.y - b.min.y, 1e-20f), 1.0f / fmax_(b.max.z - b.min.z, 1e-20f)};
-    size_t cap = (size_t)st->num_slots, tb = 0;
-    if (st->sort_vals.count < cap) {
-      YH_CUDA(st->sort_keys0.alloc(cap));
-      YH_CUDA(st->sort_keys1.alloc(cap));
-      YH_CUDA(st->sort_vals.alloc(cap));
-      cub::DeviceRadixSort::SortPairs(nullptr, tb, st->sort_keys0.ptr, st->sort_keys1.ptr, st->q_active0.ptr, st->sort_vals.ptr, (int)cap, 0, 30, s);
-      YH_CUDA(st->sort_tmp.alloc(tb));
-    }
+  // begin: the groups' streams start after ev_begin (recorded on the first group's stream)
+  cudaStream_t s0 = st->groups[0]->stream;
+  YH_CUDA(cudaEventRecord(st->ev_begin, s0));
+  int64_t launches = 0, iterations = 0, rounds = 0;
+  for (auto g : st->groups) {
+    cudaStream_t s = stream_of(g);
+    if (s != s0) YH_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
+    queues q = g->qs();
+    YH_CUDA(cudaMemsetAsync(q.count, 0, 8 * sizeof(int), s));
+    YH_CUDA(cudaMemsetAsync(q.stats, 0, 8 * sizeof(unsigned long long), s));
+    g->cur = 0, g->done = g->num_slots == 0;
+    if (g->done) continue;
+    k_start<<<(g->num_slots + 255) / 256, 256, 0, s>>>(st->ps(g->first_slot), q, st->camera, tc, g->num_slots, num_samples);
+    launches++;
   }
   int64_t min_iters = num_samples;  // every sample needs at least one iteration
+  bool    stopped   = false;
   while (true) {
-    int next = cur ^ 1;
-    k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
-    if (prof) ev();
-    k_intersect<<<grid_i, kTraceBlock, 0, s>>>(sc, ps, q, cur);
-    if (prof) ev();
-    k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
-    k_shade<false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-    k_shade<true><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-    if (prof) ev();
-    launches += 5;
-    iterations++;
-    if (sort_rays) {
-      // order the next iteration's rays by origin; the sorted ids land in the other queue buffer
-      int cap = st->num_slots;
-      k_ray_keys<<<(cap + 255) / 256, 256, 0, s>>>(ps, q.active[next], q.count + next, cap, slo, sinv, st->sort_keys0.ptr);
-      size_t tb = st->sort_tmp.bytes();
-      cub::DeviceRadixSort::SortPairs(st->sort_tmp.ptr, tb, st->sort_keys0.ptr, st->sort_keys1.ptr, q.active[next],
-          st->sort_vals.ptr, cap, 0, 30, s);
-      cudaMemcpyAsync(q.active[next], st->sort_vals.ptr, sizeof(int) * (size_t)cap, cudaMemcpyDeviceToDevice, s);
-      launches += 3;
+    bool any = false;
+    for (auto g : st->groups) {
+      if (g->done) continue;
+      any             = true;
+      cudaStream_t s  = stream_of(g);
+      path_state   ps = st->ps(g->first_slot);
+      queues       q  = g->qs();
+      int          next = g->cur ^ 1;
+      k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
+      if (prof) ev(s);
+      k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur);
+      if (prof) ev(s);
+      k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
+      k_shade<false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+      k_shade<true><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+      if (prof) ev(s);
+      launches += 5;
+      iterations++;
+      g->cur = next;
     }
-    cur = next;
-    if (iterations >= min_iters && (iterations % 4 == 0 || iterations < min_iters + 4)) {
-      YH_CUDA(cudaMemcpyAsync(st->host_counts, q.count, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
-      YH_CUDA(cudaStreamSynchronize(s));
-      if (st->host_counts[cur] == 0) break;
+    if (!any) break;
+    rounds++;
+    if (rounds >= min_iters && (rounds % 4 == 0 || rounds < min_iters + 4)) {
+      for (auto g : st->groups)
+        if (!g->done) YH_CUDA(cudaMemcpyAsync(g->host_counts, g->q_count.ptr, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream_of(g)));
+      for (auto g : st->groups) {
+        if (g->done) continue;
+        YH_CUDA(cudaStreamSynchronize(stream_of(g)));
+        if (g->host_counts[g->cur] == 0) g->done = true;
+      }
     }
-    if (stop && *stop) break;
-    if (iterations > (int64_t)num_samples * (st->params.bounces + 2) * 64 + 1024)
-      return fail(YH_ERR_STATE, "yh_trace_samples: wavefront did not drain after %lld iterations", (long long)iterations);
+    if (stop && *stop) {
+      stopped = true;
+      break;
+    }
+    if (rounds > (int64_t)num_samples * (st->params.bounces + 2) * 64 + 1024)
+      return fail(YH_ERR_STATE, "yh_trace_samples: wavefront did not drain after %lld rounds", (long long)rounds);
   }
-  YH_CUDA(cudaEventRecord(st->ev_end, s));
+  (void)stopped;
+  // end: the first group's stream waits for the others, then ev_end
+  for (auto g : st->groups) {
+    cudaStream_t s = stream_of(g);
+    if (s == s0) continue;
+    YH_CUDA(cudaEventRecord(g->ev_done, s));
+    YH_CUDA(cudaStreamWaitEvent(s0, g->ev_done, 0));
+  }
+  YH_CUDA(cudaEventRecord(st->ev_end, s0));
   YH_CUDA(cudaEventSynchronize(st->ev_end));
+  for (auto g : st->groups) YH_CUDA(cudaStreamSynchronize(g->stream));
   YH_CUDA(cudaGetLastError());
-  unsigned long long hs[8];
-  YH_CUDA(cudaMemcpy(hs, q.stats, sizeof(hs), cudaMemcpyDeviceToHost));
+  unsigned long long tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (auto g : st->groups) {
+    unsigned long long hs[8];
+    YH_CUDA(cudaMemcpy(hs, g->stats.ptr, sizeof(hs), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 8; i++) tot[i] += hs[i];
+  }
   float ms = 0;
   YH_CUDA(cudaEventElapsedTime(&ms, st->ev_begin, st->ev_end));
   st->last.samples    = (int64_t)st->num_slots * num_samples;
-  st->last.rays       = (int64_t)hs[0];
-  st->last.light_rays = (int64_t)hs[1];
+  st->last.rays       = (int64_t)tot[0];
+  st->last.light_rays = (int64_t)tot[1];
   st->last.iterations = iterations;
   st->last.launches   = launches;
   st->last.device_ms  = ms;
-  st->last.nodes_visited = (int64_t)hs[3];
-  st->last.prims_tested  = (int64_t)hs[4];
+  st->last.nodes_visited = (int64_t)tot[3];
+  st->last.prims_tested  = (int64_t)tot[4];
   if (prof) {
     float tt = 0, ts = 0;
-    for (size_t i = 0; i + 2 < ev_used; i += 3) {  // three events per iteration
+    for (size_t i = 0; i + 2 < ev_used; i += 3) {  // three events per group iteration
       float a = 0, b = 0;
       cudaEventElapsedTime(&a, st->ev_pool[i], st->ev_pool[i + 1]);
       cudaEventElapsedTime(&b, st->ev_pool[i + 1], st->ev_pool[i + 2]);

@@ -315,10 +315,34 @@ __device__ __forceinline__ bool intersect_instance(const dev_scene& sc, int obje
 //   bool load(int index, int& handle, ray3f& world_ray)
 //   void reload(int handle, vec3f& o, vec3f& d)        (world origin / direction)
 //   void store(int handle, const hit_record&)
-constexpr int kRefillIdle = 8;   // refill once this many lanes of the warp have no ray
-constexpr int kParkSlots  = 4;   // parked leaves per lane
-constexpr int kParkLanes  = 12;  // test parked leaves once this many lanes hold some
-constexpr int kWalkLanes  = 12;  // ... or once fewer lanes than this can still take a node step
+#ifndef YH_REFILL_IDLE
+#define YH_REFILL_IDLE 8
+#endif
+#ifndef YH_PARK_SLOTS
+#define YH_PARK_SLOTS 4
+#endif
+#ifndef YH_PARK_LANES
+#define YH_PARK_LANES 12
+#endif
+#ifndef YH_WALK_LANES
+#define YH_WALK_LANES 12
+#endif
+#ifndef YH_OPEN_LANES
+#define YH_OPEN_LANES 6
+#endif
+#ifndef YH_INNER_STEPS
+#define YH_INNER_STEPS 8
+#endif
+#ifndef YH_INNER_LANES
+#define YH_INNER_LANES 8
+#endif
+constexpr int kRefillIdle = YH_REFILL_IDLE;  // refill once this many lanes of the warp have no ray
+constexpr int kParkSlots  = YH_PARK_SLOTS;   // parked leaves per lane
+constexpr int kParkLanes  = YH_PARK_LANES;   // test parked leaves once this many lanes hold some
+constexpr int kWalkLanes  = YH_WALK_LANES;   // ... or once fewer lanes than this can still take a node step
+constexpr int kOpenLanes  = YH_OPEN_LANES;   // open / close shapes once this many lanes wait for it (or too few walk)
+constexpr int kInnerSteps = YH_INNER_STEPS;  // node steps taken back to back while kInnerLanes lanes can walk
+constexpr int kInnerLanes = YH_INNER_LANES;
 
 // Per-lane state that the node loop does not touch lives in shared memory
 // (word w of thread t at cold[w * kTraceBlock + t]: conflict-free), so the hot
@@ -424,8 +448,15 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       }
     }
 
-    // ---- 3. lanes between shapes: close the finished one, open the next object
-    if (have && cur == kTraverseDone && npark == 0) {
+    // ---- 3. lanes between shapes: close the finished one, open the next object.  This block is
+    // long and few lanes need it at a time, so it waits until kOpenLanes lanes do (or few can walk).
+    bool between = have && cur == kTraverseDone && npark == 0;
+    if (kOpenLanes > 1) {
+      unsigned bm = __ballot_sync(full, between);
+      unsigned wk = __ballot_sync(full, have && cur >= 0 && npark <= kParkSlots - 2);
+      if (__popc(bm) < kOpenLanes && __popc(wk) >= kWalkLanes) between = false;
+    }
+    if (between) {
       int   flags = cw(CW_FLAGS), obj = cw(CW_OBJ), handle = cw(CW_HANDLE);
       float tmin = cwf(CW_TMIN), tmax = cwf(CW_TMAX);
       if (flags & 1) {
@@ -464,7 +495,9 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       if (!opened) have = false, finished = true;
     }
 
-    // ---- 4. one node step; leaf children whose box is hit are parked
+    // ---- 4. node steps; leaf children whose box is hit are parked
+    for (int inner = 0; inner < kInnerSteps; inner++) {
+    if (inner > 0 && __popc(__ballot_sync(full, cur >= 0 && npark <= kParkSlots - 2)) < kInnerLanes) break;
     if (cur >= 0 && npark <= kParkSlots - 2) {
       const slot_words s = ld_slot(slots, cur);
       YH_STAT(if (nodes_visited)(*nodes_visited)++;)
@@ -485,6 +518,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       } else {
         cur = st.sp == 0 ? kTraverseDone : st.pop();
       }
+    }
     }
   }
 }
