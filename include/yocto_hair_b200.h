@@ -116,7 +116,7 @@ enum { YH_SHADER_NAIVE = 0, YH_SHADER_PATH = 1, YH_SHADER_EYELIGHT = 2,
        YH_SHADER_NORMAL = 3 };
 typedef struct yh_trace_params {
   int      resolution; /* 720                                               */
-  int      shader;     /* YH_SHADER_PATH is the only shader on the hot path */
+  int      shader;     /* YH_SHADER_*: naive, path (default), eyelight, normal */
   int      samples;    /* 512 (informative; the caller drives the loop)     */
   int      bounces;    /* 8                                                 */
   float    clamp;      /* 100                                               */

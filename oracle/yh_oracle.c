@@ -1043,16 +1043,23 @@ static ray_t camera_ray(const state_t* st, int i, int j, v2 puv, v2 luv) { /* pt
   return ray;
 }
 
-/* trace_path, pt:1380-1511, for the lobes of SURVEY.md 8a (hair on lines, diffuse on triangles). */
+/* trace_path pt:1380-1511, trace_naive pt:1514-1573, trace_eyelight pt:1576-1633 and trace_normal
+ * pt:1636-1651 (selected by params->shader as get_trace_shader_func does, pt:1662-1673), for the
+ * lobes of SURVEY.md 8a (hair on lines, diffuse on triangles). */
 static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_params* params, float out[4]) {
   v3  radiance = V(0, 0, 0), weight = V(1, 1, 1);
   int hit = 0;
-  for (int bounce = 0; bounce < params->bounces; bounce++) {
+  const int shader = params->shader;
+  int max_bounces = params->bounces;
+  if (shader == YH_SHADER_EYELIGHT) max_bounces = params->bounces > 4 ? params->bounces : 4; /* max(bounces, 4) */
+  if (shader == YH_SHADER_NORMAL) max_bounces = 1;
+  for (int bounce = 0; bounce < max_bounces; bounce++) {
     int   object = -1, element = -1;
     v2    uv = {0, 0};
     float dist = 0;
     if (!walk_scene(sc, &ray, &object, &element, &uv, &dist, 0)) {
       radiance = vadd(radiance, vmul(weight, eval_environment(sc, ray.d)));
+      if (shader == YH_SHADER_NORMAL) hit = 1; /* trace_normal returns alpha 1 on a miss too */
       break;
     }
     const obj_t*   ob = &sc->objs[object];
@@ -1067,6 +1074,11 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
       if (mat->thin) normal = dot3(normal, outgoing) >= 0 ? normal : vneg(normal);
     } else {
       normal = orthonorm(outgoing, eval_normal(sc, object, element, uv));
+    }
+    if (shader == YH_SHADER_NORMAL) { /* pt:1645-1650 */
+      radiance = vadds(vs(normal, 0.5f), 0.5f);
+      hit = 1;
+      break;
     }
     v3 emission = vmul(mat->emission, V(1, 1, 1)); /* no emission texture */
     /* eval_brdf, pt:405-492, with specular = metallic = transmission = 0 */
@@ -1085,9 +1097,22 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
     }
     hit      = 1;
     radiance = vadd(radiance, vmul(weight, emission));
-    /* MIS one-sample model, pt:1441-1451.  GCC evaluates call arguments right to left: rand2f first. */
+    if (shader == YH_SHADER_EYELIGHT) { /* pt:1617-1622: light at the eye, then break (never delta here) */
+      v3 f;
+      if (is_hair) {
+        f = hair_eval(&hb, outgoing, outgoing);
+      } else {
+        float no = dot3(normal, outgoing);
+        f = V(0, 0, 0);
+        if (nonzero3(diffuse)) f = vadd(f, vmul(diffuse, (no <= 0) ? V(0, 0, 0) : vs(vds(V(1, 1, 1), PIF), no)));
+      }
+      radiance = vadd(radiance, vmul(vs(weight, PIF), f));
+      break;
+    }
+    /* MIS one-sample model, pt:1441-1451 (trace_naive always samples the BSDF, pt:1548-1551).
+     * GCC evaluates call arguments right to left: rand2f first. */
     v3 incoming;
-    if (rng_1f(rng) < 0.5f) {
+    if (shader == YH_SHADER_NAIVE || rng_1f(rng) < 0.5f) {
       v2    rn = rng_2f(rng);
       float rnl = rng_1f(rng);
       if (is_hair) {
@@ -1115,8 +1140,12 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
       if (nonzero3(diffuse)) brdfcos = vadd(brdfcos, vmul(diffuse, (ni <= 0 || no <= 0) ? V(0, 0, 0) : vs(vds(V(1, 1, 1), PIF), ni)));
       if (diffuse_pdf) brdf_pdf += diffuse_pdf * ((ni <= 0 || no <= 0) ? 0 : ni / PIF);
     }
-    float light_pdf = sample_lights_pdf(sc, position, incoming);
-    weight = vmul(weight, vds(brdfcos, 0.5f * brdf_pdf + 0.5f * light_pdf));
+    if (shader == YH_SHADER_NAIVE) {
+      weight = vmul(weight, vds(brdfcos, brdf_pdf));
+    } else {
+      float light_pdf = sample_lights_pdf(sc, position, incoming);
+      weight = vmul(weight, vds(brdfcos, 0.5f * brdf_pdf + 0.5f * light_pdf));
+    }
     ray_t nr = {position, incoming, RAY_EPS, FLT_MAXF};
     ray = nr;
     if ((weight.x == 0 && weight.y == 0 && weight.z == 0) || !finite3(weight)) break;

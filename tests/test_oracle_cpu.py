@@ -88,6 +88,7 @@ SCENES = {
     "block": lambda: synth.hair_block_scene(6_000),
     "straight": lambda: synth.straight_hair_scene(5_000),
     "curly": lambda: synth.curly_hair_scene(8_000),
+    "curls_instanced": lambda: synth.hair_curls_scene(6_000),
 }
 
 
@@ -192,3 +193,19 @@ def test_port_counter_mode_properties(port, refo):
     assert abs(m_cnt / m_ref - 1) < 0.03
     for x in (sr, sp, rr, rp):
         x.close()
+
+
+@pytest.mark.parametrize("shader", [0, 2, 3], ids=["naive", "eyelight", "normal"])
+def test_port_other_shaders_bit_exact_vs_reference(shader, port, refo):
+    """trace_naive / trace_eyelight / trace_normal restated in the port (yocto_pathtrace.cpp:1514-1657)."""
+    for make in (lambda: synth.hair_block_scene(3_000), lambda: synth.straight_hair_scene(3_000)):
+        scene, cam = make()
+        for bounces in (8, 0):
+            p = make_params(resolution=48, shader=shader, bounces=bounces)
+            rr, rp = refo.scene(scene), port.scene(scene)
+            sr, sp = rr.state(cam, p), rp.state(cam, p)
+            sr.trace_samples(2), sp.trace_samples(2)
+            (_, a1, s1, g1), (_, a2, s2, g2) = sr.download(), sp.download()
+            assert np.array_equal(bits(a1), bits(a2)) and np.array_equal(s1, s2) and np.array_equal(g1, g2)
+            for x in (sr, sp, rr, rp):
+                x.close()

@@ -23,6 +23,7 @@ SCENES = {
     "straight": lambda: synth.straight_hair_scene(20_000),
     "curly": lambda: synth.curly_hair_scene(40_000),
     "straight_uniform_env": lambda: synth.straight_hair_scene(12_000, sky=False, area_lights=False),
+    "curls_instanced": lambda: synth.hair_curls_scene(16_000),  # 4 objects share one shape
 }
 
 
@@ -205,9 +206,9 @@ def test_errors_are_loud():
         ds.init_state(cam, make_params(resolution=32))
     assert e.value.status == capi.YH_ERR_STATE
     ds.init_bvh().init_lights()
-    with pytest.raises(capi.YhError) as e:  # only trace_path is on the hot path
-        ds.init_state(cam, make_params(resolution=32, shader=0))
-    assert e.value.status == capi.YH_ERR_UNSUPPORTED
+    with pytest.raises(capi.YhError) as e:  # get_trace_shader_func throws "sampler unknown" (:1669)
+        ds.init_state(cam, make_params(resolution=32, shader=7))
+    assert e.value.status == capi.YH_ERR_INVALID
     ds.close()
     sc.materials[0].specular = 0.5  # microfacet lobes are out of scope: refuse, do not approximate
     with pytest.raises(capi.YhError) as e:
@@ -309,3 +310,23 @@ def test_counter_mode_converges_to_the_reference_image(ref):
     assert err <= 1.5 * floor
     assert abs(lum(gpu) / lum(imgs["A"]) - 1) <= 5e-3
     st.close(); ds.close(); rs.close()
+
+
+@pytest.mark.parametrize("shader", [0, 2, 3], ids=["naive", "eyelight", "normal"])
+@pytest.mark.parametrize("name", ["block", "straight", "curls_instanced"])
+def test_other_shaders_bit_identical(name, shader, ref):
+    """trace_naive / trace_eyelight / trace_normal (yocto_pathtrace.cpp:1514-1657)."""
+    scene, cam = SCENES[name]()
+    for bounces in (8, 0):
+        p = make_params(resolution=96, shader=shader, bounces=bounces)
+        rs = ref.scene(scene)
+        st_r = rs.state(cam, p)
+        st_r.trace_samples(3)
+        _, a_r, s_r, rng_r = st_r.download()
+        ds = DeviceScene(scene).init_bvh().init_lights()
+        st_d = ds.init_state(cam, p)
+        st_d.trace_samples(3)
+        _, a_d, s_d = st_d.download()
+        assert np.array_equal(s_r, s_d) and np.array_equal(rng_r, st_d.rng())
+        assert np.array_equal(a_r.view(np.uint32), a_d.view(np.uint32))
+        st_r.close(); rs.close(); st_d.close(); ds.close()

@@ -68,6 +68,7 @@ struct trace_consts {
   // stream make_rng(seed, seq_pixel + (s << 31)); this state renders s = srank, srank + sworld, ...
   int                counter, srank, sworld;
   unsigned long long seed;
+  int                shader;  // YH_SHADER_*: trace_naive / trace_path / trace_eyelight / trace_normal (:1380-1657)
 };
 
 // Path state is touched once per wavefront iteration and is larger than L2
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(256) k_start(path_state ps, queues q, dev_came
   bool live = slot < num_slots && num_samples > 0;
   if (live) {
     rng_state rng = {ld_stream(&ps.rng_state[slot]), ld_stream(&ps.rng_inc[slot])};
-    if (tc.bounces <= 0) {
-      // the path loop (:1395) never runs: black sample, alpha 0, camera draws still consumed
+    if (tc.bounces <= 0 && (tc.shader == YH_SHADER_PATH || tc.shader == YH_SHADER_NAIVE)) {
+      // the path loop (:1395, :1524) never runs: black sample, alpha 0, camera draws still consumed
       int px = ld_stream(&ps.pixel[slot]), done = ld_stream(&ps.samples[px]);
       for (int s = 0; s < num_samples; s++) {
         if (tc.counter) {  // same re-seed as start_sample
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(dev_scene sc, path_state ps,
       float4    d = ld_stream(&ps.ray_d[slot]), w = ld_stream(&ps.weight[slot]), r = ld_stream(&ps.radiance[slot]);
       vec3f     radiance = vec3f{r.x, r.y, r.z} + vec3f{w.x, w.y, w.z} * eval_environment(sc, {d.x, d.y, d.z});
       rng_state rng      = {ld_stream(&ps.rng_state[slot]), ld_stream(&ps.rng_inc[slot])};
-      again              = finish_sample(ps, cam, tc, slot, radiance, w.w, rng);
+      again              = finish_sample(ps, cam, tc, slot, radiance, tc.shader == YH_SHADER_NORMAL ? 1.0f : w.w, rng);
       st_stream(&ps.rng_state[slot], rng.state);
     }
     queue_push(q.active[next], q.count + next, again, slot);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(dev_scene sc, path_state ps,
 
 // The body of trace_path for one surface vertex, :1417-1507.  HAIR selects the
 // lobe set at compile time so the two kernels stay divergence-free inside.
-template <bool HAIR>
+template <bool HAIR, int SHADER>
 __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_state& ps, const dev_camera& cam,
     const trace_consts& tc, int slot, trav_stack& st, unsigned int& light_rays) {
   float4    o4 = ld_stream(&ps.ray_o[slot]), d4 = ld_stream(&ps.ray_d[slot]), w4 = ld_stream(&ps.weight[slot]), r4 = ld_stream(&ps.radiance[slot]);
@@ -274,7 +275,11 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
   float opacity = mat.opacity * div_(1.0f + 1.0f + 1.0f, 3.0f);
   if (opacity > 0.999f) opacity = 1;
   bool finished = false;
-  if (opacity < 1 && rand1f(rng) >= opacity) {
+  if (SHADER == YH_SHADER_NORMAL) {  // trace_normal, :1636-1651: the shading normal as a colour, alpha 1
+    radiance = normal * 0.5f + 0.5f;
+    w4.w     = 1.0f;
+    finished = true;
+  } else if (opacity < 1 && rand1f(rng) >= opacity) {
     vec3f no = position + ray_d * 1e-2f;
     st_stream(&ps.ray_o[slot], make_float4(no.x, no.y, no.z, 0));  // same direction, bounce not counted
   } else {
@@ -297,9 +302,22 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     vec3f diffuse     = mat.color;
     float dmax        = max3(diffuse);
     float diffuse_pdf = dmax != 0 ? div_(dmax, dmax) : 0.0f;  // diffuse_pdf / pdf_sum, :456-471
-    // MIS one-sample model, :1441-1451.  Argument evaluation order of the oracle
-    // build (GCC, right to left): rand2f before rand1f, see camera_ray().
-    if (rand1f(rng) < 0.5f) {
+    if (SHADER == YH_SHADER_EYELIGHT) {  // trace_eyelight, :1576-1633: the light sits at the eye
+      vec3f f;
+      if (HAIR) {
+        float unused_pdf;
+        eval_hair_scattering_and_pdf(hb, ht, outgoing, f, unused_pdf);
+      } else {
+        float no = dot(normal, outgoing);
+        f        = {0, 0, 0};
+        if (nonzero(diffuse)) f = f + diffuse * ((no <= 0) ? vec3f{0, 0, 0} : vec3f{1, 1, 1} / pif * no);
+      }
+      radiance = radiance + weight * pif * f;
+      finished = true;  // never delta here (roughness ends at 1, :446-452): the loop breaks after one vertex
+    } else {
+    // MIS one-sample model, :1441-1451 (trace_naive, :1548-1551, always samples the BSDF).  Argument
+    // evaluation order of the oracle build (GCC, right to left): rand2f before rand1f, see camera_ray().
+    if (SHADER == YH_SHADER_NAIVE || rand1f(rng) < 0.5f) {
       vec2f rn  = rand2f(rng);
       float rnl = rand1f(rng);
       if (HAIR) {
@@ -328,8 +346,12 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       }
       if (diffuse_pdf != 0) brdf_pdf += diffuse_pdf * ((ni <= 0 || no <= 0) ? 0.0f : div_(ni, pif));
     }
-    float light_pdf = sample_lights_pdf(sc, position, incoming, st, light_rays);
-    weight          = weight * (brdfcos / (0.5f * brdf_pdf + 0.5f * light_pdf));
+    if (SHADER == YH_SHADER_NAIVE) {
+      weight = weight * (brdfcos / brdf_pdf);
+    } else {
+      float light_pdf = sample_lights_pdf(sc, position, incoming, st, light_rays);
+      weight          = weight * (brdfcos / (0.5f * brdf_pdf + 0.5f * light_pdf));
+    }
 
     st_stream(&ps.ray_o[slot], make_float4(position.x, position.y, position.z, 0));
     st_stream(&ps.ray_d[slot], make_float4(incoming.x, incoming.y, incoming.z, 0));
@@ -343,6 +365,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     }
     bounce += 1;
     if (bounce >= tc.bounces) finished = true;
+    }
     w4.w = alpha;
   }
   bool again;
@@ -357,7 +380,9 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
   return again;
 }
 
-template <bool HAIR>
+// one instantiation per (primitive kind, shader): the shader is a compile-time constant so the
+// path shader's code carries none of the other shaders' branches
+template <bool HAIR, int SHADER>
 #ifndef YH_SHADE_BLOCKS
 #define YH_SHADE_BLOCKS 4
 #endif
@@ -375,7 +400,7 @@ __global__ void __launch_bounds__(kTraceBlock, YH_SHADE_BLOCKS) k_shade(dev_scen
       trav_stack st;
       st.smem = smem_stack + threadIdx.x;
       st.sp   = 0;
-      again   = shade_vertex<HAIR>(sc, ps, cam, tc, slot, st, light_rays);
+      again   = shade_vertex<HAIR, SHADER>(sc, ps, cam, tc, slot, st, light_rays);
     }
     queue_push(q.active[next], q.count + next, again, slot);
   }
@@ -637,8 +662,8 @@ yh_status yh_state_create(const yh_scene* scene, const yh_camera_desc* camera, c
   YH_REQUIRE_DEVICE();
   if (!scene || !camera || !params || !out) return fail(YH_ERR_INVALID, "yh_state_create: null argument");
   *out = nullptr;
-  if (params->shader != YH_SHADER_PATH)
-    return fail(YH_ERR_UNSUPPORTED, "shader %d: only the MIS path shader (trace_path) is on the hot path", params->shader);
+  if (params->shader < YH_SHADER_NAIVE || params->shader > YH_SHADER_NORMAL)
+    return fail(YH_ERR_INVALID, "shader %d: sampler unknown", params->shader);
   if (!scene->bvh_built || !scene->lights_built)
     return fail(YH_ERR_STATE, "yh_state_create: call yh_scene_init_bvh and yh_scene_init_lights first");
   if (scene->lights.empty())
@@ -734,7 +759,7 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
   if (num_samples == 0 || st->num_slots == 0) return YH_OK;
   dev_scene    sc = st->scene->view();
   trace_consts tc = {st->width, st->height, st->params.bounces, st->params.clamp, st->counter ? 1 : 0, st->srank, st->sworld,
-      (unsigned long long)st->params.seed};
+      (unsigned long long)st->params.seed, st->params.shader};
   int  sms    = sm_count();
   bool prof   = st->profile;  // per-kernel timing: every group runs on ONE stream, nothing overlaps
   int  grid_t = sms * 8, grid_s = sms * 4;
@@ -787,8 +812,23 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
       k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur);
       if (prof) ev(s);
       k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
-      k_shade<false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-      k_shade<true><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+      switch (tc.shader) {
+        case YH_SHADER_NAIVE:
+          k_shade<false, YH_SHADER_NAIVE><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<true, YH_SHADER_NAIVE><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          break;
+        case YH_SHADER_EYELIGHT:
+          k_shade<false, YH_SHADER_EYELIGHT><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<true, YH_SHADER_EYELIGHT><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          break;
+        case YH_SHADER_NORMAL:
+          k_shade<false, YH_SHADER_NORMAL><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<true, YH_SHADER_NORMAL><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          break;
+        default:
+          k_shade<false, YH_SHADER_PATH><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<true, YH_SHADER_PATH><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+      }
       if (prof) ev(s);
       launches += 5;
       iterations++;

@@ -180,8 +180,6 @@ void init_state(ptr::state* state, const ptr::scene* scene, const ptr::camera* c
 
 void trace_samples(ptr::state* state, const ptr::scene* scene, const ptr::camera* camera, const ptr::trace_params& params,
     int num_samples, std::atomic<bool>* stop) {
-  if (params.shader != ptr::shader_type::path)  // same failure mode as get_trace_shader_func for an unknown shader
-    throw std::runtime_error("yocto_pathtrace_b200: only the path shader runs on the device");
   auto& rec = find_state(state);
   if (rec.scene != scene) throw std::runtime_error("yocto_pathtrace_b200: state was initialised for another scene");
   if (memcmp(&rec.camera, camera, sizeof(ptr::camera)) != 0)

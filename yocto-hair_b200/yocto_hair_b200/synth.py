@@ -229,6 +229,42 @@ def hair_block_scene(num_segments=200_000, seed=7, aspect=1.777777778, **hair):
     return sc, cam
 
 
+def make_hair_curl(num_segments=40_000, seed=7, sub=4, beziers_per_fibre=10) -> Shape:
+    """A hanging lock of helical fibres around the y axis (stand-in for shapes/hair-curl.ply)."""
+    rng = np.random.default_rng(seed)
+    nf = max(1, num_segments // (sub * beziers_per_fibre))
+    knots = beziers_per_fibre + 1
+    t = np.linspace(0, 1, knots, dtype=F)[None, :]
+    r0 = rng.uniform(0.05, 0.45, (nf, 1)).astype(F)
+    ph = rng.uniform(0, 2 * np.pi, (nf, 1)).astype(F)
+    turns = rng.uniform(2.0, 3.0, (nf, 1)).astype(F)
+    ang = ph + 2 * np.pi * turns * t
+    pts = np.stack([r0 * (1 + 0.6 * t) * np.cos(ang), 7.0 - 7.0 * t + 0 * r0, r0 * (1 + 0.6 * t) * np.sin(ang)], axis=-1).astype(F)
+    return _fibres_to_shape(pts, F(0.012), F(0.004), sub, rng, 0.01)
+
+
+def hair_curls_scene(num_segments=40_000, seed=7, sky=True):
+    """tests/hair-curls/hair-curls.json: FOUR objects share ONE hair shape with different
+    frames and materials (black / red / brown / blonde), two area lights, sky."""
+    sc = Scene()
+    sc.shapes.append(make_hair_curl(num_segments, seed))
+    sc.shapes.append(make_arealight_quad())
+    for mat in (dict(eumelanin=8.0), dict(pheomelanin=2.0), dict(eumelanin=1.3), dict(eumelanin=0.3)):
+        sc.materials.append(Material(**mat))
+    sc.materials.append(Material(emission=(20, 20, 20)))
+    for k, x in enumerate((-3.75, -1.25, 1.25, 3.75)):
+        sc.objects.append(Object(shape=0, material=k, frame=(1, 0, 0, 0, 1, 0, 0, 0, 1, x, 0, 0)))
+    for eye, at in (((-8, 10, 5), (-6.5, 3.5, 0)), ((0, 10, 5), (-1.5, 3.5, 0))):
+        sc.objects.append(Object(shape=1, material=4, frame=lookat_frame(eye, at, (0, 1, 0), inv_xz=True)))
+    if sky:
+        sc.textures.append(make_sky_texture())
+        sc.environments.append(Environment(emission=(1, 1, 1), emission_tex=0))
+    else:
+        sc.environments.append(Environment(emission=(1, 1, 1)))
+    cam = Camera.from_lookat((0, 4, 16), (0, 3.5, 0), (0, 1, 0), lens=0.05, aspect=1.777777778)
+    return sc, cam
+
+
 def random_rays(scene: Scene, n: int, seed=11):
     """Fixed-ray set for hit-id parity: origins inside / around the first line
     shape's bounds, uniformly random directions (incoherent rays)."""
