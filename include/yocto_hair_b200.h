@@ -147,8 +147,11 @@ void      yh_scene_destroy(yh_scene* scene);
  * segment from up to `max_split` boxes (0 = library default).               */
 typedef struct yh_bvh_params {
   int max_split;
-  int leaf_size; /* references per leaf, 1..8 (0 = library default)        */
-  int reserved[6];
+  int leaf_size; /* ignored: a leaf holds exactly one reference            */
+  int quality;   /* 0 = Morton LBVH on the device (fast build, default);
+                    1 = binned-SAH topology built on the host by all cores
+                        (slower build, fewer node visits per ray: for long renders) */
+  int reserved[5];
 } yh_bvh_params;
 yh_status yh_scene_init_bvh(yh_scene* scene, const yh_bvh_params* params);
 

@@ -4,6 +4,7 @@
 #include <cub/cub.cuh>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstring>
 #include <future>
@@ -341,7 +342,155 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
   for (int i = 0; i < n; i++) ref_pos[prims[i].primitive] = i;
 }
 
-static yh_status build_shape_bvh(host_shape& sh, int max_split) {
+// ---- quality builder (yh_bvh_params::quality = 1): binned SAH, top down, on the host ----------
+// Same outputs as k_hierarchy (left / right / parents over inner nodes 0 .. R-2, root = 0, leaf
+// children encoded as ~position) plus the permutation of the references, so the device kernels
+// k_refit and k_emit_packed finish the build exactly as for the LBVH.  Inner nodes are numbered
+// in preorder (a subtree over m references owns m - 1 consecutive ids), which lets independent
+// subtrees be built by different host threads.
+struct sah_topology {
+  std::vector<int> order, left, right, parent_inner, parent_leaf;
+};
+struct sah_bin {
+  vec3f lo{flt_max, flt_max, flt_max}, hi{-flt_max, -flt_max, -flt_max};
+  int   count = 0;
+  void  add(const ref_bounds& b) {
+    lo = min3(lo, vec3f{b.lo.x, b.lo.y, b.lo.z}), hi = max3(hi, vec3f{b.hi.x, b.hi.y, b.hi.z});
+    count++;
+  }
+  void merge(const sah_bin& o) { lo = min3(lo, o.lo), hi = max3(hi, o.hi), count += o.count; }
+  float area() const {
+    if (count == 0) return 0;
+    vec3f d = hi - lo;
+    return d.x * d.y + d.y * d.z + d.z * d.x;
+  }
+};
+constexpr int kSahBins = 16;
+static inline vec3f ref_centre(const ref_bounds& b) { return {(b.lo.x + b.hi.x) * 0.5f, (b.lo.y + b.hi.y) * 0.5f, (b.lo.z + b.hi.z) * 0.5f}; }
+static inline float axis_of(const vec3f& v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+// best binned split of order[s, e): returns the partition point (order is permuted)
+static int sah_split(const ref_bounds* refs, int* order, int s, int e) {
+  int   m = e - s;
+  vec3f cmin = {flt_max, flt_max, flt_max}, cmax = {-flt_max, -flt_max, -flt_max};
+  auto  scan_bounds = [&](int a, int b, vec3f& lo, vec3f& hi) {
+    for (int i = a; i < b; i++) {
+      vec3f c = ref_centre(refs[order[i]]);
+      lo = min3(lo, c), hi = max3(hi, c);
+    }
+  };
+  const int nthreads = m > (1 << 18) ? 8 : 1;  // the top ranges are binned by several threads
+  if (nthreads == 1) {
+    scan_bounds(s, e, cmin, cmax);
+  } else {
+    std::vector<std::future<std::pair<vec3f, vec3f>>> fs;
+    for (int t = 0; t < nthreads; t++)
+      fs.push_back(std::async(std::launch::async, [&, t]() {
+        vec3f lo = {flt_max, flt_max, flt_max}, hi = {-flt_max, -flt_max, -flt_max};
+        scan_bounds(s + (long long)m * t / nthreads, s + (long long)m * (t + 1) / nthreads, lo, hi);
+        return std::make_pair(lo, hi);
+      }));
+    for (auto& f : fs) {
+      auto r = f.get();
+      cmin = min3(cmin, r.first), cmax = max3(cmax, r.second);
+    }
+  }
+  vec3f ext = cmax - cmin;
+  if (!(ext.x > 0) && !(ext.y > 0) && !(ext.z > 0)) return (s + e) / 2;
+  vec3f scale = {ext.x > 0 ? kSahBins / ext.x : 0.0f, ext.y > 0 ? kSahBins / ext.y : 0.0f, ext.z > 0 ? kSahBins / ext.z : 0.0f};
+  auto  bin_of = [&](const vec3f& c, int a) {
+    int b = (int)((axis_of(c, a) - axis_of(cmin, a)) * axis_of(scale, a));
+    return b < 0 ? 0 : (b >= kSahBins ? kSahBins - 1 : b);
+  };
+  using bin_set = std::array<std::array<sah_bin, kSahBins>, 3>;
+  auto fill = [&](int a, int b, bin_set& bins) {
+    for (int i = a; i < b; i++) {
+      const ref_bounds& r = refs[order[i]];
+      vec3f c = ref_centre(r);
+      for (int ax = 0; ax < 3; ax++) bins[ax][bin_of(c, ax)].add(r);
+    }
+  };
+  bin_set bins;
+  if (nthreads == 1) {
+    fill(s, e, bins);
+  } else {
+    std::vector<std::future<bin_set>> fs;
+    for (int t = 0; t < nthreads; t++)
+      fs.push_back(std::async(std::launch::async, [&, t]() {
+        bin_set local;
+        fill(s + (long long)m * t / nthreads, s + (long long)m * (t + 1) / nthreads, local);
+        return local;
+      }));
+    for (auto& f : fs) {
+      bin_set local = f.get();
+      for (int ax = 0; ax < 3; ax++)
+        for (int b = 0; b < kSahBins; b++) bins[ax][b].merge(local[ax][b]);
+    }
+  }
+  float best = flt_max;
+  int   best_axis = -1, best_bin = 0;
+  for (int ax = 0; ax < 3; ax++) {
+    if (!(axis_of(ext, ax) > 0)) continue;
+    float   right_cost[kSahBins];
+    sah_bin acc;
+    for (int b = kSahBins - 1; b > 0; b--) {
+      acc.merge(bins[ax][b]);
+      right_cost[b] = acc.area() * acc.count;
+    }
+    sah_bin accl;
+    for (int b = 0; b + 1 < kSahBins; b++) {
+      accl.merge(bins[ax][b]);
+      if (accl.count == 0 || accl.count == m) continue;
+      float cost = accl.area() * accl.count + right_cost[b + 1];
+      if (cost < best) best = cost, best_axis = ax, best_bin = b;
+    }
+  }
+  if (best_axis < 0) return (s + e) / 2;
+  int mid = (int)(std::partition(order + s, order + e,
+                      [&](int id) { return bin_of(ref_centre(refs[id]), best_axis) <= best_bin; }) -
+                  order);
+  if (mid == s || mid == e) mid = (s + e) / 2;
+  return mid;
+}
+static void sah_build_range(const ref_bounds* refs, sah_topology& t, int node, int s, int e, int depth) {
+  struct item { int node, s, e; };
+  std::vector<item>              todo{{node, s, e}};
+  std::vector<std::future<void>> spawned;
+  while (!todo.empty()) {
+    item it = todo.back();
+    todo.pop_back();
+    int mid = sah_split(refs, t.order.data(), it.s, it.e);
+    int ml = mid - it.s, mr = it.e - mid;
+    int child[2] = {ml == 1 ? ~it.s : it.node + 1, mr == 1 ? ~mid : it.node + ml};
+    t.left[it.node] = child[0], t.right[it.node] = child[1];
+    int range[2][2] = {{it.s, mid}, {mid, it.e}};
+    for (int c = 0; c < 2; c++) {
+      if (child[c] < 0) {
+        t.parent_leaf[~child[c]] = it.node;
+        continue;
+      }
+      t.parent_inner[child[c]] = it.node;
+      int cnt = range[c][1] - range[c][0];
+      if (c == 0 && depth < 6 && cnt > (1 << 14) && (it.e - it.s) - cnt > (1 << 14)) {  // big sibling pair: fork
+        int cn = child[c], cs = range[c][0], ce = range[c][1];
+        spawned.push_back(std::async(std::launch::async, [refs, &t, cn, cs, ce, depth]() { sah_build_range(refs, t, cn, cs, ce, depth + 1); }));
+      } else {
+        todo.push_back({child[c], range[c][0], range[c][1]});
+      }
+    }
+    if (!spawned.empty() && depth < 6) depth++;  // forks deepen the task tree, not the loop
+  }
+  for (auto& f : spawned) f.get();
+}
+static void sah_build(const std::vector<ref_bounds>& refs, sah_topology& t) {
+  int R = (int)refs.size();
+  t.order.resize(R);
+  for (int i = 0; i < R; i++) t.order[i] = i;
+  t.left.assign(R - 1, 0), t.right.assign(R - 1, 0), t.parent_inner.assign(R - 1, -1), t.parent_leaf.assign(R, -1);
+  sah_build_range(refs.data(), t, 0, 0, R, 0);
+}
+
+static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   bool lines = sh.is_lines();
   int  n     = sh.num_elems();
   sh.root_leaf = 0, sh.num_refs = 0, sh.num_nodes = 0;
@@ -468,8 +617,20 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split) {
   YH_CUDA(flags.alloc(ni));
   YH_CUDA(node_box.alloc(ni));
   YH_CUDA(cudaMemset(flags.ptr, 0, flags.bytes()));
-  k_hierarchy<<<G(ni), B>>>(keys_out.ptr, R, left.ptr, right.ptr, first.ptr, last.ptr, parent_inner.ptr, parent_leaf.ptr);
-  YH_CUDA(cudaGetLastError());
+  if (quality >= 1) {  // binned SAH topology from the host builder; ids_out becomes its permutation
+    std::vector<ref_bounds> href(R);
+    YH_CUDA(cudaMemcpy(href.data(), refs.ptr, sizeof(ref_bounds) * (size_t)R, cudaMemcpyDeviceToHost));
+    sah_topology topo;
+    sah_build(href, topo);
+    YH_CUDA(cudaMemcpy(left.ptr, topo.left.data(), 4 * (size_t)ni, cudaMemcpyHostToDevice));
+    YH_CUDA(cudaMemcpy(right.ptr, topo.right.data(), 4 * (size_t)ni, cudaMemcpyHostToDevice));
+    YH_CUDA(cudaMemcpy(parent_inner.ptr, topo.parent_inner.data(), 4 * (size_t)ni, cudaMemcpyHostToDevice));
+    YH_CUDA(cudaMemcpy(parent_leaf.ptr, topo.parent_leaf.data(), 4 * (size_t)R, cudaMemcpyHostToDevice));
+    YH_CUDA(cudaMemcpy(ids_out.ptr, topo.order.data(), 4 * (size_t)R, cudaMemcpyHostToDevice));
+  } else {
+    k_hierarchy<<<G(ni), B>>>(keys_out.ptr, R, left.ptr, right.ptr, first.ptr, last.ptr, parent_inner.ptr, parent_leaf.ptr);
+    YH_CUDA(cudaGetLastError());
+  }
   k_refit<<<G(R), B>>>(R, ids_out.ptr, refs.ptr, left.ptr, right.ptr, parent_inner.ptr, parent_leaf.ptr, flags.ptr, node_box.ptr);
   YH_CUDA(cudaGetLastError());
   k_emit_packed<<<G(ni), B>>>(lines, ni, left.ptr, right.ptr, parent_inner.ptr, ids_out.ptr, refs.ptr, node_box.ptr,
@@ -657,7 +818,7 @@ yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
   if (max_split > 8) max_split = 8;
   sc->stats = yh_bvh_stats{};
   for (auto s : sc->shapes) {
-    yh_status st = build_shape_bvh(*s, max_split);
+    yh_status st = build_shape_bvh(*s, max_split, params ? params->quality : 0);
     if (st != YH_OK) return st;
     sc->stats.num_primitives += s->num_elems();
     sc->stats.num_references += s->num_refs;

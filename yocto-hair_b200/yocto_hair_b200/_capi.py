@@ -75,7 +75,7 @@ class TraceParams(C.Structure):
 
 
 class BvhParams(C.Structure):
-    _fields_ = [("max_split", C.c_int), ("leaf_size", C.c_int), ("reserved", C.c_int * 6)]
+    _fields_ = [("max_split", C.c_int), ("leaf_size", C.c_int), ("quality", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class BvhStats(C.Structure):

@@ -56,9 +56,9 @@ class DeviceScene:
         except Exception:
             pass
 
-    def init_bvh(self, max_split: int = 0, leaf_size: int = 0) -> "DeviceScene":
+    def init_bvh(self, max_split: int = 0, leaf_size: int = 0, quality: int = 0) -> "DeviceScene":
         p = capi.BvhParams()
-        p.max_split, p.leaf_size = max_split, leaf_size
+        p.max_split, p.leaf_size, p.quality = max_split, leaf_size, quality
         capi.check(self.lib.yh_scene_init_bvh(self.handle, C.byref(p)))
         return self
 
