@@ -178,11 +178,11 @@ __global__ void __launch_bounds__(256) k_start(path_state ps, queues q, dev_came
 }
 
 // Ray source / hit sink of the wavefront for trace_persistent().
-struct wavefront_io {
-  const dev_scene& sc;
-  const path_state& ps;
-  const queues&     q;
-  const int*        active;
+struct wavefront_io {  // by value: references to kernel parameters would force them into local memory
+  const dev_scene  sc;
+  const path_state ps;
+  const queues     q;
+  const int*       active;
   __device__ __forceinline__ bool load(int index, int& slot, ray3f& r) const {
     slot     = active[index];
     float4 o = ld_stream(&ps.ray_o[slot]), d = ld_stream(&ps.ray_d[slot]);
@@ -397,9 +397,9 @@ __global__ void __launch_bounds__(kTraceBlock, YH_SHADE_BLOCKS) k_shade(dev_scen
     bool live = idx < n, again = false;
     int  slot = live ? queue[idx] : 0;
     if (live) {
+      int        stack_overflow[kStackLocal];
       trav_stack st;
-      st.smem = smem_stack + threadIdx.x;
-      st.sp   = 0;
+      st.init(smem_stack + threadIdx.x, stack_overflow);
       again   = shade_vertex<HAIR, SHADER>(sc, ps, cam, tc, slot, st, light_rays);
     }
     queue_push(q.active[next], q.count + next, again, slot);

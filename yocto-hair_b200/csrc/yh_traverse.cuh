@@ -40,18 +40,31 @@ struct hit_record {
 // Per-thread traversal stack: the first kStackShared entries are interleaved
 // in shared memory (entry e of thread t at smem[e * blockDim.x + t], so a warp
 // touches 32 consecutive banks), deeper entries spill to local memory.
+// The overflow array is NOT a member: a dynamically indexed member would put the whole struct
+// (stack pointer and shared-memory base included) into local memory, and every push / pop
+// would go through LDL / STL and generic-address stores (seen in the SASS of the first version).
 struct trav_stack {
-  int* smem;
-  int  local[kStackLocal];
-  int  sp;
+  unsigned smem;   // shared-state-space byte address of this thread's entry 0
+  int*     local;  // kStackLocal ints of the caller's frame
+  int      sp;
+  __device__ __forceinline__ void init(int* shared_entry0, int* local_array) {
+    smem  = (unsigned)__cvta_generic_to_shared(shared_entry0);
+    local = local_array;
+    sp    = 0;
+  }
   __device__ __forceinline__ void push(int v) {
-    if (sp < kStackShared) smem[sp * kTraceBlock] = v;
+    if (sp < kStackShared) asm volatile("st.shared.s32 [%0], %1;" ::"r"(smem + (unsigned)sp * (kTraceBlock * 4u)), "r"(v) : "memory");
     else local[sp - kStackShared] = v;
     sp++;
   }
   __device__ __forceinline__ int pop() {
     sp--;
-    return sp < kStackShared ? smem[sp * kTraceBlock] : local[sp - kStackShared];
+    if (sp < kStackShared) {
+      int v;
+      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem + (unsigned)sp * (kTraceBlock * 4u)) : "memory");
+      return v;
+    }
+    return local[sp - kStackShared];
   }
 };
 
@@ -197,9 +210,10 @@ __device__ __forceinline__ void child_boxes(const slot_words& s, const slab_cons
   float c2 = __fmaf_rn(lo16(s.w4), k.az, k.bz), d2 = __fmaf_rn(hi16(s.w5), k.az, k.bz);
   tn1       = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), tlo));
   float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), thi));
-  // slack on both ends; |x| keeps it outward-going for the negative distances of a shifted origin
-  h0 = tn0 - 5e-7f * fabsf(tn0) <= tf0 + 5e-7f * fabsf(tf0);
-  h1 = tn1 - 5e-7f * fabsf(tn1) <= tf1 + 5e-7f * fabsf(tf1);
+  // relative slack of 5e-7 on both ends, outward-going also for the negative distances of a shifted
+  // origin: tn - tf <= 1e-6 * max(|tn|, |tf|) is implied by tn - 5e-7 |tn| <= tf + 5e-7 |tf|
+  h0 = tn0 <= __fmaf_rn(fmaxf(fabsf(tn0), fabsf(tf0)), 1e-6f, tf0);
+  h1 = tn1 <= __fmaf_rn(fmaxf(fabsf(tn1), fabsf(tf1)), 1e-6f, tf1);
 }
 
 __device__ __forceinline__ unsigned ray_dsign(const vec3f& d) {  // ray_dsign, :862-863
@@ -365,9 +379,9 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
     unsigned long long* prims_tested) {
   const unsigned full = 0xffffffffu;
   const int      lane = threadIdx.x & 31;
+  int            stack_overflow[kStackLocal];
   trav_stack     st;
-  st.smem = smem_stack;
-  st.sp   = 0;
+  st.init(smem_stack, stack_overflow);
   volatile int* cold = smem_cold;
   auto cw  = [&](int w) -> volatile int& { return cold[w * kTraceBlock]; };
   auto cwf = [&](int w) -> float { return __int_as_float(cold[w * kTraceBlock]); };
