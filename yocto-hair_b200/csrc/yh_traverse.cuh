@@ -518,20 +518,17 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       bool  h0, h1;
       float tn0, tn1;
       child_boxes(s, k, tlo, thi, h0, h1, tn0, tn1);
-      int ch0 = (int)s.w6, ch1 = (int)s.w6 + 1;
-      if (h0 && (s.w7 & 1u)) smem_park[npark++ * kTraceBlock] = ch0, h0 = false;
-      if (h1 && (s.w7 & 2u)) smem_park[npark++ * kTraceBlock] = ch1, h1 = false;
-      if (h0 && h1) {
-        bool swap = tn1 < tn0;
-        st.push(swap ? ch0 : ch1);
-        cur = swap ? ch1 : ch0;
-      } else if (h0) {
-        cur = ch0;
-      } else if (h1) {
-        cur = ch1;
-      } else {
-        cur = st.sp == 0 ? kTraverseDone : st.pop();
-      }
+      const int  ch0 = (int)s.w6, ch1 = (int)s.w6 + 1;
+      const bool leaf0 = (s.w7 & 1u) != 0, leaf1 = (s.w7 & 2u) != 0;
+      if (h0 && leaf0) smem_park[npark++ * kTraceBlock] = ch0;
+      if (h1 && leaf1) smem_park[npark++ * kTraceBlock] = ch1;
+      // inner children that are hit: the nearer one is next, the farther one goes on the stack
+      const bool in0 = h0 && !leaf0, in1 = h1 && !leaf1;
+      const bool second = in1 && (!in0 || tn1 < tn0);
+      const int  near = second ? ch1 : ch0;
+      if (in0 && in1) st.push(second ? ch0 : ch1);
+      if (in0 || in1) cur = near;
+      else cur = st.sp == 0 ? kTraverseDone : st.pop();
     }
     }
   }
