@@ -211,7 +211,7 @@ __global__ void k_emit_packed(int is_lines, int n_inner, const int* left, const 
     if (ch < 0) {
       int sr = sorted_ref[~ch];
       quantise(refs[sr], g, inv_s, q[c]);
-      flags |= 1u << c;
+      flags |= 0x80000000u >> c;
       // the leaf child is the primitive itself
       int    prim = ref_prim[sr];
       size_t slot = (size_t)(1 + 2 * i + c);

@@ -8,7 +8,7 @@
 //                        w2 = c0.hi.y | c0.hi.z << 16   w3 = c1.lo.x | c1.lo.y << 16
 //                        w4 = c1.lo.z | c1.hi.x << 16   w5 = c1.hi.y | c1.hi.z << 16
 //                        w6 = slot of child 0 (child 1 is the next slot)
-//                        w7 = bit 0: child 0 is a leaf, bit 1: child 1 is a leaf
+//                        w7 = bit 31: child 0 is a leaf, bit 30: child 1 is a leaf
 //                    or a leaf = ONE primitive reference:
 //                        line     : {p0.xyz, r0, p1.xyz, r1}  (the segment itself)
 //                        triangle : w0 = element id (vertices in tris[3 * id ..])

@@ -30,6 +30,10 @@ __device__ __forceinline__ slot_words ld_slot(const uint4* __restrict__ slots, i
   return s;
 }
 
+// leaf flags of an inner slot (w7): sign-bit tests are one instruction each
+__device__ __forceinline__ bool slot_leaf0(unsigned w7) { return (int)w7 < 0; }
+__device__ __forceinline__ bool slot_leaf1(unsigned w7) { return (int)(w7 << 1) < 0; }
+
 struct hit_record {
   int   object, element;
   vec2f uv;
@@ -40,31 +44,41 @@ struct hit_record {
 // Per-thread traversal stack: the first kStackShared entries are interleaved
 // in shared memory (entry e of thread t at smem[e * blockDim.x + t], so a warp
 // touches 32 consecutive banks), deeper entries spill to local memory.
-// The overflow array is NOT a member: a dynamically indexed member would put the whole struct
-// (stack pointer and shared-memory base included) into local memory, and every push / pop
-// would go through LDL / STL and generic-address stores (seen in the SASS of the first version).
+// The stack pointer is kept as the shared-memory ADDRESS of the next free entry (`top`), so a
+// push is one st.shared + one add and a pop one add + one ld.shared; nearly every node step of
+// a warp has some lane pushing and some lane popping, so these few instructions are paid by
+// the whole warp every step.  The overflow array is not a member and is touched only through
+// out-of-line helpers: a dynamically indexed member would put the whole struct into local
+// memory (seen in the SASS of the first version), and an inlined overflow path costs
+// predicated-off issue slots in the hot loop.
+constexpr unsigned kStackStride = kTraceBlock * 4u;  // bytes between two entries of one thread
+__device__ __noinline__ void stack_overflow_store(int* local, unsigned index, int v) { local[index] = v; }
+__device__ __noinline__ int  stack_overflow_load(const int* local, unsigned index) { return local[index]; }
 struct trav_stack {
-  unsigned smem;   // shared-state-space byte address of this thread's entry 0
+  unsigned base;   // shared-state-space byte address of this thread's entry 0
+  unsigned top;    // ... of its next free entry
+  unsigned limit;  // ... of the first entry that no longer fits in shared memory
   int*     local;  // kStackLocal ints of the caller's frame
-  int      sp;
   __device__ __forceinline__ void init(int* shared_entry0, int* local_array) {
-    smem  = (unsigned)__cvta_generic_to_shared(shared_entry0);
+    base  = (unsigned)__cvta_generic_to_shared(shared_entry0);
+    top   = base;
+    limit = base + kStackShared * kStackStride;
     local = local_array;
-    sp    = 0;
   }
+  __device__ __forceinline__ bool     empty() const { return top == base; }
+  __device__ __forceinline__ void     clear() { top = base; }
+  __device__ __forceinline__ unsigned mark() const { return top; }
   __device__ __forceinline__ void push(int v) {
-    if (sp < kStackShared) asm volatile("st.shared.s32 [%0], %1;" ::"r"(smem + (unsigned)sp * (kTraceBlock * 4u)), "r"(v) : "memory");
-    else local[sp - kStackShared] = v;
-    sp++;
+    if (top < limit) asm volatile("st.shared.s32 [%0], %1;" ::"r"(top), "r"(v) : "memory");
+    else stack_overflow_store(local, (top - limit) / kStackStride, v);
+    top += kStackStride;
   }
   __device__ __forceinline__ int pop() {
-    sp--;
-    if (sp < kStackShared) {
-      int v;
-      asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem + (unsigned)sp * (kTraceBlock * 4u)) : "memory");
-      return v;
-    }
-    return local[sp - kStackShared];
+    top -= kStackStride;
+    int v;
+    if (top < limit) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(top) : "memory");
+    else v = stack_overflow_load(local, (top - limit) / kStackStride);
+    return v;
   }
 };
 
@@ -216,6 +230,103 @@ __device__ __forceinline__ void child_boxes(const slot_words& s, const slab_cons
   h1 = tn1 <= __fmaf_rn(fmaxf(fabsf(tn1), fabsf(tf1)), 1e-6f, tf1);
 }
 
+// The same two box tests as entry distance + far limit: child c is hit iff tn_c <= lim_c.
+__device__ __forceinline__ void child_dists(const slot_words& s, const slab_consts& k, float tlo, float thi, float& tn0,
+    float& lim0, float& tn1, float& lim1) {
+  auto lo16 = [](unsigned w) { return (float)(w & 0xffffu); };
+  auto hi16 = [](unsigned w) { return (float)(w >> 16); };
+  float a0 = __fmaf_rn(lo16(s.w0), k.ax, k.bx), b0 = __fmaf_rn(hi16(s.w1), k.ax, k.bx);
+  float a1 = __fmaf_rn(hi16(s.w0), k.ay, k.by), b1 = __fmaf_rn(lo16(s.w2), k.ay, k.by);
+  float a2 = __fmaf_rn(lo16(s.w1), k.az, k.bz), b2 = __fmaf_rn(hi16(s.w2), k.az, k.bz);
+  tn0       = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tlo));
+  float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), thi));
+  float c0 = __fmaf_rn(lo16(s.w3), k.ax, k.bx), d0 = __fmaf_rn(hi16(s.w4), k.ax, k.bx);
+  float c1 = __fmaf_rn(hi16(s.w3), k.ay, k.by), d1 = __fmaf_rn(lo16(s.w5), k.ay, k.by);
+  float c2 = __fmaf_rn(lo16(s.w4), k.az, k.bz), d2 = __fmaf_rn(hi16(s.w5), k.az, k.bz);
+  tn1       = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), tlo));
+  float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), thi));
+  lim0 = __fmaf_rn(fmaxf(fabsf(tn0), fabsf(tf0)), 1e-6f, tf0);  // see child_boxes
+  lim1 = __fmaf_rn(fmaxf(fabsf(tn1), fabsf(tf1)), 1e-6f, tf1);
+}
+
+// What follows the two box tests of a node step, written in PTX so that it stays predicated:
+// nearly every step of a warp has SOME lane parking a leaf, some lane pushing and some lane
+// popping, so whatever these paths cost is paid by the whole warp on every step (the compiler's
+// version of the same logic, with its branches and select chains, was 56 instructions; this is
+// about 40).  In C++ terms:
+//     h0 = tn0 <= lim0, h1 = tn1 <= lim1; leaf0 = w7 bit 31, leaf1 = w7 bit 30; ch0 = w6, ch1 = w6 + 1
+//     if (h0 && leaf0) *park_top++ = ch0;   if (h1 && leaf1) *park_top++ = ch1;
+//     in0 = h0 && !leaf0, in1 = h1 && !leaf1; second = in1 && (!in0 || tn1 < tn0)
+//     if (in0 && in1) push(second ? ch0 : ch1)
+//     cur = (in0 || in1) ? (second ? ch1 : ch0) : (stack empty ? kTraverseDone : pop())
+// park_top and the stack top are shared-memory addresses, entries kStackStride bytes apart; stack
+// entries beyond `limit` live in the local overflow array (rare: generic stores / loads behind a branch).
+__device__ __forceinline__ void node_control(float tn0, float lim0, float tn1, float lim1, unsigned w6, unsigned w7,
+    int& cur, unsigned& park_top, trav_stack& st) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred h0, h1, l0, l1, pa, pb, i0, i1, both, any, sec, fit, q, slow;\n\t"
+      ".reg .s32 ch1, nr, fr;\n\t"
+      ".reg .u32 t;\n\t"
+      ".reg .u64 a;\n\t"
+      "setp.le.f32 h0, %5, %6;\n\t"
+      "setp.le.f32 h1, %7, %8;\n\t"
+      "setp.lt.s32 l0, %10, 0;\n\t"
+      "and.b32 t, %10, 0x40000000;\n\t"
+      "setp.ne.u32 l1, t, 0;\n\t"
+      "add.s32 ch1, %9, 1;\n\t"
+      "and.pred pa, h0, l0;\n\t"
+      "and.pred pb, h1, l1;\n\t"
+      "and.pred i0, h0, !l0;\n\t"
+      "and.pred i1, h1, !l1;\n\t"
+      "@pa st.shared.s32 [%1], %9;\n\t"
+      "@pa add.u32 %1, %1, %12;\n\t"
+      "@pb st.shared.s32 [%1], ch1;\n\t"
+      "@pb add.u32 %1, %1, %12;\n\t"
+      "setp.lt.f32 sec, %7, %5;\n\t"
+      "or.pred sec, sec, !i0;\n\t"
+      "and.pred sec, sec, i1;\n\t"
+      "selp.s32 nr, ch1, %9, sec;\n\t"
+      "selp.s32 fr, %9, ch1, sec;\n\t"
+      "and.pred both, i0, i1;\n\t"
+      "or.pred any, i0, i1;\n\t"
+      // push the farther child
+      "setp.lt.u32 fit, %2, %4;\n\t"
+      "and.pred q, both, fit;\n\t"
+      "and.pred slow, both, !fit;\n\t"
+      "@q st.shared.s32 [%2], fr;\n\t"
+      "@!slow bra PUSHED;\n\t"
+      "sub.u32 t, %2, %4;\n\t"
+      "shr.u32 t, t, 7;\n\t"  // entry index * 4 (entries are 512 bytes apart)
+      "cvt.u64.u32 a, t;\n\t"
+      "add.u64 a, a, %11;\n\t"
+      "st.s32 [a], fr;\n\t"
+      "PUSHED:\n\t"
+      "@both add.u32 %2, %2, %12;\n\t"
+      // next node: the nearer child, else the top of the stack, else done
+      "mov.s32 %0, nr;\n\t"
+      "@!any mov.s32 %0, 0x80000000;\n\t"
+      "setp.ne.u32 q, %2, %3;\n\t"
+      "and.pred q, q, !any;\n\t"
+      "@q sub.u32 %2, %2, %12;\n\t"
+      "setp.lt.u32 fit, %2, %4;\n\t"
+      "and.pred slow, q, !fit;\n\t"
+      "and.pred q, q, fit;\n\t"
+      "@q ld.shared.s32 %0, [%2];\n\t"
+      "@!slow bra POPPED;\n\t"
+      "sub.u32 t, %2, %4;\n\t"
+      "shr.u32 t, t, 7;\n\t"
+      "cvt.u64.u32 a, t;\n\t"
+      "add.u64 a, a, %11;\n\t"
+      "ld.s32 %0, [a];\n\t"
+      "POPPED:\n\t"
+      "}"
+      : "+r"(cur), "+r"(park_top), "+r"(st.top)
+      : "r"(st.base), "r"(st.limit), "f"(tn0), "f"(lim0), "f"(tn1), "f"(lim1), "r"(w6), "r"(w7), "l"(st.local),
+        "n"(kStackStride)
+      : "memory");
+}
+
 __device__ __forceinline__ unsigned ray_dsign(const vec3f& d) {  // ray_dsign, :862-863
   return ((1.0f / d.x) < 0 ? 1u : 0u) | ((1.0f / d.y) < 0 ? 2u : 0u) | ((1.0f / d.z) < 0 ? 4u : 0u);
 }
@@ -246,8 +357,8 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
     leaf(0);
     return hit;
   }
-  int base = st.sp;
-  int cur  = 0;
+  const unsigned base = st.mark();
+  int            cur  = 0;
   while (true) {
     const slot_words s = ld_slot(sh.slots, cur);
     YH_STAT(if (nodes_visited)(*nodes_visited)++;)
@@ -255,10 +366,10 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
     float tn0, tn1;
     child_boxes(s, sr.k, shifted_tmin(ray.tmin, sr.t0), shifted_tmax(ray.tmax, sr.t0), h0, h1, tn0, tn1);
     int ch0 = (int)s.w6, ch1 = (int)s.w6 + 1;
-    if (h0 && (s.w7 & 1u)) leaf(ch0), h0 = false;
-    if (h1 && (s.w7 & 2u)) leaf(ch1), h1 = false;
+    if (h0 && slot_leaf0(s.w7)) leaf(ch0), h0 = false;
+    if (h1 && slot_leaf1(s.w7)) leaf(ch1), h1 = false;
     if (find_any && hit) {
-      st.sp = base;
+      st.top = base;
       return true;
     }
     if (h0 && h1) {
@@ -270,7 +381,7 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
     } else if (h1) {
       cur = ch1;
     } else {
-      if (st.sp == base) break;
+      if (st.mark() == base) break;
       cur = st.pop();
     }
   }
@@ -357,6 +468,10 @@ constexpr int kWalkLanes  = YH_WALK_LANES;   // ... or once fewer lanes than thi
 constexpr int kOpenLanes  = YH_OPEN_LANES;   // open / close shapes once this many lanes wait for it (or too few walk)
 constexpr int kInnerSteps = YH_INNER_STEPS;  // node steps taken back to back while kInnerLanes lanes can walk
 constexpr int kInnerLanes = YH_INNER_LANES;
+#ifndef YH_VOTE_EVERY
+#define YH_VOTE_EVERY 8
+#endif
+constexpr int kVoteEvery = YH_VOTE_EVERY;    // node steps between two votes of the inner loop
 
 // Per-lane state that the node loop does not touch lives in shared memory
 // (word w of thread t at cold[w * kTraceBlock + t]: conflict-free), so the hot
@@ -392,7 +507,11 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
   };
   // registers of the node loop
   bool  have = false, finished = false, exhausted = false;
-  int   cur = kTraverseDone, npark = 0;
+  int   cur = kTraverseDone;
+  // parked leaves: shared-memory address of the next free entry of this lane's list (entries kStackStride apart)
+  const unsigned park_base = (unsigned)__cvta_generic_to_shared(smem_park);
+  const unsigned park_walk = park_base + (kParkSlots - 2) * kStackStride;  // a node step may park two more up to here
+  unsigned       park_top  = park_base;
   float tlo = 0, thi = 0;  // [tmin, tmax] as seen from the (possibly shifted) box origin
   slab_consts k = {0, 0, 0, 0, 0, 0};
   const uint4* __restrict__ slots = nullptr;
@@ -417,7 +536,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
           ray3f wr;
           int   handle;
           if (index < n && io.load(index, handle, wr)) {
-            have = true, cur = kTraverseDone, st.sp = 0, npark = 0;
+            have = true, cur = kTraverseDone, st.clear(), park_top = park_base;
             put(CW_TMIN, wr.tmin), put(CW_TMAX, wr.tmax);
             cw(CW_HANDLE) = handle, cw(CW_OBJ) = -1, cw(CW_FLAGS) = 0;
             cw(CW_BOBJ) = -1, cw(CW_BELEM) = -1, put(CW_BU, 0), put(CW_BV, 0), put(CW_BDIST, 0);
@@ -431,10 +550,10 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
 
     // ---- 2. parked leaves
     {
-      bool     can_walk = have && cur >= 0 && npark <= kParkSlots - 2;
-      unsigned pm = __ballot_sync(full, npark > 0);
+      bool     can_walk = have && cur >= 0 && park_top <= park_walk;
+      unsigned pm = __ballot_sync(full, park_top != park_base);
       unsigned wm = __ballot_sync(full, can_walk);
-      if (npark > 0 && (__popc(pm) >= kParkLanes || __popc(wm) < kWalkLanes)) {
+      if (park_top != park_base && (__popc(pm) >= kParkLanes || __popc(wm) < kWalkLanes)) {
         ray3f ray = {{cwf(CW_OX), cwf(CW_OY), cwf(CW_OZ)}, {cwf(CW_DX), cwf(CW_DY), cwf(CW_DZ)}, cwf(CW_TMIN),
             cwf(CW_TMAX)};
         float uu = __fmaf_rn(ray.d.x, ray.d.x, __fmaf_rn(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
@@ -444,30 +563,31 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         unsigned dsign = (flags >> 4) & 7;
         vec2f uv = {cwf(CW_U), cwf(CW_V)};
         const dev_shape& sh = *shape_ptr();
-        for (int e = 0; e < npark; e++) {
-          int   slot = smem_park[e * kTraceBlock];
+        for (unsigned pe = park_base; pe != park_top; pe += kStackStride) {
+          int slot;
+          asm volatile("ld.shared.s32 %0, [%1];" : "=r"(slot) : "r"(pe) : "memory");
           vec2f uvc;
           float tc;
           YH_STAT(if (prims_tested)(*prims_tested)++;)
           if (test_leaf_slot(sh, is_lines, ray, uu, mo, slot, uvc, tc))
             accept_hit(sh, dsign, slot, uvc, tc, shape_hit, ref, uv, ray.tmax);
         }
-        npark = 0;
+        park_top = park_base;
         if (shape_hit) {
           put(CW_TMAX, ray.tmax);
           thi = shifted_tmax(ray.tmax, cwf(CW_T0));
           cw(CW_FLAGS) = flags | 1, cw(CW_REF) = ref, put(CW_U, uv.x), put(CW_V, uv.y);
-          if (find_any) st.sp = 0, cur = kTraverseDone;
+          if (find_any) st.clear(), cur = kTraverseDone;
         }
       }
     }
 
     // ---- 3. lanes between shapes: close the finished one, open the next object.  This block is
     // long and few lanes need it at a time, so it waits until kOpenLanes lanes do (or few can walk).
-    bool between = have && cur == kTraverseDone && npark == 0;
+    bool between = have && cur == kTraverseDone && park_top == park_base;
     if (kOpenLanes > 1) {
       unsigned bm = __ballot_sync(full, between);
-      unsigned wk = __ballot_sync(full, have && cur >= 0 && npark <= kParkSlots - 2);
+      unsigned wk = __ballot_sync(full, have && cur >= 0 && park_top <= park_walk);
       if (__popc(bm) < kOpenLanes && __popc(wk) >= kWalkLanes) between = false;
     }
     if (between) {
@@ -500,7 +620,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         flags = (flags & 3) | (sh.is_lines ? 4 : 0) | (int)(ray_dsign(d) << 4);
         slots = sh.slots;
         cw(CW_REF) = -1;
-        if (sh.root_leaf) smem_park[0] = 0, npark = 1, cur = kTraverseDone;  // the whole shape is one leaf
+        if (sh.root_leaf) smem_park[0] = 0, park_top = park_base + kStackStride, cur = kTraverseDone;  // the whole shape is one leaf
         else cur = 0;
         opened = true;
         break;
@@ -509,27 +629,25 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       if (!opened) have = false, finished = true;
     }
 
-    // ---- 4. node steps; leaf children whose box is hit are parked
-    for (int inner = 0; inner < kInnerSteps; inner++) {
-    if (inner > 0 && __popc(__ballot_sync(full, cur >= 0 && npark <= kParkSlots - 2)) < kInnerLanes) break;
-    if (cur >= 0 && npark <= kParkSlots - 2) {
+    // ---- 4. node steps; leaf children whose box is hit are parked.  Two steps between two votes:
+    // the vote (and its branch) costs as much as a tenth of a step.
+    auto node_step = [&]() {
       const slot_words s = ld_slot(slots, cur);
       YH_STAT(if (nodes_visited)(*nodes_visited)++;)
-      bool  h0, h1;
-      float tn0, tn1;
-      child_boxes(s, k, tlo, thi, h0, h1, tn0, tn1);
-      const int  ch0 = (int)s.w6, ch1 = (int)s.w6 + 1;
-      const bool leaf0 = (s.w7 & 1u) != 0, leaf1 = (s.w7 & 2u) != 0;
-      if (h0 && leaf0) smem_park[npark++ * kTraceBlock] = ch0;
-      if (h1 && leaf1) smem_park[npark++ * kTraceBlock] = ch1;
-      // inner children that are hit: the nearer one is next, the farther one goes on the stack
-      const bool in0 = h0 && !leaf0, in1 = h1 && !leaf1;
-      const bool second = in1 && (!in0 || tn1 < tn0);
-      const int  near = second ? ch1 : ch0;
-      if (in0 && in1) st.push(second ? ch0 : ch1);
-      if (in0 || in1) cur = near;
-      else cur = st.sp == 0 ? kTraverseDone : st.pop();
-    }
+      float tn0, lim0, tn1, lim1;
+      child_dists(s, k, tlo, thi, tn0, lim0, tn1, lim1);
+      node_control(tn0, lim0, tn1, lim1, s.w6, s.w7, cur, park_top, st);
+    };
+#if YH_INNER_ROLLED
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+    for (int inner = 0; inner < kInnerSteps; inner += kVoteEvery) {
+      if (inner > 0 && __popc(__ballot_sync(full, cur >= 0 && park_top <= park_walk)) < kInnerLanes) break;
+#pragma unroll
+      for (int v = 0; v < kVoteEvery; v++)
+        if (cur >= 0 && park_top <= park_walk) node_step();
     }
   }
 }
