@@ -182,12 +182,15 @@ __global__ void k_refit(int n, const int* sorted_ref, const ref_bounds* refs, co
   }
 }
 
-// Quantises one box onto the shape's 16-bit grid, outwards.
-__device__ __forceinline__ void quantise(const ref_bounds& b, const vec3f& g, const vec3f& inv_s, unsigned q[6]) {
+// Quantises one box onto the shape's 16-bit grid, outwards, after padding it by `pad` grid steps
+// per axis (fold_pad_steps(): the traversal's plane decode moves all planes of an axis together
+// by up to about half a step, yh_traverse.cuh slab_consts).
+__device__ __forceinline__ void quantise(const ref_bounds& b, const vec3f& g, const vec3f& inv_s, const vec3f& pad,
+    unsigned q[6]) {
   auto dn = [](float v) { return (unsigned)fminf(fmaxf(floorf(v), 0.0f), 65535.0f); };
   auto up = [](float v) { return (unsigned)fminf(fmaxf(ceilf(v), 0.0f), 65535.0f); };
-  q[0] = dn((b.lo.x - g.x) * inv_s.x), q[1] = dn((b.lo.y - g.y) * inv_s.y), q[2] = dn((b.lo.z - g.z) * inv_s.z);
-  q[3] = up((b.hi.x - g.x) * inv_s.x), q[4] = up((b.hi.y - g.y) * inv_s.y), q[5] = up((b.hi.z - g.z) * inv_s.z);
+  q[0] = dn((b.lo.x - g.x) * inv_s.x - pad.x), q[1] = dn((b.lo.y - g.y) * inv_s.y - pad.y), q[2] = dn((b.lo.z - g.z) * inv_s.z - pad.z);
+  q[3] = up((b.hi.x - g.x) * inv_s.x + pad.x), q[4] = up((b.hi.y - g.y) * inv_s.y + pad.y), q[5] = up((b.hi.z - g.z) * inv_s.z + pad.z);
 }
 
 // Writes the packed tree (yh_scene.cuh "shape BVH"): one thread per inner node
@@ -195,7 +198,7 @@ __device__ __forceinline__ void quantise(const ref_bounds& b, const vec3f& g, co
 // reserved for it, and the primitive records of its leaf children next to it.
 __global__ void k_emit_packed(int is_lines, int n_inner, const int* left, const int* right, const int* parent_inner,
     const int* sorted_ref, const ref_bounds* refs, const ref_bounds* node_box, const int* ref_prim, const int* elems,
-    const float* pos, const float* radius, vec3f g, vec3f inv_s, uint4* slots, int* slot_elem) {
+    const float* pos, const float* radius, vec3f g, vec3f inv_s, vec3f pad, uint4* slots, int* slot_elem) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_inner) return;
   int my_slot = 0;
@@ -210,7 +213,7 @@ __global__ void k_emit_packed(int is_lines, int n_inner, const int* left, const 
     int ch = child[c];
     if (ch < 0) {
       int sr = sorted_ref[~ch];
-      quantise(refs[sr], g, inv_s, q[c]);
+      quantise(refs[sr], g, inv_s, pad, q[c]);
       flags |= 0x80000000u >> c;
       // the leaf child is the primitive itself
       int    prim = ref_prim[sr];
@@ -225,12 +228,13 @@ __global__ void k_emit_packed(int is_lines, int n_inner, const int* left, const 
       }
       slot_elem[slot] = prim;
     } else {
-      quantise(node_box[ch], g, inv_s, q[c]);
+      quantise(node_box[ch], g, inv_s, pad, q[c]);
     }
   }
-  slots[2 * (size_t)my_slot] = make_uint4(q[0][0] | (q[0][1] << 16), q[0][2] | (q[0][3] << 16), q[0][4] | (q[0][5] << 16),
-      q[1][0] | (q[1][1] << 16));
-  slots[2 * (size_t)my_slot + 1] = make_uint4(q[1][2] | (q[1][3] << 16), q[1][4] | (q[1][5] << 16), (unsigned)(1 + 2 * i), flags);
+  // one word per axis: lo | hi << 16
+  slots[2 * (size_t)my_slot] = make_uint4(q[0][0] | (q[0][3] << 16), q[0][1] | (q[0][4] << 16), q[0][2] | (q[0][5] << 16),
+      q[1][0] | (q[1][3] << 16));
+  slots[2 * (size_t)my_slot + 1] = make_uint4(q[1][1] | (q[1][4] << 16), q[1][2] | (q[1][5] << 16), (unsigned)(1 + 2 * i), flags);
 }
 
 // Triangle vertices by element (48 bytes): leaf slots of triangle shapes hold the element id.
@@ -573,6 +577,16 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   sh.grid_origin = glo;
   sh.grid_step   = {step(glo.x, ghi.x), step(glo.y, ghi.y), step(glo.z, ghi.z)};
   vec3f inv_step = {1.0f / sh.grid_step.x, 1.0f / sh.grid_step.y, 1.0f / sh.grid_step.z};
+  // Padding in grid steps that covers the traversal's folded plane decode t = fma(2^23 + q, a, b - 2^23 a):
+  // b - 2^23 a is rounded once, to half an ulp of a number of magnitude 2^23 |a| + |b|, where |b| <= (distance
+  // of the box origin from the grid origin, at most 2 scale + extent) / step * |a|.  In steps: ulp <= 2 * 2^-24 *
+  // (2^23 + |b| / |a|), doubled once more when the sum crosses a power of two => pad = 0.5 * (1 + |b/a| 2^-23) * 1.06.
+  auto fold_pad_steps = [&](float lo, float hi, float inv) {
+    float reach = (2.0f * sh.scale + (hi - lo)) * inv;  // |b / a| bound, in steps
+    return 0.53f * (1.0f + reach / 8388608.0f) + 0.01f;
+  };
+  vec3f pad_steps = {fold_pad_steps(glo.x, ghi.x, inv_step.x), fold_pad_steps(glo.y, ghi.y, inv_step.y),
+      fold_pad_steps(glo.z, ghi.z, inv_step.z)};
   sh.num_refs    = R;
   if (!lines) {
     YH_CUDA(sh.d_prims.alloc((size_t)n * 3));
@@ -634,7 +648,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   k_refit<<<G(R), B>>>(R, ids_out.ptr, refs.ptr, left.ptr, right.ptr, parent_inner.ptr, parent_leaf.ptr, flags.ptr, node_box.ptr);
   YH_CUDA(cudaGetLastError());
   k_emit_packed<<<G(ni), B>>>(lines, ni, left.ptr, right.ptr, parent_inner.ptr, ids_out.ptr, refs.ptr, node_box.ptr,
-      ref_prim.ptr, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, sh.grid_origin, inv_step, sh.d_slots.ptr,
+      ref_prim.ptr, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, sh.grid_origin, inv_step, pad_steps, sh.d_slots.ptr,
       sh.d_slot_elem.ptr);
   YH_CUDA(cudaGetLastError());
   ref_bounds rb;

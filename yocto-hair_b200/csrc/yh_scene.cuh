@@ -4,9 +4,9 @@
 //                  (LDG.E.256 on sm_100a).  A slot is either
 //                    an inner node: the boxes of BOTH children on the shape's 16-bit
 //                      grid (box = grid_origin + q * grid_step, rounded outwards)
-//                        w0 = c0.lo.x | c0.lo.y << 16   w1 = c0.lo.z | c0.hi.x << 16
-//                        w2 = c0.hi.y | c0.hi.z << 16   w3 = c1.lo.x | c1.lo.y << 16
-//                        w4 = c1.lo.z | c1.hi.x << 16   w5 = c1.hi.y | c1.hi.z << 16
+//                        w0 = c0.lo.x | c0.hi.x << 16   w1 = c0.lo.y | c0.hi.y << 16
+//                        w2 = c0.lo.z | c0.hi.z << 16   w3 = c1.lo.x | c1.hi.x << 16
+//                        w4 = c1.lo.y | c1.hi.y << 16   w5 = c1.lo.z | c1.hi.z << 16
 //                        w6 = slot of child 0 (child 1 is the next slot)
 //                        w7 = bit 31: child 0 is a leaf, bit 30: child 1 is a leaf
 //                    or a leaf = ONE primitive reference:

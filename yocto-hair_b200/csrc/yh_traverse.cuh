@@ -175,8 +175,20 @@ __device__ __forceinline__ void accept_hit(const dev_shape& sh, unsigned dsign, 
 // touch the shape, otherwise box distances are measured from there and compared
 // with [tmin - t0, tmax - t0].  Primitive tests always see the original ray.
 struct slab_consts {
-  float ax, ay, az, bx, by, bz;
+  float    ax, ay, az, bx, by, bz;
+  unsigned nx, ny, nz, fx, fy, fz;  // PRMT selectors of the entry (near) and exit (far) plane of each axis
 };
+// Decoding a plane costs ONE instruction before the FMA and none on the conversion pipe: a box word
+// holds the lo and hi grid coordinate of one axis (lo | hi << 16); PRMT picks the half this ray
+// enters (or leaves) through - the selector depends only on the sign of the direction - and
+// drops it into the mantissa of the float 2^23 + q, exactly.  The 2^23 is folded into the slab
+// offset, b' = b - 2^23 a, so  t = fma(2^23 + q, a, b').  The rounding of b' (half an ulp of
+// ~2^23 |a|, i.e. about half a grid step) moves ALL planes of that axis by the same amount for
+// this ray; the builder pads every box by that much (yh_scene.cu, fold_pad_steps).
+constexpr unsigned kSelLo = 0x7610u, kSelHi = 0x7632u;
+__device__ __forceinline__ float plane_float(unsigned w, unsigned sel) {
+  return __uint_as_float(__byte_perm(w, 0x4b000000u, sel));
+}
 struct shape_ray {
   slab_consts k;
   float       t0;     // box distances are measured from o + t0 * d
@@ -200,53 +212,42 @@ __device__ __forceinline__ shape_ray make_shape_ray(const dev_shape& sh, const v
   }
   auto  safe = [](float v) { return fabsf(v) < 1e-20f ? copysignf(1e-20f, v) : v; };
   float idx = 1.0f / safe(d.x), idy = 1.0f / safe(d.y), idz = 1.0f / safe(d.z);
-  r.k = {sh.grid_step.x * idx, sh.grid_step.y * idy, sh.grid_step.z * idz,
-      __fmaf_rn(sh.grid_origin.x, idx, -bo.x * idx), __fmaf_rn(sh.grid_origin.y, idy, -bo.y * idy),
-      __fmaf_rn(sh.grid_origin.z, idz, -bo.z * idz)};
+  const float ax = sh.grid_step.x * idx, ay = sh.grid_step.y * idy, az = sh.grid_step.z * idz;
+  const float bx = __fmaf_rn(sh.grid_origin.x, idx, -bo.x * idx), by = __fmaf_rn(sh.grid_origin.y, idy, -bo.y * idy),
+              bz = __fmaf_rn(sh.grid_origin.z, idz, -bo.z * idz);
+  r.k = {ax, ay, az, __fmaf_rn(-8388608.0f, ax, bx), __fmaf_rn(-8388608.0f, ay, by), __fmaf_rn(-8388608.0f, az, bz),
+      idx < 0 ? kSelHi : kSelLo, idy < 0 ? kSelHi : kSelLo, idz < 0 ? kSelHi : kSelLo,
+      idx < 0 ? kSelLo : kSelHi, idy < 0 ? kSelLo : kSelHi, idz < 0 ? kSelLo : kSelHi};
   return r;
 }
 // [tmin, tmax] seen from the shifted origin, widened by the rounding of t0
 __device__ __forceinline__ float shifted_tmin(float tmin, float t0) { return tmin - t0 - 4e-6f * t0; }
 __device__ __forceinline__ float shifted_tmax(float tmax, float t0) { return tmax - t0 + 4e-6f * t0; }
 
+// One child box (three words, one per axis: lo | hi << 16) against [tlo, thi]: entry distance and
+// far limit; the box is hit iff tn <= lim.  lim carries a relative slack of 5e-7 on both ends,
+// outward-going also for the negative distances of a shifted origin:
+// tn - tf <= 1e-6 * max(|tn|, |tf|) is implied by tn - 5e-7 |tn| <= tf + 5e-7 |tf|.
+__device__ __forceinline__ void child_dist(unsigned wx, unsigned wy, unsigned wz, const slab_consts& k, float tlo,
+    float thi, float& tn, float& lim) {
+  const float nx = __fmaf_rn(plane_float(wx, k.nx), k.ax, k.bx), fx = __fmaf_rn(plane_float(wx, k.fx), k.ax, k.bx);
+  const float ny = __fmaf_rn(plane_float(wy, k.ny), k.ay, k.by), fy = __fmaf_rn(plane_float(wy, k.fy), k.ay, k.by);
+  const float nz = __fmaf_rn(plane_float(wz, k.nz), k.az, k.bz), fz = __fmaf_rn(plane_float(wz, k.fz), k.az, k.bz);
+  tn             = fmaxf(fmaxf(nx, ny), fmaxf(nz, tlo));
+  const float tf = fminf(fminf(fx, fy), fminf(fz, thi));
+  lim            = __fmaf_rn(fmaxf(fabsf(tn), fabsf(tf)), 1e-6f, tf);
+}
+__device__ __forceinline__ void child_dists(const slot_words& s, const slab_consts& k, float tlo, float thi, float& tn0,
+    float& lim0, float& tn1, float& lim1) {
+  child_dist(s.w0, s.w1, s.w2, k, tlo, thi, tn0, lim0);
+  child_dist(s.w3, s.w4, s.w5, k, tlo, thi, tn1, lim1);
+}
 // both child boxes of an inner slot against [tlo, thi]
 __device__ __forceinline__ void child_boxes(const slot_words& s, const slab_consts& k, float tlo, float thi,
     bool& h0, bool& h1, float& tn0, float& tn1) {
-  auto lo16 = [](unsigned w) { return (float)(w & 0xffffu); };
-  auto hi16 = [](unsigned w) { return (float)(w >> 16); };
-  float a0 = __fmaf_rn(lo16(s.w0), k.ax, k.bx), b0 = __fmaf_rn(hi16(s.w1), k.ax, k.bx);
-  float a1 = __fmaf_rn(hi16(s.w0), k.ay, k.by), b1 = __fmaf_rn(lo16(s.w2), k.ay, k.by);
-  float a2 = __fmaf_rn(lo16(s.w1), k.az, k.bz), b2 = __fmaf_rn(hi16(s.w2), k.az, k.bz);
-  tn0       = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tlo));
-  float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), thi));
-  float c0 = __fmaf_rn(lo16(s.w3), k.ax, k.bx), d0 = __fmaf_rn(hi16(s.w4), k.ax, k.bx);
-  float c1 = __fmaf_rn(hi16(s.w3), k.ay, k.by), d1 = __fmaf_rn(lo16(s.w5), k.ay, k.by);
-  float c2 = __fmaf_rn(lo16(s.w4), k.az, k.bz), d2 = __fmaf_rn(hi16(s.w5), k.az, k.bz);
-  tn1       = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), tlo));
-  float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), thi));
-  // relative slack of 5e-7 on both ends, outward-going also for the negative distances of a shifted
-  // origin: tn - tf <= 1e-6 * max(|tn|, |tf|) is implied by tn - 5e-7 |tn| <= tf + 5e-7 |tf|
-  h0 = tn0 <= __fmaf_rn(fmaxf(fabsf(tn0), fabsf(tf0)), 1e-6f, tf0);
-  h1 = tn1 <= __fmaf_rn(fmaxf(fabsf(tn1), fabsf(tf1)), 1e-6f, tf1);
-}
-
-// The same two box tests as entry distance + far limit: child c is hit iff tn_c <= lim_c.
-__device__ __forceinline__ void child_dists(const slot_words& s, const slab_consts& k, float tlo, float thi, float& tn0,
-    float& lim0, float& tn1, float& lim1) {
-  auto lo16 = [](unsigned w) { return (float)(w & 0xffffu); };
-  auto hi16 = [](unsigned w) { return (float)(w >> 16); };
-  float a0 = __fmaf_rn(lo16(s.w0), k.ax, k.bx), b0 = __fmaf_rn(hi16(s.w1), k.ax, k.bx);
-  float a1 = __fmaf_rn(hi16(s.w0), k.ay, k.by), b1 = __fmaf_rn(lo16(s.w2), k.ay, k.by);
-  float a2 = __fmaf_rn(lo16(s.w1), k.az, k.bz), b2 = __fmaf_rn(hi16(s.w2), k.az, k.bz);
-  tn0       = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), tlo));
-  float tf0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), thi));
-  float c0 = __fmaf_rn(lo16(s.w3), k.ax, k.bx), d0 = __fmaf_rn(hi16(s.w4), k.ax, k.bx);
-  float c1 = __fmaf_rn(hi16(s.w3), k.ay, k.by), d1 = __fmaf_rn(lo16(s.w5), k.ay, k.by);
-  float c2 = __fmaf_rn(lo16(s.w4), k.az, k.bz), d2 = __fmaf_rn(hi16(s.w5), k.az, k.bz);
-  tn1       = fmaxf(fmaxf(fminf(c0, d0), fminf(c1, d1)), fmaxf(fminf(c2, d2), tlo));
-  float tf1 = fminf(fminf(fmaxf(c0, d0), fmaxf(c1, d1)), fminf(fmaxf(c2, d2), thi));
-  lim0 = __fmaf_rn(fmaxf(fabsf(tn0), fabsf(tf0)), 1e-6f, tf0);  // see child_boxes
-  lim1 = __fmaf_rn(fmaxf(fabsf(tn1), fabsf(tf1)), 1e-6f, tf1);
+  float lim0, lim1;
+  child_dists(s, k, tlo, thi, tn0, lim0, tn1, lim1);
+  h0 = tn0 <= lim0, h1 = tn1 <= lim1;
 }
 
 // What follows the two box tests of a node step, written in PTX so that it stays predicated:
@@ -513,7 +514,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
   const unsigned park_walk = park_base + (kParkSlots - 2) * kStackStride;  // a node step may park two more up to here
   unsigned       park_top  = park_base;
   float tlo = 0, thi = 0;  // [tmin, tmax] as seen from the (possibly shifted) box origin
-  slab_consts k = {0, 0, 0, 0, 0, 0};
+  slab_consts k = {0, 0, 0, 0, 0, 0, kSelLo, kSelLo, kSelLo, kSelHi, kSelHi, kSelHi};
   const uint4* __restrict__ slots = nullptr;
 
   while (true) {
