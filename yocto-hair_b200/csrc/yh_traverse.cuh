@@ -52,8 +52,9 @@ struct hit_record {
 // memory (seen in the SASS of the first version), and an inlined overflow path costs
 // predicated-off issue slots in the hot loop.
 constexpr unsigned kStackStride = kTraceBlock * 4u;  // bytes between two entries of one thread
-__device__ __noinline__ void stack_overflow_store(int* local, unsigned index, int v) { local[index] = v; }
-__device__ __noinline__ int  stack_overflow_load(const int* local, unsigned index) { return local[index]; }
+// (extern "C": node_control() calls them by name from PTX)
+extern "C" __device__ __noinline__ void yh_stack_overflow_store(int* local, unsigned index, int v) { local[index] = v; }
+extern "C" __device__ __noinline__ int  yh_stack_overflow_load(const int* local, unsigned index) { return local[index]; }
 struct trav_stack {
   unsigned base;   // shared-state-space byte address of this thread's entry 0
   unsigned top;    // ... of its next free entry
@@ -70,14 +71,14 @@ struct trav_stack {
   __device__ __forceinline__ unsigned mark() const { return top; }
   __device__ __forceinline__ void push(int v) {
     if (top < limit) asm volatile("st.shared.s32 [%0], %1;" ::"r"(top), "r"(v) : "memory");
-    else stack_overflow_store(local, (top - limit) / kStackStride, v);
+    else yh_stack_overflow_store(local, (top - limit) / kStackStride, v);
     top += kStackStride;
   }
   __device__ __forceinline__ int pop() {
     top -= kStackStride;
     int v;
     if (top < limit) asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(top) : "memory");
-    else v = stack_overflow_load(local, (top - limit) / kStackStride);
+    else v = yh_stack_overflow_load(local, (top - limit) / kStackStride);
     return v;
   }
 };
@@ -187,7 +188,9 @@ struct slab_consts {
 // this ray; the builder pads every box by that much (yh_scene.cu, fold_pad_steps).
 constexpr unsigned kSelLo = 0x7610u, kSelHi = 0x7632u;
 __device__ __forceinline__ float plane_float(unsigned w, unsigned sel) {
-  return __uint_as_float(__byte_perm(w, 0x4b000000u, sel));
+  unsigned m;  // prmt directly: __byte_perm() masks the selector first (one LOP3 per plane)
+  asm("prmt.b32 %0, %1, 0x4b000000, %2;" : "=r"(m) : "r"(w), "r"(sel));
+  return __uint_as_float(m);
 }
 struct shape_ray {
   slab_consts k;
@@ -269,7 +272,6 @@ __device__ __forceinline__ void node_control(float tn0, float lim0, float tn1, f
       ".reg .pred h0, h1, l0, l1, pa, pb, i0, i1, both, any, sec, fit, q, slow;\n\t"
       ".reg .s32 ch1, nr, fr;\n\t"
       ".reg .u32 t;\n\t"
-      ".reg .u64 a;\n\t"
       "setp.le.f32 h0, %5, %6;\n\t"
       "setp.le.f32 h1, %7, %8;\n\t"
       "setp.lt.s32 l0, %10, 0;\n\t"
@@ -297,11 +299,17 @@ __device__ __forceinline__ void node_control(float tn0, float lim0, float tn1, f
       "and.pred slow, both, !fit;\n\t"
       "@q st.shared.s32 [%2], fr;\n\t"
       "@!slow bra PUSHED;\n\t"
+      "{\n\t"
+      ".param .b64 p0;\n\t"
+      ".param .b32 p1;\n\t"
+      ".param .b32 p2;\n\t"
       "sub.u32 t, %2, %4;\n\t"
-      "shr.u32 t, t, 7;\n\t"  // entry index * 4 (entries are 512 bytes apart)
-      "cvt.u64.u32 a, t;\n\t"
-      "add.u64 a, a, %11;\n\t"
-      "st.s32 [a], fr;\n\t"
+      "shr.u32 t, t, 9;\n\t"
+      "st.param.b64 [p0], %11;\n\t"
+      "st.param.b32 [p1], t;\n\t"
+      "st.param.b32 [p2], fr;\n\t"
+      "call yh_stack_overflow_store, (p0, p1, p2);\n\t"
+      "}\n\t"
       "PUSHED:\n\t"
       "@both add.u32 %2, %2, %12;\n\t"
       // next node: the nearer child, else the top of the stack, else done
@@ -315,11 +323,17 @@ __device__ __forceinline__ void node_control(float tn0, float lim0, float tn1, f
       "and.pred q, q, fit;\n\t"
       "@q ld.shared.s32 %0, [%2];\n\t"
       "@!slow bra POPPED;\n\t"
+      "{\n\t"
+      ".param .b64 p0;\n\t"
+      ".param .b32 p1;\n\t"
+      ".param .b32 r0;\n\t"
       "sub.u32 t, %2, %4;\n\t"
-      "shr.u32 t, t, 7;\n\t"
-      "cvt.u64.u32 a, t;\n\t"
-      "add.u64 a, a, %11;\n\t"
-      "ld.s32 %0, [a];\n\t"
+      "shr.u32 t, t, 9;\n\t"
+      "st.param.b64 [p0], %11;\n\t"
+      "st.param.b32 [p1], t;\n\t"
+      "call (r0), yh_stack_overflow_load, (p0, p1);\n\t"
+      "ld.param.b32 %0, [r0];\n\t"
+      "}\n\t"
       "POPPED:\n\t"
       "}"
       : "+r"(cur), "+r"(park_top), "+r"(st.top)
