@@ -205,7 +205,7 @@ struct wavefront_io {  // by value: references to kernel parameters would force 
 // Closest hit for every slot of the active queue, then the slot id goes to the
 // miss / surface / hair queue.  Persistent warps, q.count[5] is the ray cursor.
 #ifndef YH_INTERSECT_BLOCKS
-#define YH_INTERSECT_BLOCKS 6
+#define YH_INTERSECT_BLOCKS 7
 #endif
 __global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
