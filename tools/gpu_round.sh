@@ -10,6 +10,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --c
    python bench.py --steps 1 --warmup 1 --spp-step 4 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 34 -c 1 -f -o gpurun_out/k_intersect \
    python bench.py --steps 1 --warmup 1 --spp-step 4 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 60 -c 1 -f -o gpurun_out/k_shade \
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:^k_shade$' -s 61 -c 2 -f -o gpurun_out/k_shade \
    python bench.py --steps 1 --warmup 1 --spp-step 4 --no-cpu-baseline > gpurun_out/ncu_full_shade.log 2>&1
 tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench_c3.json
