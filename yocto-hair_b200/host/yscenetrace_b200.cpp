@@ -3,7 +3,7 @@
 // through the reference's own yocto_sceneio, same image writers) with the
 // per-sample hot path running in the CUDA library behind include/yocto_hair_b200.h.
 //
-//   yscenetrace_b200 [--backend cuda|cpu] [--spp-batch N] [--seed S] [--device D]
+//   yscenetrace_b200 [--backend cuda|cpu] [--loader fast|reference] [--spp-batch N] [--seed S] [--device D]
 //                    [--camera NAME] [-r RES] [-s SAMPLES] [-t path] [-b BOUNCES]
 //                    [--clamp C] [--save-batch] [-o out.pfm] scene.json
 //
@@ -19,6 +19,7 @@
 #include <map>
 #include <memory>
 
+#include "yh_sceneio.h"
 #include "yocto_pathtrace_b200.h"
 
 using namespace std::string_literals;
@@ -108,10 +109,12 @@ int main(int argc, const char* argv[]) {
   auto spp_batch   = 16;
   auto device      = 0;
   auto seed        = (int)ptr::default_seed;
+  auto loader      = "fast"s;
 
   auto cli = cli::make_cli("yscenetrace_b200", "Offline hair path tracing on B200");
   add_option(cli, "--backend", backend, "cuda (B200 library) or cpu (the reference's own code).");
   add_option(cli, "--spp-batch", spp_batch, "Samples per pixel per device call.");
+  add_option(cli, "--loader", loader, "fast (bulk PLY reader, yh_sceneio) or reference (yocto_sceneio).");
   add_option(cli, "--device", device, "CUDA device.");
   add_option(cli, "--seed", seed, "Render seed (trace_params::seed).");
   add_option(cli, "--camera", camera_name, "Camera name.");
@@ -130,7 +133,12 @@ int main(int argc, const char* argv[]) {
 
   auto ioscene = std::make_unique<sio::model>();
   auto ioerror = ""s;
-  if (!load_scene(filename, ioscene.get(), ioerror, cli::print_progress)) cli::print_fatal(ioerror);
+  if (loader != "fast" && loader != "reference") cli::print_fatal("unknown loader " + loader);
+  auto tl0    = std::chrono::steady_clock::now();
+  auto loaded = loader == "fast" ? gpu::load_scene(filename, ioscene.get(), ioerror, cli::print_progress)
+                                 : sio::load_scene(filename, ioscene.get(), ioerror, cli::print_progress);
+  if (!loaded) cli::print_fatal(ioerror);
+  printf("loader %s: %.3f s\n", loader.c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - tl0).count());
   auto scene  = std::make_unique<ptr::scene>();
   auto camera = build_trace_scene(scene.get(), ioscene.get(), get_camera(ioscene.get(), camera_name));
   ioscene.reset();
