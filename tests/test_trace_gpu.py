@@ -78,6 +78,26 @@ def test_render_bit_identical(name, ref):
     st_r.close(); rs.close(); st_d.close(); ds.close()
 
 
+@pytest.mark.parametrize("alpha", [0.0, 2.0])
+@pytest.mark.parametrize("beta_n", [0.3, 0.6, 0.9])
+@pytest.mark.parametrize("beta_m", [0.1, 0.25, 0.6])
+def test_bsdf_parameter_sweep_renders_bit_identical(beta_m, beta_n, alpha, ref):
+    """BASELINE config C4 (the README's longitudinal / azimuthal roughness and scale-tilt sweep) on the hair
+    block, at a size the CPU checker renders in a second: every sweep point is bit-identical."""
+    scene, cam = synth.hair_block_scene(6_000, aspect=1.0, beta_m=beta_m, beta_n=beta_n, alpha=alpha)
+    p = make_params(resolution=64)
+    rs = ref.scene(scene)
+    st_r = rs.state(cam, p)
+    st_r.trace_samples(3)
+    a_r = st_r.download()[1]
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    st_d = ds.init_state(cam, p)
+    st_d.trace_samples(3)
+    a_d = st_d.download()[1]
+    assert np.array_equal(a_r.view(np.uint32), a_d.view(np.uint32))
+    st_r.close(); rs.close(); st_d.close(); ds.close()
+
+
 def rel_mse(x, y):
     """mean((x - y)^2 / (y^2 + 1e-2)) on linear RGB."""
     x, y = x[..., :3].astype(np.float64), y[..., :3].astype(np.float64)
