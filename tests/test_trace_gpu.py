@@ -195,6 +195,55 @@ def test_edge_cases(ref):
         st_r.close(); rs.close(); st_d.close(); ds.close()
 
 
+@pytest.mark.parametrize("quality", [0, 1], ids=["lbvh", "sah"])
+def test_deep_tree_uses_the_stack_overflow(quality, ref):
+    """Sticks at geometrically spaced positions (ratio 2 over 40 octaves): every split peels off the largest
+    one, so the tree is a chain and a ray that starts at the small end pushes one far child per level - the
+    traversal stack grows past its 16 shared-memory entries into the local overflow (yh_traverse.cuh,
+    yh_stack_overflow_store / _load).  Hit records must still be the reference's, from both builders."""
+    n = 40
+    x = (2.0 ** (np.arange(n) - 20)).astype(np.float32)
+    pos = np.zeros((2 * n, 3), np.float32)
+    pos[0::2, 0], pos[1::2, 0] = x, x
+    pos[0::2, 1], pos[1::2, 1] = -0.1 * x, 0.1 * x
+    rad = np.repeat(0.02 * x, 2).astype(np.float32)
+    lines = np.stack([np.arange(0, 2 * n, 2), np.arange(1, 2 * n, 2)], axis=1).astype(np.int32)
+    sc = tiny_scene(lines, pos, rad)
+    rng = np.random.default_rng(11)
+    m = 30_000
+    k = rng.integers(0, n, m)
+    x0 = (x[k] * rng.uniform(0.55, 0.95, m)).astype(np.float32)
+    slope = rng.uniform(-0.15, 0.15, (m, 2)).astype(np.float32)
+    o = np.stack([x0, slope[:, 0] * x0, 0.01 * slope[:, 1] * x0], axis=1).astype(np.float32)
+    d = np.stack([np.ones(m, np.float32), slope[:, 0], 0.01 * slope[:, 1]], axis=1).astype(np.float32)
+    d[m // 2:] *= -1  # half of them walk towards the small end
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = make_rays(o, d)
+    rs = ref.scene(sc)
+    ds = DeviceScene(sc).init_bvh(0, 0, quality).init_lights()
+    hr, hd = rs.intersect(rays.view(np.float32).reshape(-1, 8)), ds.intersect(rays)
+    assert 0.2 < hr["hit"].mean() < 0.98
+    assert_hits_identical(hr, hd)
+    rs.close(); ds.close()
+
+
+@pytest.mark.parametrize("offset", [(300.0, -200.0, 500.0), (0.0, 4000.0, 0.0)], ids=["far", "very_far_y"])
+def test_shape_far_from_its_origin(offset, ref):
+    """Object-space coordinates far from the origin compared with the shape's size (|p| / extent up to 4000):
+    the 16-bit grid, the folded plane decode and its padding (yh_scene.cu fold_pad_steps) must stay
+    conservative where fp32 has few bits left for the shape itself.  Hit records stay bit-exact."""
+    sc, cam = synth.curly_hair_scene(6_000, sky=False)
+    sh = sc.shapes[0]
+    sh.positions = (sh.positions + np.array(offset, np.float32)).astype(np.float32)
+    rays = synth.random_rays(sc, 150_000)
+    rs = ref.scene(sc)
+    ds = DeviceScene(sc).init_bvh().init_lights()
+    hr, hd = rs.intersect(rays.view(np.float32).reshape(-1, 8), threads=8), ds.intersect(rays)
+    assert 0.02 < hr["hit"].mean() < 0.98
+    assert_hits_identical(hr, hd)
+    rs.close(); ds.close()
+
+
 def test_empty_shape_and_zero_bounces(ref):
     sc = tiny_scene(np.zeros((0, 2), np.int32), np.zeros((0, 3), np.float32), np.zeros((0,), np.float32))
     ds = DeviceScene(sc).init_bvh().init_lights()
