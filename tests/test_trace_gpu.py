@@ -195,14 +195,15 @@ def test_edge_cases(ref):
         st_r.close(); rs.close(); st_d.close(); ds.close()
 
 
+@pytest.mark.parametrize("n,ratio", [(40, 2.0), (200, 1.25)], ids=["40x2", "200x1.25"])
 @pytest.mark.parametrize("quality", [0, 1], ids=["lbvh", "sah"])
-def test_deep_tree_uses_the_stack_overflow(quality, ref):
+def test_deep_tree_uses_the_stack_overflow(quality, n, ratio, ref):
     """Sticks at geometrically spaced positions (ratio 2 over 40 octaves): every split peels off the largest
     one, so the tree is a chain and a ray that starts at the small end pushes one far child per level - the
     traversal stack grows past its 16 shared-memory entries into the local overflow (yh_traverse.cuh,
-    yh_stack_overflow_store / _load).  Hit records must still be the reference's, from both builders."""
-    n = 40
-    x = (2.0 ** (np.arange(n) - 20)).astype(np.float32)
+    yh_stack_overflow_store / _load).  With 200 sticks a pure SAH chain would be deeper than the stack (96):
+    the builder halves ranges below depth 64 (kSahMaxDepth).  Hit records must still be the reference's."""
+    x = (ratio ** (np.arange(n) - n // 2)).astype(np.float32)
     pos = np.zeros((2 * n, 3), np.float32)
     pos[0::2, 0], pos[1::2, 0] = x, x
     pos[0::2, 1], pos[1::2, 1] = -0.1 * x, 0.1 * x

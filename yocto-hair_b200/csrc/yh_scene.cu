@@ -456,14 +456,19 @@ static int sah_split(const ref_bounds* refs, int* order, int s, int e) {
   if (mid == s || mid == e) mid = (s + e) / 2;
   return mid;
 }
-static void sah_build_range(const ref_bounds* refs, sah_topology& t, int node, int s, int e, int depth) {
-  struct item { int node, s, e; };
-  std::vector<item>              todo{{node, s, e}};
+// Tree depth at which the builder stops looking for the best split and halves the range instead: the
+// traversal stack holds one entry per level (kStackShared + kStackLocal = 96, yh_traverse.cuh), and inputs
+// such as geometrically spaced primitives make every SAH split peel off ONE reference.  Below this depth
+// the subtree is balanced, so the total depth stays under kSahMaxDepth + log2(references) < 96.
+constexpr int kSahMaxDepth = 64;
+static void sah_build_range(const ref_bounds* refs, sah_topology& t, int node, int s, int e, int depth, int tree_depth) {
+  struct item { int node, s, e, level; };
+  std::vector<item>              todo{{node, s, e, tree_depth}};
   std::vector<std::future<void>> spawned;
   while (!todo.empty()) {
     item it = todo.back();
     todo.pop_back();
-    int mid = sah_split(refs, t.order.data(), it.s, it.e);
+    int mid = it.level >= kSahMaxDepth ? (it.s + it.e) / 2 : sah_split(refs, t.order.data(), it.s, it.e);
     int ml = mid - it.s, mr = it.e - mid;
     int child[2] = {ml == 1 ? ~it.s : it.node + 1, mr == 1 ? ~mid : it.node + ml};
     t.left[it.node] = child[0], t.right[it.node] = child[1];
@@ -476,10 +481,10 @@ static void sah_build_range(const ref_bounds* refs, sah_topology& t, int node, i
       t.parent_inner[child[c]] = it.node;
       int cnt = range[c][1] - range[c][0];
       if (c == 0 && depth < 6 && cnt > (1 << 14) && (it.e - it.s) - cnt > (1 << 14)) {  // big sibling pair: fork
-        int cn = child[c], cs = range[c][0], ce = range[c][1];
-        spawned.push_back(std::async(std::launch::async, [refs, &t, cn, cs, ce, depth]() { sah_build_range(refs, t, cn, cs, ce, depth + 1); }));
+        int cn = child[c], cs = range[c][0], ce = range[c][1], cl = it.level + 1;
+        spawned.push_back(std::async(std::launch::async, [refs, &t, cn, cs, ce, depth, cl]() { sah_build_range(refs, t, cn, cs, ce, depth + 1, cl); }));
       } else {
-        todo.push_back({child[c], range[c][0], range[c][1]});
+        todo.push_back({child[c], range[c][0], range[c][1], it.level + 1});
       }
     }
     if (!spawned.empty() && depth < 6) depth++;  // forks deepen the task tree, not the loop
@@ -491,7 +496,7 @@ static void sah_build(const std::vector<ref_bounds>& refs, sah_topology& t) {
   t.order.resize(R);
   for (int i = 0; i < R; i++) t.order[i] = i;
   t.left.assign(R - 1, 0), t.right.assign(R - 1, 0), t.parent_inner.assign(R - 1, -1), t.parent_leaf.assign(R, -1);
-  sah_build_range(refs.data(), t, 0, 0, R, 0);
+  sah_build_range(refs.data(), t, 0, 0, R, 0, 0);
 }
 
 static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
