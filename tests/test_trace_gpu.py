@@ -400,3 +400,35 @@ def test_other_shaders_bit_identical(name, shader, ref):
         assert np.array_equal(s_r, s_d) and np.array_equal(rng_r, st_d.rng())
         assert np.array_equal(a_r.view(np.uint32), a_d.view(np.uint32))
         st_r.close(); rs.close(); st_d.close(); ds.close()
+
+
+@pytest.mark.parametrize("shader", [1, 0, 2], ids=["path", "naive", "eyelight"])
+def test_surface_lobes_bit_identical(shader, ref):
+    """specular / metal / thin-transmission lobes, their delta forms and opacity on the
+    triangles around the hair (yh_surface.cuh) against the reference build: renders bit-identical, all
+    three shaders that evaluate materials."""
+    if ref.kind != "reference":
+        pytest.skip("the plain-C port restates the hair path only; these lobes are checked against the reference build")
+    scene, cam = synth.surface_lobes_scene()
+    p = make_params(resolution=144, shader=shader)
+    rs = ref.scene(scene)
+    st_r = rs.state(cam, p)
+    st_r.trace_samples(4)
+    _, a_r, s_r, rng_r = st_r.download()
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    st_d = ds.init_state(cam, p)
+    st_d.trace_samples(4)
+    _, a_d, s_d = st_d.download()
+    assert np.array_equal(s_r, s_d) and np.array_equal(rng_r, st_d.rng())
+    diff = np.nonzero((a_r.view(np.uint32) != a_d.view(np.uint32)).any(axis=-1))
+    assert diff[0].size == 0, "first differing pixels (y, x): %s" % list(zip(diff[0][:8], diff[1][:8]))
+    assert np.isfinite(a_d).all() and a_d[..., :3].max() > 0
+    st_r.close(); rs.close(); st_d.close(); ds.close()
+
+
+def test_refraction_is_refused():
+    scene, _ = synth.surface_lobes_scene(500, sky=False)
+    scene.materials[2].transmission, scene.materials[2].thin = 1.0, False
+    with pytest.raises(capi.YhError) as e:
+        DeviceScene(scene)
+    assert e.value.status == capi.YH_ERR_UNSUPPORTED

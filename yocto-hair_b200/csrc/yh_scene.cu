@@ -736,9 +736,9 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
   // ---- validate: anything outside the hot-path scope fails loudly ----
   for (int i = 0; i < d->num_materials; i++) {
     auto& m = d->materials[i];
-    if (m.specular != 0 || m.metallic != 0 || m.transmission != 0)
+    if (m.transmission != 0 && !m.thin)
       return fail(YH_ERR_UNSUPPORTED,
-          "material %d: specular/metallic/transmission lobes are outside the hair hot path (SURVEY 8a P13)", i);
+          "material %d: refraction (transmission with thin = false) needs the volume stack of trace_path, which is not built", i);
     if (m.scattering[0] != 0 || m.scattering[1] != 0 || m.scattering[2] != 0)
       return fail(YH_ERR_UNSUPPORTED, "material %d: volumetric scattering is outside the hot path", i);
     int texs[] = {m.emission_tex, m.color_tex, m.specular_tex, m.metallic_tex, m.roughness_tex,
@@ -750,6 +750,11 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
     auto& o = d->objects[i];
     if (o.shape < 0 || o.shape >= d->num_shapes || o.material < 0 || o.material >= d->num_materials)
       return fail(YH_ERR_INVALID, "object %d: shape/material index out of range", i);
+    // the hair kernel assumes the hair lobe alone: a line shape whose material also has surface lobes would make
+    // is_delta() (yocto_pathtrace.cpp:495) depend on them
+    auto& m = d->materials[o.material];
+    if (d->shapes[o.shape].num_lines > 0 && (m.specular != 0 || m.metallic != 0 || m.transmission != 0))
+      return fail(YH_ERR_UNSUPPORTED, "object %d: specular / metallic / transmission on a line shape is not built", i);
   }
   for (int i = 0; i < d->num_environments; i++)
     if (d->environments[i].emission_tex >= d->num_textures)
@@ -803,6 +808,7 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
     auto&        m = d->materials[i];
     dev_material dm{};
     dm.emission = to_vec(m.emission), dm.color = to_vec(m.color), dm.opacity = m.opacity, dm.thin = m.thin;
+    dm.specular = m.specular, dm.metallic = m.metallic, dm.roughness = m.roughness, dm.ior = m.ior, dm.transmission = m.transmission;
     dm.eumelanin = m.eumelanin, dm.pheomelanin = m.pheomelanin, dm.sigma_a = to_vec(m.sigma_a);
     dm.beta_m = m.beta_m, dm.beta_n = m.beta_n, dm.alpha = m.alpha, dm.eta = m.eta;
     sc->materials.push_back(dm);

@@ -63,6 +63,7 @@ struct dev_material {
   vec3f color;
   float opacity;
   int   thin;
+  float specular, metallic, roughness, ior, transmission;  // surface lobes (yh_surface.cuh)
   // hair block (yocto_pathtrace.h:310-316)
   float eumelanin, pheomelanin;
   vec3f sigma_a;

@@ -5,6 +5,7 @@
 #pragma once
 #include "yh_hair.cuh"
 #include "yh_rng.cuh"
+#include "yh_surface.cuh"
 #include "yh_traverse.cuh"
 
 namespace yh {
@@ -194,15 +195,6 @@ __device__ __forceinline__ float sample_lights_pdf(const dev_scene& sc, const ve
   }
   pdf *= div_(1.0f, (float)sc.num_lights);  // sample_uniform_pdf
   return pdf;
-}
-
-// sample_hemisphere_cos(normal, ruv), yocto_math.h:4873-4879
-__device__ __forceinline__ vec3f sample_hemisphere_cos(const vec3f& normal, const vec2f& ruv) {
-  float z   = sqrt_(ruv.y);
-  float r   = sqrt_(1 - z * z);
-  float phi = 2 * pif * ruv.x;
-  vec3f local = {r * cosf_(phi), r * sinf_(phi), z};
-  return transform_direction(basis_fromz(normal), local);
 }
 
 }  // namespace yh

@@ -286,47 +286,58 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     float alpha = 1.0f;
     radiance    = radiance + weight * emission;  // :1437
 
-    // eval_brdf, :405-492: with specular = metallic = transmission = 0 the only
-    // surface lobe is diffuse = color and roughness ends at 1 (never delta).
+    // eval_brdf, :405-492: the hair lobe for line shapes (HAIR), the surface lobes of yh_surface.cuh
+    // for triangles; a surface with roughness 0 is a delta brdf (:495) and takes the sample_delta branch
     vec3f         incoming;
     vec3f         brdfcos;
     float         brdf_pdf;
     hair_brdf     hb;
     hair_wo_terms ht;
+    surface_brdf  sb;
+    bool          delta = false;
     if (HAIR) {
       hair_material hm = {mat.sigma_a, mat.beta_m, mat.beta_n, mat.alpha, mat.eta, mat.color, mat.eumelanin,
           mat.pheomelanin};
       hb = eval_hair_brdf(hm, uv.y, normal, tangent);  // :474-490
       ht = hair_prepare_wo(hb, outgoing);
+    } else {
+      surface_material sm = {mat.color, mat.specular, mat.metallic, mat.roughness, mat.ior, mat.transmission};
+      sb    = eval_surface_brdf(sm, normal, outgoing);
+      delta = is_delta(sb);
     }
-    vec3f diffuse     = mat.color;
-    float dmax        = max3(diffuse);
-    float diffuse_pdf = dmax != 0 ? div_(dmax, dmax) : 0.0f;  // diffuse_pdf / pdf_sum, :456-471
+    bool continues = true;  // the path goes on to `incoming` (false: this vertex ended the sample)
     if (SHADER == YH_SHADER_EYELIGHT) {  // trace_eyelight, :1576-1633: the light sits at the eye
       vec3f f;
       if (HAIR) {
         float unused_pdf;
         eval_hair_scattering_and_pdf(hb, ht, outgoing, f, unused_pdf);
       } else {
-        float no = dot(normal, outgoing);
-        f        = {0, 0, 0};
-        if (nonzero(diffuse)) f = f + diffuse * ((no <= 0) ? vec3f{0, 0, 0} : vec3f{1, 1, 1} / pif * no);
+        f = eval_brdfcos(sb, normal, outgoing, outgoing);
       }
       radiance = radiance + weight * pif * f;
-      finished = true;  // never delta here (roughness ends at 1, :446-452): the loop breaks after one vertex
+      if (!delta) {
+        finished = true, continues = false;  // :1618
+      } else {  // mirrors and glass sheets are followed, :1619-1626 (no Russian roulette, bound max(bounces, 4))
+        float rnl = rand1f(rng);
+        incoming  = sample_delta(sb, normal, outgoing, rnl);
+        weight    = weight * (eval_delta(sb, normal, outgoing, incoming) / sample_delta_pdf(sb, normal, outgoing, incoming));
+        if ((weight == vec3f{0, 0, 0}) || !isfinite3(weight)) finished = true;
+        bounce += 1;
+        if (bounce >= (tc.bounces > 4 ? tc.bounces : 4)) finished = true;
+      }
+    } else {
+    if (delta) {  // :1452-1456, trace_naive :1552-1556
+      float rnl = rand1f(rng);
+      incoming  = sample_delta(sb, normal, outgoing, rnl);
+      weight    = weight * (eval_delta(sb, normal, outgoing, incoming) / sample_delta_pdf(sb, normal, outgoing, incoming));
     } else {
     // MIS one-sample model, :1441-1451 (trace_naive, :1548-1551, always samples the BSDF).  Argument
     // evaluation order of the oracle build (GCC, right to left): rand2f before rand1f, see camera_ray().
     if (SHADER == YH_SHADER_NAIVE || rand1f(rng) < 0.5f) {
       vec2f rn  = rand2f(rng);
       float rnl = rand1f(rng);
-      if (HAIR) {
-        incoming = sample_hair_scattering(hb, ht, rn);  // :1133-1135
-      } else {  // sample_brdfcos diffuse lobe, :1141-1144; yocto_math.h:4515-4519
-        incoming = {0, 0, 0};
-        if (diffuse_pdf != 0 && rnl < diffuse_pdf && !(dot(normal, outgoing) <= 0))
-          incoming = sample_hemisphere_cos(normal, rn);
-      }
+      if (HAIR) incoming = sample_hair_scattering(hb, ht, rn);  // :1133-1135
+      else incoming = sample_brdfcos(sb, normal, outgoing, rnl, rn);
     } else {
       vec2f ruv = rand2f(rng);
       float rel = rand1f(rng);
@@ -336,15 +347,8 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     if (HAIR) {
       eval_hair_scattering_and_pdf(hb, ht, incoming, brdfcos, brdf_pdf);  // :1071-1073, :1219-1221
     } else {
-      // eval_diffuse_reflection / sample_diffuse_reflection_pdf, yocto_math.h:4427, :4572
-      brdfcos  = {0, 0, 0};
-      brdf_pdf = 0;
-      float ni = dot(normal, incoming), no = dot(normal, outgoing);
-      if (nonzero(diffuse)) {
-        vec3f lobe = (ni <= 0 || no <= 0) ? vec3f{0, 0, 0} : vec3f{1, 1, 1} / pif * ni;
-        brdfcos    = brdfcos + diffuse * lobe;
-      }
-      if (diffuse_pdf != 0) brdf_pdf += diffuse_pdf * ((ni <= 0 || no <= 0) ? 0.0f : div_(ni, pif));
+      brdfcos  = eval_brdfcos(sb, normal, outgoing, incoming);
+      brdf_pdf = sample_brdfcos_pdf(sb, normal, outgoing, incoming);
     }
     if (SHADER == YH_SHADER_NAIVE) {
       weight = weight * (brdfcos / brdf_pdf);
@@ -352,9 +356,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       float light_pdf = sample_lights_pdf(sc, position, incoming, st, light_rays);
       weight          = weight * (brdfcos / (0.5f * brdf_pdf + 0.5f * light_pdf));
     }
-
-    st_stream(&ps.ray_o[slot], make_float4(position.x, position.y, position.z, 0));
-    st_stream(&ps.ray_d[slot], make_float4(incoming.x, incoming.y, incoming.z, 0));
+    }
 
     // :1500-1507, then the loop condition bounce < params.bounces
     if ((weight == vec3f{0, 0, 0}) || !isfinite3(weight)) finished = true;
@@ -365,6 +367,10 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     }
     bounce += 1;
     if (bounce >= tc.bounces) finished = true;
+    }
+    if (continues) {
+      st_stream(&ps.ray_o[slot], make_float4(position.x, position.y, position.z, 0));
+      st_stream(&ps.ray_d[slot], make_float4(incoming.x, incoming.y, incoming.z, 0));
     }
     w4.w = alpha;
   }

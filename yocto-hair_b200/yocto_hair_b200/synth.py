@@ -229,6 +229,54 @@ def hair_block_scene(num_segments=200_000, seed=7, aspect=1.777777778, **hair):
     return sc, cam
 
 
+SURFACE_MATERIALS = {
+    "coated": dict(color=(0.8, 0.3, 0.1), specular=1, roughness=0.3),                # diffuse + rough dielectric coat
+    "coated_smooth": dict(color=(0.2, 0.5, 0.8), specular=1, roughness=0),           # roughness clamps to 0.03^2 (diffuse != 0)
+    "gold": dict(color=(1.0, 0.78, 0.34), metallic=1, roughness=0.25),               # rough conductor
+    "mirror": dict(color=(0.9, 0.9, 0.9), metallic=1, roughness=0),                  # delta conductor
+    "varnish": dict(color=(0, 0, 0), specular=1, roughness=0),                       # delta dielectric reflection only
+    "frosted": dict(color=(0.9, 0.95, 1.0), transmission=1, roughness=0.4, thin=True),   # rough thin-sheet transmission
+    "sheet": dict(color=(0.7, 0.9, 0.7), transmission=1, specular=1, roughness=0, thin=True),  # delta transmission + reflection
+    "mixed": dict(color=(0.6, 0.6, 0.2), specular=0.7, metallic=0.3, transmission=0.4, roughness=0.5, ior=1.33, thin=True),
+    "veil": dict(color=(0.5, 0.5, 0.9), specular=1, roughness=0.2, opacity=0.6),      # opacity pass-through in front of lobes
+}
+
+
+def surface_lobes_scene(num_segments=4_000, seed=7, sky=True):
+    """a hair block among spheres and sheets that carry every surface lobe of the reference's
+    material model that the device builds (diffuse, specular, metal, thin transmission, delta forms, opacity),
+    a diffuse floor, one area light and the sky."""
+    sc = Scene()
+    sc.shapes.append(make_hair_block(num_segments, seed))      # 0
+    sc.shapes.append(make_uv_sphere((24, 12), radius=0.38))    # 1
+    sc.shapes.append(make_arealight_quad())                    # 2 (6 x 6 quad: floor, sheets, light)
+    sc.materials.append(Material(eumelanin=1.3))
+    sc.objects.append(Object(shape=0, material=0, frame=(1, 0, 0, 0, 0, 1, 0, -1, 0, 0.5, 1, -0.5)))
+    sc.materials.append(Material(color=(0.7, 0.7, 0.7)))       # floor: plain diffuse
+    sc.objects.append(Object(shape=2, material=1, frame=(1, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0)))
+    names = list(SURFACE_MATERIALS)
+    for k, name in enumerate(names):
+        sc.materials.append(Material(**SURFACE_MATERIALS[name]))
+        m = len(sc.materials) - 1
+        if name in ("frosted", "sheet", "veil"):               # upright sheets in front of the block
+            s = 0.12
+            x = -1.6 + 1.1 * (["frosted", "sheet", "veil"].index(name))
+            sc.objects.append(Object(shape=2, material=m, frame=(s, 0, 0, 0, s, 0, 0, 0, s, x, 0.5, 1.2)))
+        else:
+            j = [n for n in names if n not in ("frosted", "sheet", "veil")].index(name)
+            sc.objects.append(Object(shape=1, material=m, frame=(1, 0, 0, 0, 1, 0, 0, 0, 1, -2.0 + 0.8 * j, 0.38, 0.3 * (j % 2))))
+    sc.materials.append(Material(emission=(20, 20, 20)))
+    sc.objects.append(Object(shape=2, material=len(sc.materials) - 1,
+                             frame=lookat_frame((3, 6, 5), (0, 0.5, 0), (0, 1, 0), inv_xz=True)))
+    if sky:
+        sc.textures.append(make_sky_texture())
+        sc.environments.append(Environment(emission=(1, 1, 1), emission_tex=0))
+    else:
+        sc.environments.append(Environment(emission=(1, 1, 1)))
+    cam = Camera.from_lookat((0.0, 2.2, 6.0), (0.0, 0.5, 0.0), (0, 1, 0), lens=0.05, aspect=1.5)
+    return sc, cam
+
+
 def make_hair_curl(num_segments=40_000, seed=7, sub=4, beziers_per_fibre=10) -> Shape:
     """A hanging lock of helical fibres around the y axis (stand-in for shapes/hair-curl.ply)."""
     rng = np.random.default_rng(seed)
