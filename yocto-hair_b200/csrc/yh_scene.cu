@@ -736,11 +736,6 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
   // ---- validate: anything outside the hot-path scope fails loudly ----
   for (int i = 0; i < d->num_materials; i++) {
     auto& m = d->materials[i];
-    if (m.transmission != 0 && !m.thin)
-      return fail(YH_ERR_UNSUPPORTED,
-          "material %d: refraction (transmission with thin = false) needs the volume stack of trace_path, which is not built", i);
-    if (m.scattering[0] != 0 || m.scattering[1] != 0 || m.scattering[2] != 0)
-      return fail(YH_ERR_UNSUPPORTED, "material %d: volumetric scattering is outside the hot path", i);
     int texs[] = {m.emission_tex, m.color_tex, m.specular_tex, m.metallic_tex, m.roughness_tex,
         m.transmission_tex, m.spectint_tex, m.scattering_tex, m.opacity_tex, m.normal_tex};
     for (int t : texs)
@@ -809,6 +804,8 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
     dev_material dm{};
     dm.emission = to_vec(m.emission), dm.color = to_vec(m.color), dm.opacity = m.opacity, dm.thin = m.thin;
     dm.specular = m.specular, dm.metallic = m.metallic, dm.roughness = m.roughness, dm.ior = m.ior, dm.transmission = m.transmission;
+    dm.scattering = to_vec(m.scattering), dm.scanisotropy = m.scanisotropy, dm.trdepth = m.trdepth;
+    if (!m.thin && m.transmission != 0) sc->has_volumes = true;  // has_volume(), yocto_pathtrace.cpp:529-531
     dm.eumelanin = m.eumelanin, dm.pheomelanin = m.pheomelanin, dm.sigma_a = to_vec(m.sigma_a);
     dm.beta_m = m.beta_m, dm.beta_n = m.beta_n, dm.alpha = m.alpha, dm.eta = m.eta;
     sc->materials.push_back(dm);

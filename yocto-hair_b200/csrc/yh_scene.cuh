@@ -64,6 +64,8 @@ struct dev_material {
   float opacity;
   int   thin;
   float specular, metallic, roughness, ior, transmission;  // surface lobes (yh_surface.cuh)
+  vec3f scattering;                                        // volume behind a refractive surface (!thin && transmission)
+  float scanisotropy, trdepth;
   // hair block (yocto_pathtrace.h:310-316)
   float eumelanin, pheomelanin;
   vec3f sigma_a;
@@ -150,6 +152,7 @@ struct yh_scene {
   yh::dev_buffer<yh::dev_environment> d_environments;
   yh::dev_buffer<yh::dev_light>       d_lights;
   bool bvh_built = false, lights_built = false;
+  bool has_volumes = false;  // some material is refractive (!thin && transmission): paths carry a volume state
   int  device = 0;
   yh_bvh_stats stats{};
   yh::dev_scene view() const;

@@ -48,6 +48,10 @@ struct path_state {
   int*                pixel;      // image pixel index j * width + i
   float4*             accum;      // image layout, pixel.accumulated
   int*                samples;    // image layout, pixel.samples
+  // only when the scene has a refractive material (else null): the one-entry volume stack of trace_path
+  float4*             vol_density;  // vsdf.density.xyz, vsdf.anisotropy
+  float4*             vol_scatter;  // vsdf.scatter.xyz, 1 while the path is inside the volume (0: stack empty)
+  float*              hit_dist;     // intersection.distance of the current vertex
 };
 
 struct queues {
@@ -125,6 +129,7 @@ __device__ __forceinline__ void start_sample(const path_state& ps, const dev_cam
   st_stream(&ps.ray_d[slot], make_float4(ray.d.x, ray.d.y, ray.d.z, 0));
   st_stream(&ps.weight[slot], make_float4(1, 1, 1, 0));
   st_stream(&ps.radiance[slot], make_float4(0, 0, 0, __int_as_float(0)));
+  if (ps.vol_scatter) st_stream(&ps.vol_scatter[slot], make_float4(0, 0, 0, 0));  // a new path starts outside every volume
 }
 
 // trace_sample tail, :1683-1688, then regenerate or retire the slot.
@@ -195,6 +200,7 @@ struct wavefront_io {  // by value: references to kernel parameters would force 
   }
   __device__ __forceinline__ void store(int slot, const hit_record& h) const {
     st_stream(&ps.hit[slot], make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y)));
+    if (ps.hit_dist) st_stream(&ps.hit_dist[slot], h.distance);
     int kind     = !h.hit ? 0 : (sc.shapes[sc.objects[h.object].shape].is_lines ? 2 : 1);
     queue_push(q.miss, q.count + 2, kind == 0, slot);
     queue_push(q.surface, q.count + 3, kind == 1, slot);
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(256) k_shade_miss(dev_scene sc, path_state ps,
 
 // The body of trace_path for one surface vertex, :1417-1507.  HAIR selects the
 // lobe set at compile time so the two kernels stay divergence-free inside.
-template <bool HAIR, int SHADER>
+template <bool HAIR, int SHADER, bool VOL>
 __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_state& ps, const dev_camera& cam,
     const trace_consts& tc, int slot, trav_stack& st, unsigned int& light_rays) {
   float4    o4 = ld_stream(&ps.ray_o[slot]), d4 = ld_stream(&ps.ray_d[slot]), w4 = ld_stream(&ps.weight[slot]), r4 = ld_stream(&ps.radiance[slot]);
@@ -256,9 +262,64 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
   vec2f     uv = {__int_as_float(h4.z), __int_as_float(h4.w)};
   const dev_object&   ob  = sc.objects[object];
   const dev_material& mat = sc.materials[ob.material];
-  (void)o4;
 
   vec3f outgoing = -ray_d;
+  // Inside a volume (trace_path only, :1403-1414): sample a distance along the ray against the transmittance; a
+  // distance short of the surface makes this vertex a scattering event in the medium (:1470-1497).
+  vsdf vol;
+  bool has_vol = false;
+  if (VOL) {
+    float4 vs4 = ld_stream(&ps.vol_scatter[slot]);
+    has_vol    = vs4.w != 0;
+    if (has_vol) {
+      float4 vd4 = ld_stream(&ps.vol_density[slot]);
+      vol        = {{vd4.x, vd4.y, vd4.z}, {vs4.x, vs4.y, vs4.z}, vd4.w};
+      float hit_distance = ld_stream(&ps.hit_dist[slot]);
+      float rd = rand1f(rng);  // arguments are evaluated right to left in the oracle build: rd, then rl
+      float rl = rand1f(rng);
+      float distance = sample_transmittance(vol.density, hit_distance, rl, rd);
+      weight = weight * (eval_transmittance(vol.density, distance) / sample_transmittance_pdf(vol.density, distance, hit_distance));
+      if (distance < hit_distance) {
+        vec3f ray_o = {o4.x, o4.y, o4.z};
+        vec3f vpos  = ray_o + ray_d * distance;
+        vec3f vin;
+        if (rand1f(rng) < 0.5f) {
+          vec2f rn  = rand2f(rng);
+          float rnl = rand1f(rng);
+          (void)rnl;
+          vin = sample_scattering(vol, outgoing, rn);
+        } else {
+          vec2f ruv = rand2f(rng);
+          float rel = rand1f(rng);
+          float rl2 = rand1f(rng);
+          vin       = sample_lights(sc, vpos, rl2, rel, ruv);
+        }
+        float light_pdf = sample_lights_pdf(sc, vpos, vin, st, light_rays);
+        weight = weight * (eval_scattering(vol, outgoing, vin) / (0.5f * sample_scattering_pdf(vol, outgoing, vin) + 0.5f * light_pdf));
+        st_stream(&ps.ray_o[slot], make_float4(vpos.x, vpos.y, vpos.z, 0));
+        st_stream(&ps.ray_d[slot], make_float4(vin.x, vin.y, vin.z, 0));
+        bool vfinished = false;
+        if ((weight == vec3f{0, 0, 0}) || !isfinite3(weight)) vfinished = true;
+        if (!vfinished && bounce > 3) {
+          float rr_prob = fmin_(0.99f, max3(weight));
+          if (rand1f(rng) >= rr_prob) vfinished = true;
+          else weight = weight * div_(1.0f, rr_prob);
+        }
+        bounce += 1;
+        if (bounce >= tc.bounces) vfinished = true;
+        bool vagain;
+        if (vfinished) {
+          vagain = finish_sample(ps, cam, tc, slot, radiance, 1.0f, rng);
+        } else {
+          st_stream(&ps.weight[slot], make_float4(weight.x, weight.y, weight.z, 1.0f));
+          st_stream(&ps.radiance[slot], make_float4(radiance.x, radiance.y, radiance.z, __int_as_float(bounce)));
+          vagain = true;
+        }
+        st_stream(&ps.rng_state[slot], rng.state);
+        return vagain;
+      }
+    }
+  }
   vec3f position = eval_position(sc, object, element, uv);
   // eval_shading_normal, :350-369
   vec3f normal, tangent;
@@ -301,7 +362,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       hb = eval_hair_brdf(hm, uv.y, normal, tangent);  // :474-490
       ht = hair_prepare_wo(hb, outgoing);
     } else {
-      surface_material sm = {mat.color, mat.specular, mat.metallic, mat.roughness, mat.ior, mat.transmission};
+      surface_material sm = {mat.color, mat.specular, mat.metallic, mat.roughness, mat.ior, mat.transmission, mat.thin != 0};
       sb    = eval_surface_brdf(sm, normal, outgoing);
       delta = is_delta(sb);
     }
@@ -368,6 +429,16 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     bounce += 1;
     if (bounce >= tc.bounces) finished = true;
     }
+    // update the volume stack, :1458-1467: crossing a refractive surface enters its volume or leaves the current one
+    if (VOL && !HAIR && !mat.thin && mat.transmission != 0 && dot(normal, outgoing) * dot(normal, incoming) < 0) {
+      if (!has_vol) {
+        vsdf v = eval_vsdf(mat.color, mat.transmission, mat.thin != 0, mat.scattering, mat.scanisotropy, mat.trdepth);
+        st_stream(&ps.vol_density[slot], make_float4(v.density.x, v.density.y, v.density.z, v.anisotropy));
+        st_stream(&ps.vol_scatter[slot], make_float4(v.scatter.x, v.scatter.y, v.scatter.z, 1.0f));
+      } else {
+        st_stream(&ps.vol_scatter[slot], make_float4(0, 0, 0, 0));
+      }
+    }
     if (continues) {
       st_stream(&ps.ray_o[slot], make_float4(position.x, position.y, position.z, 0));
       st_stream(&ps.ray_d[slot], make_float4(incoming.x, incoming.y, incoming.z, 0));
@@ -388,7 +459,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
 
 // one instantiation per (primitive kind, shader): the shader is a compile-time constant so the
 // path shader's code carries none of the other shaders' branches
-template <bool HAIR, int SHADER>
+template <bool HAIR, int SHADER, bool VOL>
 #ifndef YH_SHADE_BLOCKS
 #define YH_SHADE_BLOCKS 4
 #endif
@@ -406,7 +477,7 @@ __global__ void __launch_bounds__(kTraceBlock, YH_SHADE_BLOCKS) k_shade(dev_scen
       int        stack_overflow[kStackLocal];
       trav_stack st;
       st.init(smem_stack + threadIdx.x, stack_overflow);
-      again   = shade_vertex<HAIR, SHADER>(sc, ps, cam, tc, slot, st, light_rays);
+      again   = shade_vertex<HAIR, SHADER, VOL>(sc, ps, cam, tc, slot, st, light_rays);
     }
     queue_push(q.active[next], q.count + next, again, slot);
   }
@@ -552,7 +623,8 @@ struct yh_state {
   int             rank = 0, world = 1;
   bool            counter = false;          // per-sample streams (yh_state_set_sample_shard)
   int             srank = 0, sworld = 1;    // sample indices srank, srank + sworld, ... are rendered here
-  dev_buffer<float4>             ray_o, ray_d, weight, radiance, accum, render;
+  dev_buffer<float4>             ray_o, ray_d, weight, radiance, accum, render, vol_density, vol_scatter;
+  dev_buffer<float>              hit_dist;
   dev_buffer<int4>               hit;
   dev_buffer<unsigned long long> rng_state, rng_inc, rng_base;
   dev_buffer<int>                remaining, pixel, samples;
@@ -566,7 +638,8 @@ struct yh_state {
   path_state      ps(int first = 0) {
     return {ray_o.ptr + first, ray_d.ptr + first, weight.ptr + first, radiance.ptr + first, hit.ptr + first,
         rng_state.ptr + first, rng_inc.ptr + first, rng_base.ptr + first, remaining.ptr + first, pixel.ptr + first,
-        accum.ptr, samples.ptr};
+        accum.ptr, samples.ptr, vol_density.ptr ? vol_density.ptr + first : nullptr,
+        vol_scatter.ptr ? vol_scatter.ptr + first : nullptr, hit_dist.ptr ? hit_dist.ptr + first : nullptr};
   }
   void clear_groups() {
     for (auto g : groups) delete g;
@@ -633,6 +706,11 @@ static yh_status assign_slots(yh_state* st) {
   YH_CUDA(st->rng_base.alloc(n));
   YH_CUDA(st->remaining.alloc(n));
   YH_CUDA(st->pixel.alloc(n));
+  if (st->scene->has_volumes) {
+    YH_CUDA(st->vol_density.alloc(n));
+    YH_CUDA(st->vol_scatter.alloc(n));
+    YH_CUDA(st->hit_dist.alloc(n));
+  }
   st->clear_groups();
   for (int g = 0; g < ngroups; g++) {
     auto grp = new wave_group{};
@@ -820,20 +898,25 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
       k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
       switch (tc.shader) {
         case YH_SHADER_NAIVE:
-          k_shade<false, YH_SHADER_NAIVE><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-          k_shade<true, YH_SHADER_NAIVE><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<false, YH_SHADER_NAIVE, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<true, YH_SHADER_NAIVE, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           break;
         case YH_SHADER_EYELIGHT:
-          k_shade<false, YH_SHADER_EYELIGHT><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-          k_shade<true, YH_SHADER_EYELIGHT><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<false, YH_SHADER_EYELIGHT, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<true, YH_SHADER_EYELIGHT, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           break;
         case YH_SHADER_NORMAL:
-          k_shade<false, YH_SHADER_NORMAL><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-          k_shade<true, YH_SHADER_NORMAL><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<false, YH_SHADER_NORMAL, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          k_shade<true, YH_SHADER_NORMAL, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           break;
         default:
-          k_shade<false, YH_SHADER_PATH><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-          k_shade<true, YH_SHADER_PATH><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          if (st->scene->has_volumes) {  // only trace_path follows volumes; the volume-free kernels stay as they were
+            k_shade<false, YH_SHADER_PATH, true><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+            k_shade<true, YH_SHADER_PATH, true><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          } else {
+            k_shade<false, YH_SHADER_PATH, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+            k_shade<true, YH_SHADER_PATH, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          }
       }
       if (prof) ev(s);
       launches += 5;

@@ -240,9 +240,19 @@ SURFACE_MATERIALS = {
     "mixed": dict(color=(0.6, 0.6, 0.2), specular=0.7, metallic=0.3, transmission=0.4, roughness=0.5, ior=1.33, thin=True),
     "veil": dict(color=(0.5, 0.5, 0.9), specular=1, roughness=0.2, opacity=0.6),      # opacity pass-through in front of lobes
 }
+# refraction (thin = False with transmission) opens a homogeneous volume behind the surface (has_volume, eval_vsdf)
+VOLUME_MATERIALS = {
+    "glass": dict(color=(1, 1, 1), specular=1, transmission=1, roughness=0, thin=False),                     # delta refraction, empty volume
+    "rough_glass": dict(color=(0.9, 0.95, 1.0), specular=1, transmission=1, roughness=0.15, thin=False, trdepth=0.5),
+    "wax": dict(color=(0.8, 0.5, 0.25), specular=1, transmission=1, roughness=0.5, thin=False, scattering=(0.8, 0.5, 0.25),
+                scanisotropy=-0.8, trdepth=0.05),                                                            # sloth "body"
+    "milk": dict(color=(0.9, 0.9, 0.85), transmission=0.8, roughness=0.3, thin=False, scattering=(0.9, 0.9, 0.9),
+                 scanisotropy=0.0, trdepth=0.2, ior=1.3),
+    "air": dict(color=(0.5, 0.9, 0.5), transmission=1, roughness=0, thin=False, ior=1.0005, trdepth=0.3),    # |ior - 1| < 1e-3 branch
+}
 
 
-def surface_lobes_scene(num_segments=4_000, seed=7, sky=True):
+def surface_lobes_scene(num_segments=4_000, seed=7, sky=True, volumes=False):
     """a hair block among spheres and sheets that carry every surface lobe of the reference's
     material model that the device builds (diffuse, specular, metal, thin transmission, delta forms, opacity),
     a diffuse floor, one area light and the sky."""
@@ -254,9 +264,10 @@ def surface_lobes_scene(num_segments=4_000, seed=7, sky=True):
     sc.objects.append(Object(shape=0, material=0, frame=(1, 0, 0, 0, 0, 1, 0, -1, 0, 0.5, 1, -0.5)))
     sc.materials.append(Material(color=(0.7, 0.7, 0.7)))       # floor: plain diffuse
     sc.objects.append(Object(shape=2, material=1, frame=(1, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0)))
-    names = list(SURFACE_MATERIALS)
+    table = VOLUME_MATERIALS if volumes else SURFACE_MATERIALS
+    names = list(table)
     for k, name in enumerate(names):
-        sc.materials.append(Material(**SURFACE_MATERIALS[name]))
+        sc.materials.append(Material(**table[name]))
         m = len(sc.materials) - 1
         if name in ("frosted", "sheet", "veil"):               # upright sheets in front of the block
             s = 0.12
