@@ -64,9 +64,10 @@ typedef struct yh_texture_desc {
 /* yocto::pathtrace::material, yocto_pathtrace.h:293-329.  Texture slots are
  * indices into yh_scene_desc::textures or -1.  Built on the device: the hair
  * block on line shapes; on triangles emission, color (diffuse), specular,
- * metallic, roughness, ior, thin transmission and opacity (eval_brdf,
- * yocto_pathtrace.cpp:405-471).  yh_scene_create refuses (YH_ERR_UNSUPPORTED):
- * transmission with thin = 0 (refraction), scattering, any material texture,
+ * metallic, roughness, ior, transmission (thin sheet, or refraction with
+ * thin = 0 and the volume given by scattering / scanisotropy / trdepth) and
+ * opacity (eval_brdf / eval_vsdf, yocto_pathtrace.cpp:405-531).
+ * yh_scene_create refuses (YH_ERR_UNSUPPORTED): any material texture, and
  * specular / metallic / transmission on a line shape.                        */
 typedef struct yh_material_desc {
   float emission[3];

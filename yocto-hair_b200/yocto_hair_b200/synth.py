@@ -254,8 +254,8 @@ VOLUME_MATERIALS = {
 
 def surface_lobes_scene(num_segments=4_000, seed=7, sky=True, volumes=False):
     """a hair block among spheres and sheets that carry every surface lobe of the reference's
-    material model that the device builds (diffuse, specular, metal, thin transmission, delta forms, opacity),
-    a diffuse floor, one area light and the sky."""
+    material model (diffuse, specular, metal, thin transmission, delta forms, opacity; with volumes=True the
+    refractive materials and their media instead), a diffuse floor, one area light and the sky."""
     sc = Scene()
     sc.shapes.append(make_hair_block(num_segments, seed))      # 0
     sc.shapes.append(make_uv_sphere((24, 12), radius=0.38))    # 1
