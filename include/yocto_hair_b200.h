@@ -66,9 +66,15 @@ typedef struct yh_texture_desc {
  * block on line shapes; on triangles emission, color (diffuse), specular,
  * metallic, roughness, ior, transmission (thin sheet, or refraction with
  * thin = 0 and the volume given by scattering / scanisotropy / trdepth) and
- * opacity (eval_brdf / eval_vsdf, yocto_pathtrace.cpp:405-531).
- * yh_scene_create refuses (YH_ERR_UNSUPPORTED): any material texture, and
- * specular / metallic / transmission on a line shape.                        */
+ * opacity (eval_brdf / eval_vsdf, yocto_pathtrace.cpp:405-531), each times the
+ * float RGB texture in its slot (x channel for the scalar factors, mean for
+ * opacity).  transmission_tex scales `transmission`: the reference reads its
+ * EMISSION texture for that (:420-421), so callers that want its behaviour
+ * pass the emission texture here (the C++ shim does).  Byte (LDR) textures
+ * are expanded by the caller: sRGB-decoded for emission / color / scattering,
+ * linear for the other slots.  spectint_tex is never evaluated.
+ * yh_scene_create refuses (YH_ERR_UNSUPPORTED): normal_tex, and specular /
+ * metallic / transmission on a line shape.                                   */
 typedef struct yh_material_desc {
   float emission[3];
   float color[3];

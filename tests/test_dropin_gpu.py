@@ -50,3 +50,36 @@ def test_save_batch_matches_one_sample_at_a_time(tmp_path):
     for k in range(3):  # <name>-s<k>.pfm after every pass, as the reference app names them
         a, b = scenefiles.read_pfm(tmp_path / f"g-s{k}.pfm"), scenefiles.read_pfm(tmp_path / f"c-s{k}.pfm")
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_materials_and_byte_textures_through_the_app(tmp_path):
+    """The whole material model through the files and the shim: surface lobes, a refractive scattering sphere, and
+    BYTE textures (.png: sRGB-decoded in the colour slot, linear in the roughness / opacity slots - the shim uploads
+    the two expansions, yocto_pathtrace_b200.cpp) with the reference's own loaders on both sides."""
+    if not APP.exists():
+        pytest.skip("host/_build/yscenetrace_b200 not built")
+    import json
+    from PIL import Image
+    scene, cam = synth.surface_lobes_scene(3_000)
+    vol, _ = synth.surface_lobes_scene(500, volumes=True)
+    wax = vol.materials[2 + list(synth.VOLUME_MATERIALS).index("wax")]
+    scene.materials.append(wax)
+    from yocto_hair_b200.scene import Object
+    scene.objects.append(Object(shape=1, material=len(scene.materials) - 1, frame=(1, 0, 0, 0, 1, 0, 0, 0, 1, 0.4, 0.38, 1.6)))
+    js = scenefiles.write_scene(tmp_path, "materials", scene, cam)
+    rng = np.random.default_rng(9)
+    Image.fromarray(rng.integers(30, 255, (16, 24, 3), dtype=np.uint8)).save(tmp_path / "textures" / "checker.png")
+    Image.fromarray(rng.integers(0, 255, (8, 8), dtype=np.uint8)).save(tmp_path / "textures" / "gray.png")   # scalar (1-channel) file
+    d = json.loads(Path(js).read_text())
+    d["materials"]["mat001"]["color_tex"] = "checker"        # floor: sRGB reading
+    d["materials"]["mat002"]["roughness_tex"] = "checker"    # the SAME file read as linear
+    d["materials"]["mat002"]["color_tex"] = "checker"
+    d["materials"]["mat004"]["roughness_tex"] = "gray"
+    d["materials"]["mat010"]["opacity_tex"] = "gray"
+    Path(js).write_text(json.dumps(d))
+    out = run_app("--backend", "cuda", "-s", 4, "-r", 160, "--spp-batch", 2, "-o", tmp_path / "gpu.pfm", js)
+    assert "backend cuda" in out
+    run_app("--backend", "cpu", "-s", 4, "-r", 160, "-o", tmp_path / "cpu.pfm", js)
+    a, b = scenefiles.read_pfm(tmp_path / "gpu.pfm"), scenefiles.read_pfm(tmp_path / "cpu.pfm")
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert a.mean() > 0.01

@@ -451,3 +451,61 @@ def test_refraction_and_volumes_bit_identical(shader, ref):
         assert diff[0].size == 0, "first differing pixels (y, x): %s" % list(zip(diff[0][:8], diff[1][:8]))
         assert np.isfinite(a_d).all() and a_d[..., :3].max() > 0
         st_r.close(); rs.close(); st_d.close(); ds.close()
+
+
+@pytest.mark.parametrize("shader", [1, 0, 2], ids=["path", "naive", "eyelight"])
+def test_material_textures_bit_identical(shader, ref):
+    """Float RGB textures in every material slot the reference's tracer evaluates (emission, color, specular,
+    metallic, roughness, opacity, scattering, and the transmission factor it reads from the EMISSION texture,
+    yocto_pathtrace.cpp:397-424, :505-526), with vertex texcoords (tiled, negative) on the quads and the
+    element-uv fallback on the spheres (eval_texcoord, :294-309)."""
+    if ref.kind != "reference":
+        pytest.skip("checked against the reference build (the plain-C port restates the hair path only)")
+    from yocto_hair_b200.scene import Texture
+    scene, cam = synth.surface_lobes_scene(volumes=False)
+    vol, _ = synth.surface_lobes_scene(volumes=True)
+    rng = np.random.default_rng(5)
+
+    def tex(lo, hi, size=(12, 20)):
+        scene.textures.append(Texture(colorf=rng.uniform(lo, hi, (*size, 3)).astype(np.float32)))
+        return len(scene.textures) - 1
+
+    quad = scene.shapes[2]
+    quad.texcoords = np.array([[-0.4, 0.1], [2.7, 0.1], [-0.4, 3.3], [2.7, 3.3]], np.float32)
+    names = ["hair", "floor"] + list(synth.SURFACE_MATERIALS) + ["light"]
+    m = dict(zip(names, scene.materials))
+    m["floor"].color_tex = tex(0.2, 1.0)
+    m["coated"].color_tex, m["coated"].roughness_tex, m["coated"].specular_tex = tex(0.1, 1.0), tex(0.3, 1.0), tex(0.0, 1.0)
+    m["gold"].metallic_tex, m["gold"].roughness_tex = tex(0.0, 1.0), tex(0.0, 1.0)          # roughness 0 texels: delta vertices
+    m["frosted"].emission = (0.3, 0.2, 0.1)
+    m["frosted"].emission_tex = m["frosted"].transmission_tex = tex(0.0, 1.0)              # emission texture scales transmission
+    m["veil"].opacity_tex, m["veil"].color_tex = tex(0.0, 1.0), tex(0.2, 0.9)
+    m["light"].emission_tex = tex(0.5, 1.0)
+    m["hair"].opacity, m["hair"].opacity_tex = 0.9, tex(0.6, 1.0)                           # textured opacity on the hair itself
+    # a scattering sphere with textured albedo and density
+    wax = vol.materials[2 + list(synth.VOLUME_MATERIALS).index("wax")]
+    wax.scattering_tex, wax.color_tex = tex(0.3, 1.0), tex(0.4, 1.0)
+    scene.materials.append(wax)
+    scene.objects.append(Object(shape=1, material=len(scene.materials) - 1, frame=(1, 0, 0, 0, 1, 0, 0, 0, 1, 0.4, 0.38, 1.6)))
+    p = make_params(resolution=144, shader=shader)
+    rs = ref.scene(scene)
+    st_r = rs.state(cam, p)
+    st_r.trace_samples(4)
+    _, a_r, s_r, rng_r = st_r.download()
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    st_d = ds.init_state(cam, p)
+    st_d.trace_samples(4)
+    _, a_d, s_d = st_d.download()
+    assert np.array_equal(s_r, s_d) and np.array_equal(rng_r, st_d.rng())
+    diff = np.nonzero((a_r.view(np.uint32) != a_d.view(np.uint32)).any(axis=-1))
+    assert diff[0].size == 0, "first differing pixels (y, x): %s" % list(zip(diff[0][:8], diff[1][:8]))
+    st_r.close(); rs.close(); st_d.close(); ds.close()
+
+
+def test_normal_maps_are_refused():
+    scene, _ = synth.surface_lobes_scene(500, sky=True)
+    lib = capi.load()
+    desc, keep = scene.to_desc()
+    desc.materials[1].normal_tex = 0
+    handle = capi.C.c_void_p()
+    assert lib.yh_scene_create(capi.C.byref(desc), capi.C.byref(handle)) == capi.YH_ERR_UNSUPPORTED

@@ -715,6 +715,7 @@ static yh_status upload_tables(yh_scene* sc) {
     d.scale = s->scale, d.grid_origin = s->grid_origin, d.grid_step = s->grid_step;
     d.has_normals = s->normals.empty() ? 0 : 1;
     d.positions = s->d_positions.ptr, d.normals = s->d_normals.ptr, d.elems = s->d_elems.ptr;
+    d.texcoords = s->texcoords.empty() ? nullptr : s->d_texcoords.ptr;
     d.num_elems = s->num_elems();
     ds.push_back(d);
   }
@@ -736,10 +737,11 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
   // ---- validate: anything outside the hot-path scope fails loudly ----
   for (int i = 0; i < d->num_materials; i++) {
     auto& m = d->materials[i];
+    if (m.normal_tex >= 0) return fail(YH_ERR_UNSUPPORTED, "material %d: normal maps are not built", i);
     int texs[] = {m.emission_tex, m.color_tex, m.specular_tex, m.metallic_tex, m.roughness_tex,
-        m.transmission_tex, m.spectint_tex, m.scattering_tex, m.opacity_tex, m.normal_tex};
+        m.transmission_tex, m.spectint_tex, m.scattering_tex, m.opacity_tex};
     for (int t : texs)
-      if (t >= 0) return fail(YH_ERR_UNSUPPORTED, "material %d: material textures are outside the hot path", i);
+      if (t >= d->num_textures) return fail(YH_ERR_INVALID, "material %d: texture index out of range", i);
   }
   for (int i = 0; i < d->num_objects; i++) {
     auto& o = d->objects[i];
@@ -761,6 +763,8 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
       return fail(YH_ERR_INVALID, "shape %d: lines need one radius per vertex", i);
     if (s.num_normals && s.num_normals != s.num_positions)
       return fail(YH_ERR_INVALID, "shape %d: normals/positions size mismatch", i);
+    if (s.num_texcoords && s.num_texcoords != s.num_positions)
+      return fail(YH_ERR_INVALID, "shape %d: texcoords/positions size mismatch", i);
     for (int k = 0; k < 2 * s.num_lines; k++)
       if (s.lines[k] < 0 || s.lines[k] >= s.num_positions) return fail(YH_ERR_INVALID, "shape %d: line index out of range", i);
     for (int k = 0; k < 3 * s.num_triangles; k++)
@@ -780,11 +784,13 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
     hs->positions.assign(s.positions, s.positions + 3 * (size_t)s.num_positions);
     if (s.num_normals) hs->normals.assign(s.normals, s.normals + 3 * (size_t)s.num_normals);
     if (s.num_radius) hs->radius.assign(s.radius, s.radius + s.num_radius);
+    if (s.num_texcoords) hs->texcoords.assign(s.texcoords, s.texcoords + 2 * (size_t)s.num_texcoords);
     if (s.num_lines) hs->lines.assign(s.lines, s.lines + 2 * (size_t)s.num_lines);
     if (s.num_triangles) hs->triangles.assign(s.triangles, s.triangles + 3 * (size_t)s.num_triangles);
     if (hs->d_positions.upload(hs->positions.data(), hs->positions.size()) != cudaSuccess ||
         hs->d_normals.upload(hs->normals.data(), hs->normals.size()) != cudaSuccess ||
         hs->d_radius.upload(hs->radius.data(), hs->radius.size()) != cudaSuccess ||
+        hs->d_texcoords.upload(hs->texcoords.data(), hs->texcoords.size()) != cudaSuccess ||
         hs->d_elems.upload(hs->is_lines() ? hs->lines.data() : hs->triangles.data(),
             hs->is_lines() ? hs->lines.size() : hs->triangles.size()) != cudaSuccess)
       return bail(fail(YH_ERR_CUDA, "shape %d: device upload failed: %s", i, cudaGetErrorString(cudaGetLastError())));
@@ -806,6 +812,11 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
     dm.specular = m.specular, dm.metallic = m.metallic, dm.roughness = m.roughness, dm.ior = m.ior, dm.transmission = m.transmission;
     dm.scattering = to_vec(m.scattering), dm.scanisotropy = m.scanisotropy, dm.trdepth = m.trdepth;
     if (!m.thin && m.transmission != 0) sc->has_volumes = true;  // has_volume(), yocto_pathtrace.cpp:529-531
+    dm.emission_tex = m.emission_tex, dm.color_tex = m.color_tex, dm.specular_tex = m.specular_tex;
+    dm.metallic_tex = m.metallic_tex, dm.roughness_tex = m.roughness_tex, dm.transmission_tex = m.transmission_tex;
+    dm.opacity_tex = m.opacity_tex, dm.scattering_tex = m.scattering_tex;
+    dm.any_tex = (m.emission_tex >= 0 || m.color_tex >= 0 || m.specular_tex >= 0 || m.metallic_tex >= 0 || m.roughness_tex >= 0 ||
+                  m.transmission_tex >= 0 || m.opacity_tex >= 0 || m.scattering_tex >= 0) ? 1 : 0;
     dm.eumelanin = m.eumelanin, dm.pheomelanin = m.pheomelanin, dm.sigma_a = to_vec(m.sigma_a);
     dm.beta_m = m.beta_m, dm.beta_n = m.beta_n, dm.alpha = m.alpha, dm.eta = m.eta;
     sc->materials.push_back(dm);

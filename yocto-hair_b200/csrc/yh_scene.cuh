@@ -54,6 +54,7 @@ struct dev_shape {
   int           has_normals;
   const float*  positions;  // xyz
   const float*  normals;    // xyz (hair tangents for lines)
+  const float*  texcoords;  // uv per vertex, or null (eval_texcoord then returns the element uv)
   const int*    elems;      // lines: 2 ints, triangles: 3 ints
   int           num_elems;
 };
@@ -66,6 +67,9 @@ struct dev_material {
   float specular, metallic, roughness, ior, transmission;  // surface lobes (yh_surface.cuh)
   vec3f scattering;                                        // volume behind a refractive surface (!thin && transmission)
   float scanisotropy, trdepth;
+  // float RGB textures (index into dev_scene::textures or -1), eval_brdf / eval_emission / eval_vsdf
+  int emission_tex, color_tex, specular_tex, metallic_tex, roughness_tex, transmission_tex, opacity_tex, scattering_tex;
+  int any_tex;  // some slot is set: the shading code then evaluates eval_texcoord
   // hair block (yocto_pathtrace.h:310-316)
   float eumelanin, pheomelanin;
   vec3f sigma_a;
@@ -116,9 +120,9 @@ struct dev_scene {
 
 // Host-side copy of one shape (kept for light CDFs and BVH set-up).
 struct host_shape {
-  std::vector<float> positions, normals, radius;
+  std::vector<float> positions, normals, radius, texcoords;
   std::vector<int>   lines, triangles;
-  dev_buffer<float>  d_positions, d_normals, d_radius;
+  dev_buffer<float>  d_positions, d_normals, d_radius, d_texcoords;
   dev_buffer<int>    d_elems;
   dev_buffer<uint4>  d_slots;
   dev_buffer<float4> d_prims;  // triangle vertices by element

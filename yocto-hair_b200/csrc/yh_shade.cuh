@@ -73,6 +73,22 @@ __device__ __forceinline__ vec3f eval_texture(const dev_scene& sc, int tex, cons
          lookup_texture(t, ii, j) * u * (1 - v) + lookup_texture(t, ii, jj) * u * v;
 }
 
+// eval_texcoord, :294-309 (interpolate_triangle / interpolate_line of the vertex texcoords, the element uv without them)
+__device__ __forceinline__ vec2f eval_texcoord(const dev_scene& sc, int object, int element, const vec2f& uv) {
+  const dev_shape& sh = sc.shapes[sc.objects[object].shape];
+  if (!sh.texcoords) return uv;
+  auto ldt = [&](int i) -> vec2f { return {__ldg(sh.texcoords + 2 * i), __ldg(sh.texcoords + 2 * i + 1)}; };
+  if (!sh.is_lines) {
+    int   a = __ldg(sh.elems + 3 * element), b = __ldg(sh.elems + 3 * element + 1), c = __ldg(sh.elems + 3 * element + 2);
+    vec2f t0 = ldt(a), t1 = ldt(b), t2 = ldt(c);
+    float w = 1 - uv.x - uv.y;
+    return {t0.x * w + t1.x * uv.x + t2.x * uv.y, t0.y * w + t1.y * uv.x + t2.y * uv.y};
+  }
+  int   a = __ldg(sh.elems + 2 * element), b = __ldg(sh.elems + 2 * element + 1);
+  vec2f t0 = ldt(a), t1 = ldt(b);
+  return {t0.x * (1 - uv.x) + t1.x * uv.x, t0.y * (1 - uv.x) + t1.y * uv.x};
+}
+
 // eval_environment, :536-547
 __device__ __forceinline__ vec3f eval_environment(const dev_scene& sc, const vec3f& dir) {
   vec3f emission = {0, 0, 0};

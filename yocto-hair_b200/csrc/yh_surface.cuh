@@ -4,8 +4,8 @@
 // (yocto_pathtrace.cpp:405-471), eval_brdfcos / sample_brdfcos / sample_brdfcos_pdf and the delta
 // trio (:1069-1280) and the lobe functions of yocto_math.h:4215-4760, same operation order, so
 // renders stay bit-identical to the reference.  Refraction (thin = false with transmission) and the
-// homogeneous volume it opens (eval_vsdf :505-526, trace_path :1403-1414, :1458-1497) are here too;
-// material textures are not - yh_scene_create refuses those.
+// homogeneous volume it opens (eval_vsdf :505-526, trace_path :1403-1414, :1458-1497) are here too.
+// Textures multiply the material factors before these functions see them (shade_vertex, yh_trace.cu).
 #pragma once
 #include "yh_libm.cuh"
 
@@ -255,13 +255,13 @@ YH_HD float sample_microfacet_transmission_pdf(float roughness, const vec3f& nor
 struct surface_material {
   vec3f color;
   float specular, metallic, roughness, ior, transmission;
-  bool  thin;  // material.thin as set by the caller; eval_brdf uses thin || !transmission (:425)
+  bool  thin;  // material.thin || !material.transmission (:425: the UNTEXTURED transmission decides)
 };
 YH_HD surface_brdf eval_surface_brdf(const surface_material& m, const vec3f& normal, const vec3f& outgoing) {
   surface_brdf brdf;
   vec3f base   = m.color;
   vec3f weight = {1, 1, 1};
-  bool  thin   = m.thin || m.transmission == 0;
+  bool  thin   = m.thin;
   brdf.metal   = weight * m.metallic;
   weight       = weight * (1 - m.metallic);
   brdf.refraction = thin ? vec3f{0, 0, 0} : (weight * m.transmission);
@@ -426,8 +426,7 @@ struct vsdf {
   float anisotropy;
 };
 // eval_vsdf, :505-526 (every texture at its {1,1,1} default); called only when has_volume() holds
-YH_HD vsdf eval_vsdf(const vec3f& color, float transmission, bool thin_, const vec3f& scattering, float scanisotropy, float trdepth) {
-  bool thin = thin_ || transmission == 0;
+YH_HD vsdf eval_vsdf(const vec3f& color, float transmission, bool thin, const vec3f& scattering, float scanisotropy, float trdepth) {
   vsdf v;
   v.density = {0, 0, 0};
   if (transmission != 0 && !thin) {

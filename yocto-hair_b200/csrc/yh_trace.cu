@@ -330,10 +330,26 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     normal = eval_normal(sc, object, element, uv);
     if (mat.thin) normal = dot(normal, outgoing) >= 0 ? normal : -normal;
   }
-  vec3f emission = mat.emission;  // eval_emission with no texture, :397-402
+  // material factors x textures, eval_emission :397-402 and eval_brdf :409-424 (a missing texture evaluates to
+  // {1,1,1}, and x * 1 is exact, so untextured materials take the cheap branch).  The transmission factor comes from
+  // the slot the caller put in transmission_tex - the reference reads its EMISSION texture there (:420-421).
+  vec3f emission = mat.emission, base = mat.color, scattering = mat.scattering;
+  float specular = mat.specular, metallic = mat.metallic, roughness = mat.roughness, transmission = mat.transmission;
+  float opacity_mean = div_(1.0f + 1.0f + 1.0f, 3.0f);
+  if (mat.any_tex) {
+    vec2f texcoord = eval_texcoord(sc, object, element, uv);
+    emission     = mat.emission * eval_texture(sc, mat.emission_tex, texcoord);
+    base         = mat.color * eval_texture(sc, mat.color_tex, texcoord);
+    specular     = mat.specular * eval_texture(sc, mat.specular_tex, texcoord).x;
+    metallic     = mat.metallic * eval_texture(sc, mat.metallic_tex, texcoord).x;
+    roughness    = mat.roughness * eval_texture(sc, mat.roughness_tex, texcoord).x;
+    transmission = mat.transmission * eval_texture(sc, mat.transmission_tex, texcoord).x;
+    scattering   = mat.scattering * eval_texture(sc, mat.scattering_tex, texcoord);
+    opacity_mean = mean3(eval_texture(sc, mat.opacity_tex, texcoord));
+  }
 
   // opacity, :423-424, :453, :1429-1433 (mean of the {1,1,1} texture default is exactly 1)
-  float opacity = mat.opacity * div_(1.0f + 1.0f + 1.0f, 3.0f);
+  float opacity = mat.opacity * opacity_mean;
   if (opacity > 0.999f) opacity = 1;
   bool finished = false;
   if (SHADER == YH_SHADER_NORMAL) {  // trace_normal, :1636-1651: the shading normal as a colour, alpha 1
@@ -362,7 +378,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       hb = eval_hair_brdf(hm, uv.y, normal, tangent);  // :474-490
       ht = hair_prepare_wo(hb, outgoing);
     } else {
-      surface_material sm = {mat.color, mat.specular, mat.metallic, mat.roughness, mat.ior, mat.transmission, mat.thin != 0};
+      surface_material sm = {base, specular, metallic, roughness, mat.ior, transmission, mat.thin != 0 || mat.transmission == 0};
       sb    = eval_surface_brdf(sm, normal, outgoing);
       delta = is_delta(sb);
     }
@@ -432,7 +448,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     // update the volume stack, :1458-1467: crossing a refractive surface enters its volume or leaves the current one
     if (VOL && !HAIR && !mat.thin && mat.transmission != 0 && dot(normal, outgoing) * dot(normal, incoming) < 0) {
       if (!has_vol) {
-        vsdf v = eval_vsdf(mat.color, mat.transmission, mat.thin != 0, mat.scattering, mat.scanisotropy, mat.trdepth);
+        vsdf v = eval_vsdf(base, transmission, mat.thin != 0 || mat.transmission == 0, scattering, mat.scanisotropy, mat.trdepth);
         st_stream(&ps.vol_density[slot], make_float4(v.density.x, v.density.y, v.density.z, v.anisotropy));
         st_stream(&ps.vol_scatter[slot], make_float4(v.scatter.x, v.scatter.y, v.scatter.z, 1.0f));
       } else {

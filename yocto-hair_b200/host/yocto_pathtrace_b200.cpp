@@ -2,6 +2,7 @@
 #include "yocto_pathtrace_b200.h"
 
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <stdexcept>
 #include <unordered_map>
@@ -87,6 +88,28 @@ yh_scene* upload(const ptr::scene* scene) {
       }
     textures[i] = {px.data(), size.x, size.y};
   }
+  // Slots the reference evaluates with ldr_as_linear = true (specular, metallic, roughness, opacity and the
+  // transmission factor, yocto_pathtrace.cpp:413-424) need the BYTE textures expanded without the sRGB curve:
+  // such a texture gets a second, linear copy the first time one of those slots refers to it.
+  std::map<int, int> linear_copy;
+  auto linear_of = [&](int index) -> int {
+    if (index < 0) return -1;
+    auto t = scene->textures[index];
+    if (t->colorb.empty() && t->scalarb.empty()) return index;  // float textures have one reading
+    if (!t->colorf.empty()) return index;                      // lookup_texture prefers colorf (:149-150)
+    auto it = linear_copy.find(index);
+    if (it != linear_copy.end()) return it->second;
+    auto size = !t->colorb.empty() ? t->colorb.size() : t->scalarb.size();
+    texels.emplace_back(3 * (size_t)size.x * size.y);
+    auto& px = texels.back();
+    for (int j = 0; j < size.y; j++)
+      for (int k = 0; k < size.x; k++) {
+        auto c = !t->colorb.empty() ? math::byte_to_float(t->colorb[{k, j}]) : math::byte_to_float(math::vec3b{t->scalarb[{k, j}]});
+        memcpy(&px[3 * ((size_t)j * size.x + k)], &c, 12);
+      }
+    textures.push_back({px.data(), size.x, size.y});
+    return linear_copy[index] = (int)textures.size() - 1;
+  };
   std::vector<yh_material_desc> materials(scene->materials.size());
   for (size_t i = 0; i < materials.size(); i++) {
     auto  m = scene->materials[i];
@@ -100,11 +123,14 @@ yh_scene* upload(const ptr::scene* scene) {
     d.eumelanin = m->eumelanin, d.pheomelanin = m->pheomelanin;
     d.beta_m = m->beta_m, d.beta_n = m->beta_n, d.alpha = m->alpha, d.eta = m->eta;
     d.emission_tex = index_of(scene->textures, m->emission_tex), d.color_tex = index_of(scene->textures, m->color_tex);
-    d.specular_tex = index_of(scene->textures, m->specular_tex), d.metallic_tex = index_of(scene->textures, m->metallic_tex);
-    d.roughness_tex = index_of(scene->textures, m->roughness_tex);
-    d.transmission_tex = index_of(scene->textures, m->transmission_tex);
-    d.spectint_tex = index_of(scene->textures, m->spectint_tex), d.scattering_tex = index_of(scene->textures, m->scattering_tex);
-    d.opacity_tex = index_of(scene->textures, m->opacity_tex), d.normal_tex = index_of(scene->textures, m->normal_tex);
+    d.specular_tex  = linear_of(index_of(scene->textures, m->specular_tex));
+    d.metallic_tex  = linear_of(index_of(scene->textures, m->metallic_tex));
+    d.roughness_tex = linear_of(index_of(scene->textures, m->roughness_tex));
+    // the reference multiplies transmission by its EMISSION texture (:420-421), read as linear
+    d.transmission_tex = linear_of(index_of(scene->textures, m->emission_tex));
+    d.spectint_tex = -1;  // never evaluated by the reference's tracer
+    d.scattering_tex = index_of(scene->textures, m->scattering_tex);
+    d.opacity_tex = linear_of(index_of(scene->textures, m->opacity_tex)), d.normal_tex = index_of(scene->textures, m->normal_tex);
   }
   std::vector<yh_object_desc> objects(scene->objects.size());
   for (size_t i = 0; i < objects.size(); i++) {

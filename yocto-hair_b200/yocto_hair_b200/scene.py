@@ -96,6 +96,12 @@ class Material:
     eta: float = 1.55
     emission_tex: int = -1
     color_tex: int = -1
+    specular_tex: int = -1
+    metallic_tex: int = -1
+    roughness_tex: int = -1
+    transmission_tex: int = -1  # the reference reads its EMISSION texture for this factor (yocto_pathtrace.cpp:420-421)
+    scattering_tex: int = -1
+    opacity_tex: int = -1
 
 
 @dataclass
@@ -189,10 +195,10 @@ class Scene:
             d.eumelanin, d.pheomelanin = m.eumelanin, m.pheomelanin
             d.sigma_a[:] = m.sigma_a
             d.beta_m, d.beta_n, d.alpha, d.eta = m.beta_m, m.beta_n, m.alpha, m.eta
-            for name in ("specular_tex", "metallic_tex", "roughness_tex", "transmission_tex",
-                         "spectint_tex", "scattering_tex", "opacity_tex", "normal_tex"):
-                setattr(d, name, -1)
-            d.emission_tex, d.color_tex = m.emission_tex, m.color_tex
+            d.spectint_tex = d.normal_tex = -1
+            for name in ("emission_tex", "color_tex", "specular_tex", "metallic_tex", "roughness_tex", "transmission_tex",
+                         "scattering_tex", "opacity_tex"):
+                setattr(d, name, getattr(m, name))
         objects = (capi.ObjectDesc * max(1, len(self.objects)))()
         for d, o in zip(objects, self.objects):
             d.frame[:] = [float(x) for x in o.frame]

@@ -106,7 +106,8 @@ def write_scene(directory, name: str, scene: Scene, camera: Camera) -> Path:
         js["materials"][f"mat{i:03d}"] = {
             "emission": _floats(m.emission), "color": _floats(m.color), "specular": m.specular, "roughness": m.roughness,
             "metallic": m.metallic, "ior": _floats([m.ior])[0], "transmission": m.transmission, "opacity": _floats([m.opacity])[0],
-            "thin": bool(m.thin), "eumelanin": _floats([m.eumelanin])[0], "pheomelanin": _floats([m.pheomelanin])[0],
+            "thin": bool(m.thin), "scattering": _floats(m.scattering), "scanisotropy": _floats([m.scanisotropy])[0],
+            "trdepth": _floats([m.trdepth])[0], "eumelanin": _floats([m.eumelanin])[0], "pheomelanin": _floats([m.pheomelanin])[0],
             "sigma_a": _floats(m.sigma_a), "beta_m": _floats([m.beta_m])[0], "beta_n": _floats([m.beta_n])[0],
             "alpha": _floats([m.alpha])[0], "eta": _floats([m.eta])[0]}
     for i, o in enumerate(scene.objects):  # JSON objects iterate alphabetically: the names keep the order
