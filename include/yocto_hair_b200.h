@@ -72,9 +72,10 @@ typedef struct yh_texture_desc {
  * EMISSION texture for that (:420-421), so callers that want its behaviour
  * pass the emission texture here (the C++ shim does).  Byte (LDR) textures
  * are expanded by the caller: sRGB-decoded for emission / color / scattering,
- * linear for the other slots.  spectint_tex is never evaluated.
- * yh_scene_create refuses (YH_ERR_UNSUPPORTED): normal_tex, and specular /
- * metallic / transmission on a line shape.                                   */
+ * linear for the other slots (normal_tex: tangent-space normal map on
+ * triangles, eval_normalmap :326-347).  spectint_tex is never evaluated.
+ * yh_scene_create refuses (YH_ERR_UNSUPPORTED): specular / metallic /
+ * transmission on a line shape.                                              */
 typedef struct yh_material_desc {
   float emission[3];
   float color[3];

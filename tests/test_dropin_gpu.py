@@ -76,6 +76,7 @@ def test_materials_and_byte_textures_through_the_app(tmp_path):
     d["materials"]["mat002"]["color_tex"] = "checker"
     d["materials"]["mat004"]["roughness_tex"] = "gray"
     d["materials"]["mat010"]["opacity_tex"] = "gray"
+    d["materials"]["mat005"]["normal_tex"] = "checker"       # byte normal map on the mirror sphere (linear reading)
     Path(js).write_text(json.dumps(d))
     out = run_app("--backend", "cuda", "-s", 4, "-r", 160, "--spp-batch", 2, "-o", tmp_path / "gpu.pfm", js)
     assert "backend cuda" in out

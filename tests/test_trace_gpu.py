@@ -487,6 +487,10 @@ def test_material_textures_bit_identical(shader, ref):
     wax.scattering_tex, wax.color_tex = tex(0.3, 1.0), tex(0.4, 1.0)
     scene.materials.append(wax)
     scene.objects.append(Object(shape=1, material=len(scene.materials) - 1, frame=(1, 0, 0, 0, 1, 0, 0, 0, 1, 0.4, 0.38, 1.6)))
+    # tangent-space normal maps (eval_normalmap, :326-347): on the floor quad (uv tangents) and on a sphere
+    # without texcoords (no tangents: the frame degenerates exactly as the reference's does)
+    m["floor"].normal_tex = tex(0.25, 0.75)
+    m["mirror"].normal_tex = tex(0.4, 0.6)
     p = make_params(resolution=144, shader=shader)
     rs = ref.scene(scene)
     st_r = rs.state(cam, p)
@@ -500,12 +504,3 @@ def test_material_textures_bit_identical(shader, ref):
     diff = np.nonzero((a_r.view(np.uint32) != a_d.view(np.uint32)).any(axis=-1))
     assert diff[0].size == 0, "first differing pixels (y, x): %s" % list(zip(diff[0][:8], diff[1][:8]))
     st_r.close(); rs.close(); st_d.close(); ds.close()
-
-
-def test_normal_maps_are_refused():
-    scene, _ = synth.surface_lobes_scene(500, sky=True)
-    lib = capi.load()
-    desc, keep = scene.to_desc()
-    desc.materials[1].normal_tex = 0
-    handle = capi.C.c_void_p()
-    assert lib.yh_scene_create(capi.C.byref(desc), capi.C.byref(handle)) == capi.YH_ERR_UNSUPPORTED

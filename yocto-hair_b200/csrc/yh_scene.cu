@@ -737,9 +737,8 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
   // ---- validate: anything outside the hot-path scope fails loudly ----
   for (int i = 0; i < d->num_materials; i++) {
     auto& m = d->materials[i];
-    if (m.normal_tex >= 0) return fail(YH_ERR_UNSUPPORTED, "material %d: normal maps are not built", i);
     int texs[] = {m.emission_tex, m.color_tex, m.specular_tex, m.metallic_tex, m.roughness_tex,
-        m.transmission_tex, m.spectint_tex, m.scattering_tex, m.opacity_tex};
+        m.transmission_tex, m.spectint_tex, m.scattering_tex, m.opacity_tex, m.normal_tex};
     for (int t : texs)
       if (t >= d->num_textures) return fail(YH_ERR_INVALID, "material %d: texture index out of range", i);
   }
@@ -814,7 +813,7 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
     if (!m.thin && m.transmission != 0) sc->has_volumes = true;  // has_volume(), yocto_pathtrace.cpp:529-531
     dm.emission_tex = m.emission_tex, dm.color_tex = m.color_tex, dm.specular_tex = m.specular_tex;
     dm.metallic_tex = m.metallic_tex, dm.roughness_tex = m.roughness_tex, dm.transmission_tex = m.transmission_tex;
-    dm.opacity_tex = m.opacity_tex, dm.scattering_tex = m.scattering_tex;
+    dm.opacity_tex = m.opacity_tex, dm.scattering_tex = m.scattering_tex, dm.normal_tex = m.normal_tex;
     dm.any_tex = (m.emission_tex >= 0 || m.color_tex >= 0 || m.specular_tex >= 0 || m.metallic_tex >= 0 || m.roughness_tex >= 0 ||
                   m.transmission_tex >= 0 || m.opacity_tex >= 0 || m.scattering_tex >= 0) ? 1 : 0;
     dm.eumelanin = m.eumelanin, dm.pheomelanin = m.pheomelanin, dm.sigma_a = to_vec(m.sigma_a);

@@ -69,6 +69,7 @@ struct dev_material {
   float scanisotropy, trdepth;
   // float RGB textures (index into dev_scene::textures or -1), eval_brdf / eval_emission / eval_vsdf
   int emission_tex, color_tex, specular_tex, metallic_tex, roughness_tex, transmission_tex, opacity_tex, scattering_tex;
+  int normal_tex;  // tangent-space normal map (eval_normalmap), triangles only
   int any_tex;  // some slot is set: the shading code then evaluates eval_texcoord
   // hair block (yocto_pathtrace.h:310-316)
   float eumelanin, pheomelanin;

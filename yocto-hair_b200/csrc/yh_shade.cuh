@@ -89,6 +89,39 @@ __device__ __forceinline__ vec2f eval_texcoord(const dev_scene& sc, int object, 
   return {t0.x * (1 - uv.x) + t1.x * uv.x, t0.y * (1 - uv.x) + t1.y * uv.x};
 }
 
+// eval_normalmap, :326-347, with eval_element_tangents :312-324 and triangle_tangents_fromuv (yocto_math.h:3360-3383):
+// the tangent-space normal of the texture in the frame built from the uv tangents and the shading normal
+__device__ __forceinline__ vec3f eval_normalmap(const dev_scene& sc, int object, int element, const vec2f& uv, int normal_tex) {
+  const dev_object& ob = sc.objects[object];
+  const dev_shape&  sh = sc.shapes[ob.shape];
+  vec3f normal   = eval_normal(sc, object, element, uv);
+  vec2f texcoord = eval_texcoord(sc, object, element, uv);
+  if (sh.is_lines) return normal;
+  vec3f t2 = 2 * eval_texture(sc, normal_tex, texcoord);
+  vec3f nm = {-1 + t2.x, -1 + t2.y, -1 + t2.z};  // -1 + 2 * texture (operator+(float, vec3f), yocto_math.h:1970)
+  vec3f tu = {0, 0, 0}, tv = {0, 0, 0};  // a shape without texcoords has no tangents (`return {}`)
+  if (sh.texcoords) {
+    int   a = __ldg(sh.elems + 3 * element), b = __ldg(sh.elems + 3 * element + 1), c = __ldg(sh.elems + 3 * element + 2);
+    vec3f p0 = ldp(sh.positions, a), p1 = ldp(sh.positions, b), p2 = ldp(sh.positions, c);
+    auto  ldt = [&](int i) -> vec2f { return {__ldg(sh.texcoords + 2 * i), __ldg(sh.texcoords + 2 * i + 1)}; };
+    vec2f uv0 = ldt(a), uv1 = ldt(b), uv2 = ldt(c);
+    vec3f p = p1 - p0, q = p2 - p0;
+    vec2f s = {uv1.x - uv0.x, uv2.x - uv0.x}, t = {uv1.y - uv0.y, uv2.y - uv0.y};
+    float d = s.x * t.y - s.y * t.x;
+    vec3f eu = {1, 0, 0}, ev = {0, 1, 0};
+    if (d != 0) {
+      eu = vec3f{t.y * p.x - t.x * q.x, t.y * p.y - t.x * q.y, t.y * p.z - t.x * q.z} / d;
+      ev = vec3f{s.x * q.x - s.y * p.x, s.x * q.y - s.y * p.y, s.x * q.z - s.y * p.z} / d;
+    }
+    tu = transform_direction(ob.frame, eu), tv = transform_direction(ob.frame, ev);
+  }
+  vec3f fx = orthonormalize(tu, normal);
+  vec3f fy = normalize(cross(normal, fx));
+  bool  flip_v = dot(fy, tv) < 0;
+  nm.y *= flip_v ? 1.0f : -1.0f;
+  return normalize(fx * nm.x + fy * nm.y + normal * nm.z);
+}
+
 // eval_environment, :536-547
 __device__ __forceinline__ vec3f eval_environment(const dev_scene& sc, const vec3f& dir) {
   vec3f emission = {0, 0, 0};

@@ -327,7 +327,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     tangent = eval_normal(sc, object, element, uv);
     normal  = orthonormalize(outgoing, tangent);
   } else {
-    normal = eval_normal(sc, object, element, uv);
+    normal = mat.normal_tex >= 0 ? eval_normalmap(sc, object, element, uv, mat.normal_tex) : eval_normal(sc, object, element, uv);
     if (mat.thin) normal = dot(normal, outgoing) >= 0 ? normal : -normal;
   }
   // material factors x textures, eval_emission :397-402 and eval_brdf :409-424 (a missing texture evaluates to

@@ -130,7 +130,7 @@ yh_scene* upload(const ptr::scene* scene) {
     d.transmission_tex = linear_of(index_of(scene->textures, m->emission_tex));
     d.spectint_tex = -1;  // never evaluated by the reference's tracer
     d.scattering_tex = index_of(scene->textures, m->scattering_tex);
-    d.opacity_tex = linear_of(index_of(scene->textures, m->opacity_tex)), d.normal_tex = index_of(scene->textures, m->normal_tex);
+    d.opacity_tex = linear_of(index_of(scene->textures, m->opacity_tex)), d.normal_tex = linear_of(index_of(scene->textures, m->normal_tex));
   }
   std::vector<yh_object_desc> objects(scene->objects.size());
   for (size_t i = 0; i < objects.size(); i++) {

@@ -102,6 +102,7 @@ class Material:
     transmission_tex: int = -1  # the reference reads its EMISSION texture for this factor (yocto_pathtrace.cpp:420-421)
     scattering_tex: int = -1
     opacity_tex: int = -1
+    normal_tex: int = -1
 
 
 @dataclass
@@ -195,9 +196,9 @@ class Scene:
             d.eumelanin, d.pheomelanin = m.eumelanin, m.pheomelanin
             d.sigma_a[:] = m.sigma_a
             d.beta_m, d.beta_n, d.alpha, d.eta = m.beta_m, m.beta_n, m.alpha, m.eta
-            d.spectint_tex = d.normal_tex = -1
+            d.spectint_tex = -1
             for name in ("emission_tex", "color_tex", "specular_tex", "metallic_tex", "roughness_tex", "transmission_tex",
-                         "scattering_tex", "opacity_tex"):
+                         "scattering_tex", "opacity_tex", "normal_tex"):
                 setattr(d, name, getattr(m, name))
         objects = (capi.ObjectDesc * max(1, len(self.objects)))()
         for d, o in zip(objects, self.objects):
