@@ -84,3 +84,39 @@ def test_materials_and_byte_textures_through_the_app(tmp_path):
     a, b = scenefiles.read_pfm(tmp_path / "gpu.pfm"), scenefiles.read_pfm(tmp_path / "cpu.pfm")
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert a.mean() > 0.01
+
+
+CUBE_OBJ = """v -1 -1 -1\nv 1 -1 -1\nv 1 1 -1\nv -1 1 -1\nv -1 -1 1\nv 1 -1 1\nv 1 1 1\nv -1 1 1
+vt 0 0\nvt 1 0\nvt 1 1\nvt 0 1
+f 1/1 4/2 3/3 2/4\nf 5/1 6/2 7/3 8/4\nf 1/1 2/2 6/3 5/4\nf 2/1 3/2 7/3 6/4\nf 3/1 4/2 8/3 7/4\nf 4/1 1/2 5/3 8/4
+"""
+
+
+def write_subdiv_scene(tmp_path):
+    """A hair block next to a Catmull-Clark cube (subdivs/<name>.obj, material.subdivisions) with a displacement map."""
+    import json
+    from PIL import Image
+    scene, cam = synth.hair_block_scene(3_000)
+    js = scenefiles.write_scene(tmp_path, "subdiv", scene, cam)
+    (tmp_path / "subdivs").mkdir()
+    (tmp_path / "subdivs" / "cube.obj").write_text(CUBE_OBJ)
+    rng = np.random.default_rng(4)
+    Image.fromarray(rng.integers(0, 255, (8, 8), dtype=np.uint8)).save(tmp_path / "textures" / "bumps.png")
+    d = json.loads(Path(js).read_text())
+    d["materials"]["clay"] = {"color": [0.7, 0.5, 0.4], "specular": 0.5, "roughness": 0.4, "subdivisions": 2,
+                              "displacement": 0.08, "displacement_tex": "bumps"}
+    d["objects"]["zcube"] = {"subdiv": "cube", "material": "clay", "frame": [0.3, 0, 0, 0, 0.3, 0, 0, 0, 0.3, 0.2, 0.35, 1.8]}
+    Path(js).write_text(json.dumps(d))
+    return js
+
+
+def test_subdivision_surfaces_through_the_app(tmp_path):
+    """Subdivision + displacement stay the reference's own host code (init_subdivs runs before either backend builds
+    its BVH, as in apps/yscenetrace/yscenetrace.cpp:243); the tesselated shape then renders bit-identically."""
+    if not APP.exists():
+        pytest.skip("host/_build/yscenetrace_b200 not built")
+    js = write_subdiv_scene(tmp_path)
+    run_app("--backend", "cuda", "-s", 4, "-r", 160, "-o", tmp_path / "gpu.pfm", js)
+    run_app("--backend", "cpu", "-s", 4, "-r", 160, "-o", tmp_path / "cpu.pfm", js)
+    a, b = scenefiles.read_pfm(tmp_path / "gpu.pfm"), scenefiles.read_pfm(tmp_path / "cpu.pfm")
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))

@@ -81,13 +81,28 @@ static ptr::camera* build_trace_scene(ptr::scene* scene, const sio::model* io, c
     ptr::set_lines(shape, s->lines);
     ptr::set_triangles(shape, s->quads.empty() ? s->triangles : shp::quads_to_triangles(s->quads));
   }
+  // subdivision surfaces: control cages go in as shapes with the subdiv fields set; the reference's own
+  // init_subdivs() tesselates and displaces them ON THE HOST before either backend builds its BVH
+  // (apps/yscenetrace/yscenetrace.cpp:120-130, :155-163, :243)
+  std::map<const void*, ptr::shape*> subdivs{{nullptr, nullptr}};
+  for (auto sd : io->subdivs) {
+    auto shape = subdivs[sd] = ptr::add_shape(scene);
+    ptr::set_subdiv_quadspos(shape, sd->quadspos);
+    ptr::set_subdiv_quadstexcoord(shape, sd->quadstexcoord);
+    ptr::set_subdiv_positions(shape, sd->positions);
+    ptr::set_subdiv_texcoords(shape, sd->texcoords);
+  }
   for (auto o : io->objects) {
-    if (o->subdiv) cli::print_fatal("subdivision surfaces are outside the hair hot path (object " + o->name + ")");
     auto frames = o->instance ? o->instance->frames : std::vector<yocto::math::frame3f>{yocto::math::identity3x4f};
     for (auto& f : frames) {
       auto object = ptr::add_object(scene);
       ptr::set_frame(object, o->instance ? f * o->frame : o->frame);
-      ptr::set_shape(object, shapes.at(o->shape));
+      if (o->shape) ptr::set_shape(object, shapes.at(o->shape));
+      if (o->subdiv) {
+        ptr::set_shape(object, subdivs.at(o->subdiv));
+        ptr::set_subdiv_subdivision(subdivs.at(o->subdiv), o->material->subdivisions, true);
+        ptr::set_subdiv_displacement(subdivs.at(o->subdiv), o->material->displacement, textures.at(o->material->displacement_tex));
+      }
       ptr::set_material(object, materials.at(o->material));
     }
   }
@@ -148,6 +163,7 @@ int main(int argc, const char* argv[]) {
   auto state = std::make_unique<ptr::state>();
   auto t0    = clock();
   try {
+    ptr::init_subdivs(scene.get(), params, cli::print_progress);  // host tesselation, the reference's own (both backends)
     if (on_gpu) {
       auto opts   = gpu::device_options{};
       opts.device = device;
@@ -156,7 +172,6 @@ int main(int argc, const char* argv[]) {
       gpu::init_lights(scene.get(), params, cli::print_progress);
       gpu::init_state(state.get(), scene.get(), camera, params);
     } else {
-      ptr::init_subdivs(scene.get(), params, cli::print_progress);
       ptr::init_bvh(scene.get(), params, cli::print_progress);
       ptr::init_lights(scene.get(), params, cli::print_progress);
       ptr::init_state(state.get(), scene.get(), camera, params);
