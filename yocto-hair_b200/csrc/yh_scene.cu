@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <future>
@@ -330,20 +331,33 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
   bool lines = sh.is_lines();
   int  n     = sh.num_elems();
   auto P     = [&](int v) { return vec3f{sh.positions[3 * v], sh.positions[3 * v + 1], sh.positions[3 * v + 2]}; };
+  // the two linear passes run in chunks on host threads (a million primitives: ~15 ms each on one core)
+  auto chunks = [n](auto&& body) {
+    const int nt = n > (1 << 16) ? 8 : 1;
+    std::vector<std::future<void>> jobs;
+    for (int t = 0; t < nt; t++)
+      jobs.push_back(std::async(nt > 1 ? std::launch::async : std::launch::deferred,
+          [&body, n, nt, t]() { body((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); }));
+    for (auto& j : jobs) j.get();
+  };
   std::vector<ref_prim> prims(n);
-  for (int i = 0; i < n; i++) {
-    bbox3f b;
-    if (lines) {
-      int a = sh.lines[2 * i], c = sh.lines[2 * i + 1];
-      b     = line_bounds(P(a), P(c), sh.radius[a], sh.radius[c]);
-    } else {
-      b = triangle_bounds(P(sh.triangles[3 * i]), P(sh.triangles[3 * i + 1]), P(sh.triangles[3 * i + 2]));
+  chunks([&](int i0, int i1) {
+    for (int i = i0; i < i1; i++) {
+      bbox3f b;
+      if (lines) {
+        int a = sh.lines[2 * i], c = sh.lines[2 * i + 1];
+        b     = line_bounds(P(a), P(c), sh.radius[a], sh.radius[c]);
+      } else {
+        b = triangle_bounds(P(sh.triangles[3 * i]), P(sh.triangles[3 * i + 1]), P(sh.triangles[3 * i + 2]));
+      }
+      prims[i] = {(b.min + b.max) / 2.0f, i};  // center(bbox), yocto_math.h:3008
     }
-    prims[i] = {(b.min + b.max) / 2.0f, i};  // center(bbox), yocto_math.h:3008
-  }
+  });
   tie_nodes = reference_tree(prims.data(), 0, n, 0);
   ref_pos.assign(n, 0);
-  for (int i = 0; i < n; i++) ref_pos[prims[i].primitive] = i;
+  chunks([&](int i0, int i1) {
+    for (int i = i0; i < i1; i++) ref_pos[prims[i].primitive] = i;
+  });
 }
 
 // ---- quality builder (yh_bvh_params::quality = 1): binned SAH, top down, on the host ----------
@@ -505,24 +519,16 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   sh.root_leaf = 0, sh.num_refs = 0, sh.num_nodes = 0;
   sh.root_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   if (n == 0) return YH_OK;
-  // the reference's leaf order is a host computation (it depends on std::partition); it runs in
-  // host threads while the device builds the LBVH below, and is uploaded at the end
-  struct tie_tables { std::vector<int> ref_pos; std::vector<int4> tie_nodes; };
-  auto tie_future = std::async(std::launch::async, [&sh]() {
-    tie_tables t;
-    reference_tree_order(sh, t.ref_pos, t.tie_nodes);
-    return t;
-  });
-  auto upload_ties = [&]() -> yh_status {
-    tie_tables t = tie_future.get();
-    YH_CUDA(sh.d_ref_pos.upload(t.ref_pos.data(), t.ref_pos.size()));
-    YH_CUDA(sh.d_tie_nodes.upload(t.tie_nodes.data(), t.tie_nodes.size()));
-    return YH_OK;
+  // YH_BUILD_TIMING=1: phase times of this build on stderr (host clock; each mark synchronises the device)
+  const bool timing = getenv("YH_BUILD_TIMING") != nullptr;
+  auto       t_last = std::chrono::steady_clock::now();
+  auto       mark   = [&](const char* what) {
+    if (!timing) return;
+    cudaDeviceSynchronize();
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "  bvh %-28s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
   };
-  struct tie_guard {  // an early return must still join the host thread before `sh` can go away
-    std::future<tie_tables>& f;
-    ~tie_guard() { if (f.valid()) f.wait(); }
-  } guard{tie_future};
   if (!lines) max_split = 1;
   const int B = 256;
   auto      G = [&](int c) { return (c + B - 1) / B; };
@@ -544,20 +550,36 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   int R = last_off + last_cnt;
   if (R >= (1 << 28)) return fail(YH_ERR_UNSUPPORTED, "shape has %d BVH references (limit 2^28)", R);
 
+  mark("count + scan references");
   // centre bounds for Morton quantisation (host pass over the vertices)
   vec3f cmin = {flt_max, flt_max, flt_max}, cmax = {-flt_max, -flt_max, -flt_max};
-  for (size_t v = 0; v + 2 < sh.positions.size(); v += 3) {
-    vec3f p = {sh.positions[v], sh.positions[v + 1], sh.positions[v + 2]};
-    cmin    = min3(cmin, p);
-    cmax    = max3(cmax, p);
-  }
   float rmax = 0;
-  for (float r : sh.radius) rmax = fmax_(rmax, fabs_(r));
+  {
+    const size_t nv = sh.positions.size() / 3;
+    const int    nt = nv > (1u << 16) ? 8 : 1;
+    struct part { vec3f lo, hi; float r; };
+    std::vector<std::future<part>> parts;
+    for (int t = 0; t < nt; t++)
+      parts.push_back(std::async(nt > 1 ? std::launch::async : std::launch::deferred, [&sh, nv, nt, t]() {
+        part q{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}, 0};
+        for (size_t v = nv * t / nt; v < nv * (t + 1) / nt; v++) {
+          vec3f p = {sh.positions[3 * v], sh.positions[3 * v + 1], sh.positions[3 * v + 2]};
+          q.lo = min3(q.lo, p), q.hi = max3(q.hi, p);
+        }
+        for (size_t v = sh.radius.size() * t / nt; v < sh.radius.size() * (t + 1) / nt; v++) q.r = fmax_(q.r, fabs_(sh.radius[v]));
+        return q;
+      }));
+    for (auto& f : parts) {
+      part q = f.get();
+      cmin = min3(cmin, q.lo), cmax = max3(cmax, q.hi), rmax = fmax_(rmax, q.r);
+    }
+  }
   sh.scale = fmax_(fmax_(fmax_(fabs_(cmin.x), fabs_(cmax.x)), fmax_(fabs_(cmin.y), fabs_(cmax.y))),
                  fmax_(fabs_(cmin.z), fabs_(cmax.z))) + rmax;
   vec3f ext  = cmax - cmin;
   vec3f cinv = {ext.x > 0 ? 1.0f / ext.x : 0.0f, ext.y > 0 ? 1.0f / ext.y : 0.0f, ext.z > 0 ? 1.0f / ext.z : 0.0f};
 
+  mark("host bounds of the vertices");
   dev_buffer<ref_bounds>         refs;
   dev_buffer<int>                ref_prim, ids_in, ids_out;
   dev_buffer<unsigned long long> keys_in, keys_out;
@@ -575,6 +597,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   YH_CUDA(tmp.alloc(tmp_bytes));
   YH_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys_in.ptr, keys_out.ptr, ids_in.ptr, ids_out.ptr, R, 0, 63));
 
+  mark("references + Morton sort");
   // grid of the packed boxes: 16 bits per axis over the (padded) bounds of the shape
   float pad  = 2e-6f * sh.scale + 1e-30f;
   vec3f glo  = cmin - (rmax + pad), ghi = cmax + (rmax + pad);
@@ -619,7 +642,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
     int zero = 0;
     YH_CUDA(cudaMemcpy(sh.d_slots.ptr, rec, 32, cudaMemcpyHostToDevice));
     YH_CUDA(cudaMemcpy(sh.d_slot_elem.ptr, &zero, 4, cudaMemcpyHostToDevice));
-    return upload_ties();
+    return YH_OK;
   }
   sh.root_leaf = 0;
 
@@ -656,11 +679,13 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
       ref_prim.ptr, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, sh.grid_origin, inv_step, pad_steps, sh.d_slots.ptr,
       sh.d_slot_elem.ptr);
   YH_CUDA(cudaGetLastError());
+  mark("hierarchy + refit + emit");
   ref_bounds rb;
   YH_CUDA(cudaMemcpy(&rb, node_box.ptr, sizeof(rb), cudaMemcpyDeviceToHost));
   sh.root_bbox = {{rb.lo.x, rb.lo.y, rb.lo.z}, {rb.hi.x, rb.hi.y, rb.hi.z}};
   YH_CUDA(cudaDeviceSynchronize());
-  return upload_ties();
+  mark("root box");
+  return YH_OK;
 }
 
 // transform_bbox(frame, bbox), yocto_math.h:3172-3182, plus padding
@@ -684,6 +709,8 @@ static bbox3f transform_bbox_padded(const frame3f& f, const bbox3f& b) {
 
 using namespace yh;
 
+static yh_status upload_tables(yh_scene* sc);
+
 yh::dev_scene yh_scene::view() const {
   dev_scene v{};
   v.shapes = d_shapes.ptr, v.materials = d_materials.ptr, v.objects = d_objects.ptr;
@@ -693,6 +720,19 @@ yh::dev_scene yh_scene::view() const {
   v.num_environments = (int)environments.size(), v.num_lights = (int)lights.size();
   return v;
 }
+yh_status yh_scene::sync_ties() const {
+  std::lock_guard<std::mutex> lock(tie_mutex);
+  if (!ties_pending) return YH_OK;
+  for (auto s : shapes) {
+    if (!s->tie_future.valid()) continue;
+    host_shape::tie_tables t = s->tie_future.get();
+    YH_CUDA(s->d_ref_pos.upload(t.ref_pos.data(), t.ref_pos.size()));
+    YH_CUDA(s->d_tie_nodes.upload(t.tie_nodes.data(), t.tie_nodes.size()));
+  }
+  ties_pending = false;
+  return upload_tables(const_cast<yh_scene*>(this));  // the shape table carries the new pointers
+}
+
 yh_scene::~yh_scene() {
   for (auto s : shapes) delete s;
   for (auto t : tex_dev) delete t;
@@ -794,6 +834,14 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
             hs->is_lines() ? hs->lines.size() : hs->triangles.size()) != cudaSuccess)
       return bail(fail(YH_ERR_CUDA, "shape %d: device upload failed: %s", i, cudaGetErrorString(cudaGetLastError())));
   }
+  for (auto hs : sc->shapes)
+    if (hs->num_elems() > 0)
+      hs->tie_future = std::async(std::launch::async, [hs]() {
+        host_shape::tie_tables t;
+        reference_tree_order(*hs, t.ref_pos, t.tie_nodes);
+        return t;
+      });
+  sc->ties_pending = true;
   for (int i = 0; i < d->num_textures; i++) {
     auto& t = d->textures[i];
     if (!t.colorf || t.width <= 0 || t.height <= 0) return bail(fail(YH_ERR_INVALID, "texture %d is empty", i));

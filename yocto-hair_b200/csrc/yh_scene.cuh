@@ -29,6 +29,8 @@
 //   shading data : the reference's own arrays (positions, normals = hair
 //                  tangents, lines / triangles) for eval_position / eval_normal.
 #pragma once
+#include <future>
+#include <mutex>
 #include <vector>
 
 #include "yh_common.cuh"
@@ -135,6 +137,17 @@ struct host_shape {
   bbox3f             root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   int  num_elems() const { return is_lines() ? (int)lines.size() / 2 : (int)triangles.size() / 3; }
   bool is_lines() const { return !lines.empty(); }
+  // The reference's leaf order (tie tables) is a host computation of ~25 ms per million primitives: it starts in
+  // yh_scene_create, runs beside the uploads, the device BVH build, the light tables and the state set-up, and
+  // is joined by the first call that traverses (yh_scene::sync_ties()).
+  struct tie_tables {
+    std::vector<int>  ref_pos;
+    std::vector<int4> tie_nodes;
+  };
+  std::future<tie_tables> tie_future;
+  ~host_shape() {
+    if (tie_future.valid()) tie_future.wait();
+  }
 };
 
 }  // namespace yh
@@ -161,5 +174,10 @@ struct yh_scene {
   int  device = 0;
   yh_bvh_stats stats{};
   yh::dev_scene view() const;
+  // joins the host threads that compute the reference leaf order and uploads their tables (once); every entry
+  // point that launches a traversal calls it first
+  yh_status sync_ties() const;
+  mutable std::mutex tie_mutex;
+  mutable bool       ties_pending = false;
   ~yh_scene();
 };
