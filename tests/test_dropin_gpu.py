@@ -120,3 +120,25 @@ def test_subdivision_surfaces_through_the_app(tmp_path):
     run_app("--backend", "cpu", "-s", 4, "-r", 160, "-o", tmp_path / "cpu.pfm", js)
     a, b = scenefiles.read_pfm(tmp_path / "gpu.pfm"), scenefiles.read_pfm(tmp_path / "cpu.pfm")
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_interactive_session_headless(tmp_path):
+    """the interactive consumer's use of the boundary (apps/ysceneitraces/ysceneitraces.cpp:255-302)
+    without the window - preview at resolution / pratio, a worker thread adding one sample per pass under a stop
+    flag, a camera edit that resets the state, a render to completion.  The preview and the post-edit image are
+    bit-identical between the backends; on the device the interrupted state equals a fresh render of the passes
+    that completed (the app checks it and fails otherwise)."""
+    if not APP.exists():
+        pytest.skip("host/_build/yscenetrace_b200 not built")
+    scene, cam = synth.straight_hair_scene(12_000)
+    js = scenefiles.write_scene(tmp_path, "session", scene, cam)
+    outs = {}
+    for backend in ("cuda", "cpu"):
+        d = tmp_path / backend
+        d.mkdir()
+        outs[backend] = run_app("--backend", backend, "-s", 5, "-r", 128, "--interactive-check", d, "--stop-after", 2, js)
+    assert "interrupted state equals a fresh" in outs["cuda"]
+    for name in ("preview.pfm", "edited.pfm"):
+        a, b = scenefiles.read_pfm(tmp_path / "cuda" / name), scenefiles.read_pfm(tmp_path / "cpu" / name)
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
+    assert scenefiles.read_pfm(tmp_path / "cuda" / "preview.pfm").shape[1] == 128 // 8  # params.pratio = 8

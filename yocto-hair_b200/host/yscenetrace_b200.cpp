@@ -15,7 +15,11 @@
 #include <yocto/yocto_shape.h>
 #include <yocto_pathtrace/yocto_pathtrace.h>
 
+#include <atomic>
 #include <chrono>
+#include <cstring>
+#include <future>
+#include <thread>
 #include <map>
 #include <memory>
 
@@ -114,6 +118,89 @@ static ptr::camera* build_trace_scene(ptr::scene* scene, const sio::model* io, c
   return chosen;
 }
 
+// ---- the interactive consumer, headless -----------------------------------------
+// What apps/ysceneitraces/ysceneitraces.cpp:255-302 (reset_display) does to the tracer, without the window: a
+// preview pass at resolution / pratio, a worker thread that adds one sample per pass and polls a stop flag, a
+// camera edit that stops the worker and resets the state, then a render to completion.  Both backends run the
+// same sequence; the files it writes (<dir>/preview.pfm, edited.pfm) must agree between them, and on the device
+// the interrupted state must equal a fresh render of exactly the passes that completed.
+template <typename Backend>
+static int interactive_session(const Backend& be, ptr::scene* scene, ptr::camera* camera, const ptr::trace_params& params,
+    const std::string& dir, int stop_after, bool check_interrupted) {
+  auto save = [&](const std::string& name, const yocto::image::image<yocto::math::vec4f>& img) {
+    auto error = ""s;
+    if (!save_image(dir + "/" + name, img, error)) cli::print_fatal(error);
+  };
+  // reset_display: preview (:268-283)
+  auto pstate = std::make_unique<ptr::state>();
+  auto pprms  = params;
+  pprms.resolution /= params.pratio;
+  pprms.samples = 1;
+  be.init_state(pstate.get(), scene, camera, pprms);
+  be.trace_samples(pstate.get(), scene, camera, pprms, nullptr);
+  save("preview.pfm", pstate->render);
+  // reset_display: the render worker (:286-300), stopped from this thread after `stop_after` passes
+  auto state = std::make_unique<ptr::state>();
+  be.init_state(state.get(), scene, camera, params);
+  std::atomic<bool> stop{false};
+  std::atomic<int>  passes{0};
+  auto worker = std::async(std::launch::async, [&]() {
+    for (auto sample = 0; sample < params.samples; sample++) {
+      if (stop) return;
+      be.trace_samples(state.get(), scene, camera, params, &stop);
+      if (stop) return;  // a pass that saw the flag did not count (the reference abandons it mid-image)
+      passes++;
+    }
+  });
+  while (passes < stop_after && passes < params.samples) std::this_thread::sleep_for(std::chrono::microseconds(200));
+  stop = true;
+  worker.get();
+  int completed = passes;
+  printf("interactive: stopped after %d of %d passes\n", completed, params.samples);
+  if (check_interrupted) {  // device passes are atomic: the interrupted image is a clean k-sample render, where k
+                            // counts the pass that was in flight when the flag rose (it ran to its end)
+    completed = be.samples_done(state.get());
+    auto fresh = std::make_unique<ptr::state>();
+    be.init_state(fresh.get(), scene, camera, params);
+    for (int s = 0; s < completed; s++) be.trace_samples(fresh.get(), scene, camera, params, nullptr);
+    bool same = completed == 0 || memcmp(fresh->render.data(), state->render.data(), sizeof(yocto::math::vec4f) * fresh->render.count()) == 0;
+    printf("interactive: interrupted state %s a fresh %d-sample render\n", same ? "equals" : "DIFFERS FROM", completed);
+    if (!same) return 3;
+  }
+  // camera edit -> reset_display again -> render to completion
+  camera->frame.o = camera->frame.o + camera->frame.x * 0.35f + camera->frame.y * 0.1f;
+  be.init_state(state.get(), scene, camera, params);
+  stop = false;
+  for (auto sample = 0; sample < params.samples; sample++) be.trace_samples(state.get(), scene, camera, params, &stop);
+  save("edited.pfm", state->render);
+  return 0;
+}
+struct device_backend {
+  int samples_done(ptr::state* st) const {
+    gpu::sync_pixels(st);
+    return st->pixels.empty() ? 0 : st->pixels[{0, 0}].samples;
+  }
+  void init_state(ptr::state* st, const ptr::scene* sc, const ptr::camera* cam, const ptr::trace_params& p) const {
+    gpu::init_state(st, sc, cam, p);
+  }
+  void trace_samples(ptr::state* st, const ptr::scene* sc, const ptr::camera* cam, const ptr::trace_params& p,
+      std::atomic<bool>* stop) const {
+    if (stop) gpu::trace_samples(st, sc, cam, p, stop);
+    else gpu::trace_samples(st, sc, cam, p);
+  }
+};
+struct reference_backend {
+  int samples_done(ptr::state* st) const { return st->pixels.empty() ? 0 : st->pixels[{0, 0}].samples; }
+  void init_state(ptr::state* st, const ptr::scene* sc, const ptr::camera* cam, const ptr::trace_params& p) const {
+    ptr::init_state(st, sc, cam, p);
+  }
+  void trace_samples(ptr::state* st, const ptr::scene* sc, const ptr::camera* cam, const ptr::trace_params& p,
+      std::atomic<bool>* stop) const {
+    if (stop) ptr::trace_samples(st, sc, cam, p, stop);
+    else ptr::trace_samples(st, sc, cam, p);
+  }
+};
+
 int main(int argc, const char* argv[]) {
   auto params      = ptr::trace_params{};
   auto save_batch  = false;
@@ -125,12 +212,16 @@ int main(int argc, const char* argv[]) {
   auto device      = 0;
   auto seed        = (int)ptr::default_seed;
   auto loader      = "fast"s;
+  auto session_dir = ""s;
+  auto stop_after  = 2;
 
   auto cli = cli::make_cli("yscenetrace_b200", "Offline hair path tracing on B200");
   add_option(cli, "--backend", backend, "cuda (B200 library) or cpu (the reference's own code).");
   add_option(cli, "--spp-batch", spp_batch, "Samples per pixel per device call.");
   add_option(cli, "--loader", loader, "fast (bulk PLY reader, yh_sceneio) or reference (yocto_sceneio).");
   add_option(cli, "--device", device, "CUDA device.");
+  add_option(cli, "--interactive-check", session_dir, "Run the headless interactive session and write its images here.");
+  add_option(cli, "--stop-after", stop_after, "Interactive session: passes before the simulated camera edit.");
   add_option(cli, "--seed", seed, "Render seed (trace_params::seed).");
   add_option(cli, "--camera", camera_name, "Camera name.");
   add_option(cli, "--resolution,-r", params.resolution, "Image resolution.");
@@ -175,6 +266,12 @@ int main(int argc, const char* argv[]) {
       ptr::init_bvh(scene.get(), params, cli::print_progress);
       ptr::init_lights(scene.get(), params, cli::print_progress);
       ptr::init_state(state.get(), scene.get(), camera, params);
+    }
+    if (!session_dir.empty()) {
+      int rc = on_gpu ? interactive_session(device_backend{}, scene.get(), camera, params, session_dir, stop_after, true)
+                      : interactive_session(reference_backend{}, scene.get(), camera, params, session_dir, stop_after, false);
+      if (on_gpu) gpu::release(scene.get());
+      return rc;
     }
     auto t1 = clock();
     if (save_batch || !on_gpu) spp_batch = 1;
