@@ -10,8 +10,11 @@
  * statistical self-tests, line / triangle / box tests, the middle-split BVH
  * (build + depth-first walk, two levels), camera, diffuse + hair lobes,
  * environment / area lights, trace_path (MIS path shader), trace_sample,
- * init_state.  Materials with specular / metallic / transmission / volumes /
- * textures are outside that scope and are not restated.
+ * init_state; and the material model of the triangles that share a scene
+ * with the hair: specular / metal / thin transmission /
+ * refraction lobes and their delta forms, opacity, homogeneous volumes, float
+ * RGB material textures and normal maps (byte textures are expanded by the
+ * caller, as for the CUDA library).
  *
  * Arithmetic: fp32, no FMA contraction (-ffp-contract=off), glibc libm, with
  * the reference's two double-precision calls (asin, sinh) kept in double.
@@ -630,12 +633,18 @@ static tree_t build_tree(bprim_t* p, int n) { /* pt:601-650: breadth-first, leav
 /* ================================================================== scene == */
 typedef struct {
   v3 *pos, *nrm;
+  v2* tex;
   float* rad;
   int *lines, *tris;
-  int   npos, nnrm, nlines, ntris;
+  int   npos, nnrm, ntex, nlines, ntris;
   tree_t bvh;
 } shape_t;
-typedef struct { v3 emission, color; float opacity; int thin; yh_hair_material hair; } mat_t;
+typedef struct {
+  v3 emission, color; float opacity; int thin; yh_hair_material hair;
+  float specular, metallic, roughness, ior, transmission; /* surface lobes, pt header :293-307 */
+  v3    scattering; float scanisotropy, trdepth;          /* volume behind a refractive surface */
+  int   emission_tex, color_tex, specular_tex, metallic_tex, roughness_tex, transmission_tex, opacity_tex, scattering_tex, normal_tex;
+} mat_t;
 typedef struct { fr3 frame; int shape, material; } obj_t;
 typedef struct { v3* px; int w, h; } tex_t;
 typedef struct { fr3 frame; v3 emission; int tex; } env_t;
@@ -733,6 +742,8 @@ void* yho_scene_create(const yh_scene_desc* d) {
     t->npos = s->num_positions, t->nnrm = s->num_normals, t->nlines = s->num_lines, t->ntris = s->num_triangles;
     t->pos = (v3*)dup_mem(s->positions, 12 * (size_t)t->npos);
     t->nrm = (v3*)dup_mem(s->normals, 12 * (size_t)t->nnrm);
+    t->ntex = s->num_texcoords;
+    t->tex = (v2*)dup_mem(s->texcoords, 8 * (size_t)t->ntex);
     t->rad = (float*)dup_mem(s->radius, 4 * (size_t)s->num_radius);
     t->lines = (int*)dup_mem(s->lines, 8 * (size_t)t->nlines);
     t->tris = (int*)dup_mem(s->triangles, 12 * (size_t)t->ntris);
@@ -751,6 +762,12 @@ void* yho_scene_create(const yh_scene_desc* d) {
     t->emission = V(m->emission[0], m->emission[1], m->emission[2]);
     t->color = V(m->color[0], m->color[1], m->color[2]);
     t->opacity = m->opacity, t->thin = m->thin;
+    t->specular = m->specular, t->metallic = m->metallic, t->roughness = m->roughness, t->ior = m->ior;
+    t->transmission = m->transmission, t->scanisotropy = m->scanisotropy, t->trdepth = m->trdepth;
+    t->scattering = V(m->scattering[0], m->scattering[1], m->scattering[2]);
+    t->emission_tex = m->emission_tex, t->color_tex = m->color_tex, t->specular_tex = m->specular_tex;
+    t->metallic_tex = m->metallic_tex, t->roughness_tex = m->roughness_tex, t->transmission_tex = m->transmission_tex;
+    t->opacity_tex = m->opacity_tex, t->scattering_tex = m->scattering_tex, t->normal_tex = m->normal_tex;
     memcpy(t->hair.sigma_a, m->sigma_a, 12);
     t->hair.beta_m = m->beta_m, t->hair.beta_n = m->beta_n, t->hair.alpha = m->alpha, t->hair.eta = m->eta;
     memcpy(t->hair.color, m->color, 12);
@@ -776,7 +793,7 @@ void yho_scene_destroy(void* h) {
   if (!sc) return;
   for (int i = 0; i < sc->nshapes; i++) {
     shape_t* s = &sc->shapes[i];
-    free(s->pos), free(s->nrm), free(s->rad), free(s->lines), free(s->tris), free(s->bvh.nodes), free(s->bvh.prims);
+    free(s->pos), free(s->nrm), free(s->tex), free(s->rad), free(s->lines), free(s->tris), free(s->bvh.nodes), free(s->bvh.prims);
   }
   for (int i = 0; i < sc->ntexs; i++) free(sc->texs[i].px);
   for (int i = 0; i < sc->nlights; i++) free(sc->lights[i].cdf);
@@ -1046,6 +1063,394 @@ static ray_t camera_ray(const state_t* st, int i, int j, v2 puv, v2 luv) { /* pt
 /* trace_path pt:1380-1511, trace_naive pt:1514-1573, trace_eyelight pt:1576-1633 and trace_normal
  * pt:1636-1651 (selected by params->shader as get_trace_shader_func does, pt:1662-1673), for the
  * lobes of SURVEY.md 8a (hair on lines, diffuse on triangles). */
+
+static v2 eval_texcoord(const scene_t* sc, int object, int element, v2 uv) { /* pt:294-309 */
+  const shape_t* s = &sc->shapes[sc->objs[object].shape];
+  if (s->ntex == 0) return uv;
+  v2 r;
+  if (s->ntris) {
+    v2    t0 = s->tex[s->tris[3 * element]], t1 = s->tex[s->tris[3 * element + 1]], t2 = s->tex[s->tris[3 * element + 2]];
+    float w = 1 - uv.x - uv.y;
+    r.x = t0.x * w + t1.x * uv.x + t2.x * uv.y, r.y = t0.y * w + t1.y * uv.x + t2.y * uv.y;
+    return r;
+  }
+  v2 t0 = s->tex[s->lines[2 * element]], t1 = s->tex[s->lines[2 * element + 1]];
+  r.x = t0.x * (1 - uv.x) + t1.x * uv.x, r.y = t0.y * (1 - uv.x) + t1.y * uv.x;
+  return r;
+}
+static v3 eval_normalmap(const scene_t* sc, int object, int element, v2 uv, int normal_tex) { /* pt:312-347 */
+  const obj_t*   ob = &sc->objs[object];
+  const shape_t* s = &sc->shapes[ob->shape];
+  v3 normal = eval_normal(sc, object, element, uv);
+  v2 texcoord = eval_texcoord(sc, object, element, uv);
+  if (!s->ntris) return normal;
+  v3 t2x = vs(eval_texture(sc, normal_tex, texcoord), 2);
+  v3 nm = V(-1 + t2x.x, -1 + t2x.y, -1 + t2x.z);
+  v3 tu = V(0, 0, 0), tv = V(0, 0, 0);
+  if (s->ntex) { /* triangle_tangents_fromuv, ym:3360-3383 */
+    int a = s->tris[3 * element], b = s->tris[3 * element + 1], c = s->tris[3 * element + 2];
+    v3  p = vsub(s->pos[b], s->pos[a]), q = vsub(s->pos[c], s->pos[a]);
+    v2  uv0 = s->tex[a], uv1 = s->tex[b], uv2 = s->tex[c];
+    float sx = uv1.x - uv0.x, sy = uv2.x - uv0.x, tx = uv1.y - uv0.y, ty = uv2.y - uv0.y;
+    float d = sx * ty - sy * tx;
+    v3 eu = V(1, 0, 0), ev = V(0, 1, 0);
+    if (d != 0) {
+      eu = vds(V(ty * p.x - tx * q.x, ty * p.y - tx * q.y, ty * p.z - tx * q.z), d);
+      ev = vds(V(sx * q.x - sy * p.x, sx * q.y - sy * p.y, sx * q.z - sy * p.z), d);
+    }
+    tu = xf_direction(&ob->frame, eu), tv = xf_direction(&ob->frame, ev);
+  }
+  v3  fx = orthonorm(tu, normal);
+  v3  fy = norm3(cross3(normal, fx));
+  int flip_v = dot3(fy, tv) < 0;
+  nm.y *= flip_v ? 1.0f : -1.0f;
+  return norm3(vadd(vadd(vs(fx, nm.x), vs(fy, nm.y)), vs(normal, nm.z)));
+}
+
+/* ---- surface lobes, refraction, volumes (ym:4215-4812; pt:405-531, :1069-1280, :1360-1378) ---------------------- */
+typedef struct {
+  v3 diffuse, specular, metal, transmission, refraction;
+  float roughness, ior;
+  v3 meta, metak;
+  float diffuse_pdf, specular_pdf, metal_pdf, transmission_pdf, refraction_pdf;
+} sbrdf; /* pt:372-393 without the hair block */
+typedef struct { v3 density, scatter; float anisotropy; } vsdf_t; /* pt:498-502 */
+
+static float fresnel_dielectric(float eta, v3 normal, v3 outgoing) { /* ym:4215-4235 */
+  float cosw = absr(dot3(normal, outgoing));
+  float sin2 = 1 - cosw * cosw, eta2 = eta * eta;
+  float cos2t = 1 - sin2 / eta2;
+  if (cos2t < 0) return 1;
+  float t0 = sqrtf(cos2t), t1 = eta * t0, t2 = eta * cosw;
+  float rs = (cosw - t1) / (cosw + t1), rp = (t0 - t2) / (t0 + t2);
+  return (rs * rs + rp * rp) / 2;
+}
+static float conductor1(float e, float k, float cosw, float cos2, float sin2) {
+  float eta2 = e * e, etak2 = k * k;
+  float t0 = eta2 - etak2 - sin2;
+  float a2plusb2 = sqrtf(t0 * t0 + 4 * eta2 * etak2);
+  float t1 = a2plusb2 + cos2;
+  float a  = sqrtf((a2plusb2 + t0) / 2);
+  float t2 = 2 * a * cosw;
+  float rs = (t1 - t2) / (t1 + t2);
+  float t3 = cos2 * a2plusb2 + sin2 * sin2;
+  float t4 = t2 * sin2;
+  float rp = rs * (t3 - t4) / (t3 + t4);
+  return (rp + rs) / 2;
+}
+static v3 fresnel_conductor(v3 eta, v3 etak, v3 normal, v3 outgoing) { /* ym:4238-4263, per component */
+  float cosw = dot3(normal, outgoing);
+  if (cosw <= 0) return V(0, 0, 0);
+  cosw = clampr(cosw, -1.0f, 1.0f);
+  float cos2 = cosw * cosw, sin2 = clampr(1 - cos2, 0.0f, 1.0f);
+  return V(conductor1(eta.x, etak.x, cosw, cos2, sin2), conductor1(eta.y, etak.y, cosw, cos2, sin2), conductor1(eta.z, etak.z, cosw, cos2, sin2));
+}
+static float refl_to_eta1(float r) { r = clampr(r, 0.0f, 0.99f); return (1 + sqrtf(r)) / (1 - sqrtf(r)); }
+static v3 reflectivity_to_eta(v3 r) { return V(refl_to_eta1(r.x), refl_to_eta1(r.y), refl_to_eta1(r.z)); } /* ym:4270-4273 */
+static v3 reflect3(v3 w, v3 n) { return vadd(vneg(w), vs(n, 2 * dot3(n, w))); }                           /* ym:2059-2061 */
+static v3 refract3(v3 w, v3 n, float inv_eta) {                                                           /* ym:2062-2067 */
+  float cosine = dot3(n, w);
+  float k = 1 + inv_eta * inv_eta * (cosine * cosine - 1);
+  if (k < 0) return V(0, 0, 0);
+  return vadd(vs(vneg(w), inv_eta), vs(n, inv_eta * cosine - sqrtf(k)));
+}
+static float mf_distribution(float roughness, v3 normal, v3 halfway) { /* ym:4307-4322, ggx */
+  float cosine = dot3(normal, halfway);
+  if (cosine <= 0) return 0;
+  float r2 = roughness * roughness, c2 = cosine * cosine;
+  return r2 / (PIF * (c2 * r2 + 1 - c2) * (c2 * r2 + 1 - c2));
+}
+static float mf_shadowing1(float roughness, v3 normal, v3 halfway, v3 direction) { /* ym:4325-4343 */
+  float cosine = dot3(normal, direction), cosineh = dot3(halfway, direction);
+  if (cosine * cosineh <= 0) return 0;
+  float r2 = roughness * roughness, c2 = cosine * cosine;
+  return 2 * absr(cosine) / (absr(cosine) + sqrtf(c2 - r2 * c2 + r2));
+}
+static float mf_shadowing(float roughness, v3 normal, v3 halfway, v3 outgoing, v3 incoming) { /* ym:4346-4351 */
+  return mf_shadowing1(roughness, normal, halfway, outgoing) * mf_shadowing1(roughness, normal, halfway, incoming);
+}
+static v3 sample_mf(float roughness, v3 normal, v2 rn) { /* ym:4354-4367 */
+  float phi = 2 * PIF * rn.x;
+  float theta = atanf(roughness * sqrtf(rn.y / (1 - rn.y)));
+  fr3   basis = basis_fromz(normal);
+  return xf_direction(&basis, V(cosf(phi) * sinf(theta), sinf(phi) * sinf(theta), cosf(theta)));
+}
+static float sample_mf_pdf(float roughness, v3 normal, v3 halfway) { /* ym:4370-4375 */
+  float cosine = dot3(normal, halfway);
+  if (cosine < 0) return 0;
+  return mf_distribution(roughness, normal, halfway) * cosine;
+}
+static v3 bcast(float v) { return V(v, v, v); }
+static v3 eval_mf_reflection(float ior, float roughness, v3 normal, v3 outgoing, v3 incoming) { /* ym:4441-4451 */
+  if (dot3(normal, incoming) <= 0 || dot3(normal, outgoing) <= 0) return V(0, 0, 0);
+  v3    halfway = norm3(vadd(incoming, outgoing));
+  float F = fresnel_dielectric(ior, halfway, incoming), D = mf_distribution(roughness, normal, halfway);
+  float G = mf_shadowing(roughness, normal, halfway, outgoing, incoming);
+  return bcast(1.0f * F * D * G / (4 * dot3(normal, outgoing) * dot3(normal, incoming)) * dot3(normal, incoming));
+}
+static v3 eval_mf_reflection_metal(v3 eta, v3 etak, float roughness, v3 normal, v3 outgoing, v3 incoming) { /* ym:4454-4464 */
+  if (dot3(normal, incoming) <= 0 || dot3(normal, outgoing) <= 0) return V(0, 0, 0);
+  v3    halfway = norm3(vadd(incoming, outgoing));
+  v3    F = fresnel_conductor(eta, etak, halfway, incoming);
+  float D = mf_distribution(roughness, normal, halfway), G = mf_shadowing(roughness, normal, halfway, outgoing, incoming);
+  return vs(vds(vs(vs(F, D), G), 4 * dot3(normal, outgoing) * dot3(normal, incoming)), dot3(normal, incoming));
+}
+static v3 eval_mf_transmission(float roughness, v3 normal, v3 outgoing, v3 incoming) { /* ym:4467-4480 */
+  if (dot3(normal, incoming) >= 0 || dot3(normal, outgoing) <= 0) return V(0, 0, 0);
+  v3    reflected = reflect3(vneg(incoming), normal);
+  v3    halfway = norm3(vadd(reflected, outgoing));
+  float D = mf_distribution(roughness, normal, halfway), G = mf_shadowing(roughness, normal, halfway, outgoing, reflected);
+  return bcast(1.0f * D * G / (4 * dot3(normal, outgoing) * dot3(normal, reflected)) * (dot3(normal, reflected)));
+}
+static v3 eval_mf_refraction(float ior, float roughness, v3 normal, v3 outgoing, v3 incoming) { /* ym:4483-4514 */
+  int   entering = dot3(normal, outgoing) >= 0;
+  v3    up_normal = entering ? normal : vneg(normal);
+  float rel_ior = entering ? ior : (1 / ior);
+  if (dot3(normal, incoming) * dot3(normal, outgoing) >= 0) {
+    v3    halfway = norm3(vadd(incoming, outgoing));
+    float F = fresnel_dielectric(rel_ior, halfway, outgoing), D = mf_distribution(roughness, up_normal, halfway);
+    float G = mf_shadowing(roughness, up_normal, halfway, outgoing, incoming);
+    return bcast(1.0f * F * D * G / absr(4 * dot3(normal, outgoing) * dot3(normal, incoming)) * absr(dot3(normal, incoming)));
+  } else {
+    v3    halfway = vs(vneg(norm3(vadd(vs(incoming, rel_ior), outgoing))), entering ? 1.0f : -1.0f);
+    float F = fresnel_dielectric(rel_ior, halfway, outgoing), D = mf_distribution(roughness, up_normal, halfway);
+    float G = mf_shadowing(roughness, up_normal, halfway, outgoing, incoming);
+    float t = rel_ior * dot3(halfway, incoming) + dot3(halfway, outgoing); /* pow(t, 2): powf folded to t * t at -O1+ */
+    return bcast(1.0f * absr((dot3(outgoing, halfway) * dot3(incoming, halfway)) / (dot3(outgoing, normal) * dot3(incoming, normal))) *
+                 (1 - F) * D * G / (t * t) * absr(dot3(normal, incoming)));
+  }
+}
+static v3 sample_mf_reflection(float roughness, v3 normal, v3 outgoing, v2 rn) { /* ym:4530-4546 */
+  if (dot3(normal, outgoing) <= 0) return V(0, 0, 0);
+  return reflect3(outgoing, sample_mf(roughness, normal, rn));
+}
+static v3 sample_mf_transmission(float roughness, v3 normal, v3 outgoing, v2 rn) { /* ym:4549-4559 */
+  if (dot3(normal, outgoing) <= 0) return V(0, 0, 0);
+  v3 reflected = reflect3(outgoing, sample_mf(roughness, normal, rn));
+  return vneg(reflect3(reflected, normal));
+}
+static v3 sample_mf_refraction(float ior, float roughness, v3 normal, v3 outgoing, float rnl, v2 rn) { /* ym:4562-4573 */
+  int entering = dot3(normal, outgoing) >= 0;
+  v3  up_normal = entering ? normal : vneg(normal);
+  v3  halfway = sample_mf(roughness, up_normal, rn);
+  if (rnl < fresnel_dielectric(entering ? ior : (1 / ior), halfway, outgoing)) return reflect3(outgoing, halfway);
+  return refract3(outgoing, halfway, entering ? (1 / ior) : ior);
+}
+static float sample_mf_reflection_pdf(float roughness, v3 normal, v3 outgoing, v3 incoming) { /* ym:4590-4608 */
+  if (dot3(normal, incoming) <= 0 || dot3(normal, outgoing) <= 0) return 0;
+  v3 halfway = norm3(vadd(outgoing, incoming));
+  return sample_mf_pdf(roughness, normal, halfway) / (4 * absr(dot3(outgoing, halfway)));
+}
+static float sample_mf_transmission_pdf(float roughness, v3 normal, v3 outgoing, v3 incoming) { /* ym:4611-4620 */
+  if (dot3(normal, incoming) >= 0 || dot3(normal, outgoing) <= 0) return 0;
+  v3 reflected = reflect3(vneg(incoming), normal);
+  v3 halfway = norm3(vadd(reflected, outgoing));
+  return sample_mf_pdf(roughness, normal, halfway) / (4 * absr(dot3(outgoing, halfway)));
+}
+static float sample_mf_refraction_pdf(float ior, float roughness, v3 normal, v3 outgoing, v3 incoming) { /* ym:4623-4641 */
+  int   entering = dot3(normal, outgoing) >= 0;
+  v3    up_normal = entering ? normal : vneg(normal);
+  float rel_ior = entering ? ior : (1 / ior);
+  if (dot3(normal, incoming) * dot3(normal, outgoing) >= 0) {
+    v3 halfway = norm3(vadd(incoming, outgoing));
+    return fresnel_dielectric(rel_ior, halfway, outgoing) * sample_mf_pdf(roughness, up_normal, halfway) / (4 * absr(dot3(outgoing, halfway)));
+  } else {
+    v3    halfway = vs(vneg(norm3(vadd(vs(incoming, rel_ior), outgoing))), entering ? 1.0f : -1.0f);
+    float t = rel_ior * dot3(halfway, incoming) + dot3(halfway, outgoing);
+    return (1 - fresnel_dielectric(rel_ior, halfway, outgoing)) * sample_mf_pdf(roughness, up_normal, halfway) * absr(dot3(halfway, outgoing)) / (t * t);
+  }
+}
+static v3 eval_delta_refraction(float ior, v3 normal, v3 outgoing, v3 incoming) { /* ym:4664-4678 */
+  if (absr(ior - 1) < 1e-3f) return dot3(normal, incoming) * dot3(normal, outgoing) <= 0 ? V(1, 1, 1) : V(0, 0, 0);
+  int   entering = dot3(normal, outgoing) >= 0;
+  v3    up_normal = entering ? normal : vneg(normal);
+  float rel_ior = entering ? ior : (1 / ior);
+  if (dot3(normal, incoming) * dot3(normal, outgoing) >= 0) return bcast(1.0f * fresnel_dielectric(rel_ior, up_normal, outgoing));
+  return bcast(1.0f * (1 / (rel_ior * rel_ior)) * (1 - fresnel_dielectric(rel_ior, up_normal, outgoing)));
+}
+static v3 sample_delta_refraction(float ior, v3 normal, v3 outgoing, float rnl) { /* ym:4706-4717 */
+  if (absr(ior - 1) < 1e-3f) return vneg(outgoing);
+  int   entering = dot3(normal, outgoing) >= 0;
+  v3    up_normal = entering ? normal : vneg(normal);
+  float rel_ior = entering ? ior : (1 / ior);
+  if (rnl < fresnel_dielectric(rel_ior, up_normal, outgoing)) return reflect3(outgoing, up_normal);
+  return refract3(outgoing, up_normal, 1 / rel_ior);
+}
+static float sample_delta_refraction_pdf(float ior, v3 normal, v3 outgoing, v3 incoming) { /* ym:4741-4754 */
+  if (absr(ior - 1) < 1e-3f) return dot3(normal, incoming) * dot3(normal, outgoing) < 0 ? 1.0f : 0.0f;
+  int   entering = dot3(normal, outgoing) >= 0;
+  v3    up_normal = entering ? normal : vneg(normal);
+  float rel_ior = entering ? ior : (1 / ior);
+  if (dot3(normal, incoming) * dot3(normal, outgoing) >= 0) return fresnel_dielectric(rel_ior, up_normal, outgoing);
+  return (1 - fresnel_dielectric(rel_ior, up_normal, outgoing));
+}
+/* eval_brdf, pt:405-471, from the (already textured) material factors; thin = material.thin || !material.transmission */
+static sbrdf eval_sbrdf(v3 base, float specular, float metallic, float roughness, float ior, float transmission, int thin,
+    v3 normal, v3 outgoing) {
+  sbrdf b;
+  v3    weight = V(1, 1, 1);
+  b.metal = vs(weight, metallic);
+  weight  = vs(weight, 1 - metallic);
+  b.refraction = thin ? V(0, 0, 0) : vs(weight, transmission);
+  weight       = vs(weight, 1 - (thin ? 0.0f : transmission));
+  b.specular = vs(weight, specular);
+  weight     = vs(weight, 1 - specular * fresnel_dielectric(ior, outgoing, normal));
+  b.transmission = thin ? vmul(vs(weight, transmission), base) : V(0, 0, 0);
+  weight         = vs(weight, 1 - (thin ? transmission : 0.0f));
+  b.diffuse = vmul(weight, base);
+  b.meta = reflectivity_to_eta(base), b.metak = V(0, 0, 0);
+  b.roughness = roughness * roughness, b.ior = ior;
+  if (nonzero3(b.diffuse) || b.roughness) b.roughness = clampr(b.roughness, 0.03f * 0.03f, 1.0f);
+  if (!nonzero3(b.specular) && !nonzero3(b.metal) && !nonzero3(b.transmission) && !nonzero3(b.refraction)) b.roughness = 1;
+  b.diffuse_pdf = max3(b.diffuse);
+  b.specular_pdf = max3(vs(b.specular, fresnel_dielectric(b.ior, normal, outgoing)));
+  b.metal_pdf = max3(vmul(b.metal, fresnel_conductor(b.meta, b.metak, normal, outgoing)));
+  b.transmission_pdf = max3(b.transmission);
+  b.refraction_pdf = max3(b.refraction);
+  float pdf_sum = b.diffuse_pdf + b.specular_pdf + b.metal_pdf + b.transmission_pdf + b.refraction_pdf;
+  if (pdf_sum) {
+    b.diffuse_pdf /= pdf_sum, b.specular_pdf /= pdf_sum, b.metal_pdf /= pdf_sum;
+    b.transmission_pdf /= pdf_sum, b.refraction_pdf /= pdf_sum;
+  }
+  return b;
+}
+static v3 s_eval_brdfcos(const sbrdf* b, v3 normal, v3 outgoing, v3 incoming) { /* pt:1069-1103 */
+  if (!b->roughness) return V(0, 0, 0);
+  v3 r = V(0, 0, 0);
+  if (nonzero3(b->diffuse)) {
+    float ni = dot3(normal, incoming), no = dot3(normal, outgoing);
+    r = vadd(r, vmul(b->diffuse, (ni <= 0 || no <= 0) ? V(0, 0, 0) : vs(vds(V(1, 1, 1), PIF), ni)));
+  }
+  if (nonzero3(b->specular)) r = vadd(r, vmul(b->specular, eval_mf_reflection(b->ior, b->roughness, normal, outgoing, incoming)));
+  if (nonzero3(b->metal)) r = vadd(r, vmul(b->metal, eval_mf_reflection_metal(b->meta, b->metak, b->roughness, normal, outgoing, incoming)));
+  if (nonzero3(b->transmission)) r = vadd(r, vmul(b->transmission, eval_mf_transmission(b->roughness, normal, outgoing, incoming)));
+  if (nonzero3(b->refraction)) r = vadd(r, vmul(b->refraction, eval_mf_refraction(b->ior, b->roughness, normal, outgoing, incoming)));
+  return r;
+}
+static v3 s_eval_delta(const sbrdf* b, v3 normal, v3 outgoing, v3 incoming) { /* pt:1105-1129 */
+  if (b->roughness) return V(0, 0, 0);
+  v3    r = V(0, 0, 0);
+  float ni = dot3(normal, incoming), no = dot3(normal, outgoing);
+  if (nonzero3(b->specular) && !nonzero3(b->refraction))
+    r = vadd(r, vmul(b->specular, bcast((ni <= 0 || no <= 0) ? 0.0f : 1.0f * fresnel_dielectric(b->ior, normal, outgoing))));
+  if (nonzero3(b->metal)) r = vadd(r, vmul(b->metal, (ni <= 0 || no <= 0) ? V(0, 0, 0) : fresnel_conductor(b->meta, b->metak, normal, outgoing)));
+  if (nonzero3(b->transmission)) r = vadd(r, vmul(b->transmission, (ni >= 0 || no <= 0) ? V(0, 0, 0) : V(1, 1, 1)));
+  if (nonzero3(b->refraction)) r = vadd(r, vmul(b->refraction, eval_delta_refraction(b->ior, normal, outgoing, incoming)));
+  return r;
+}
+static v3 s_sample_brdfcos(const sbrdf* b, v3 normal, v3 outgoing, float rnl, v2 rn) { /* pt:1132-1176 */
+  if (!b->roughness) return V(0, 0, 0);
+  float cdf = 0.0f;
+  if (b->diffuse_pdf) {
+    cdf += b->diffuse_pdf;
+    if (rnl < cdf) { /* sample_diffuse_reflection -> sample_hemisphere_cos, ym:4515, :4873-4879 */
+      if (dot3(normal, outgoing) <= 0) return V(0, 0, 0);
+      float z = sqrtf(rn.y), r = sqrtf(1 - z * z), phi = 2 * PIF * rn.x;
+      fr3   basis = basis_fromz(normal);
+      return xf_direction(&basis, V(r * cosf(phi), r * sinf(phi), z));
+    }
+  }
+  if (b->specular_pdf && !b->refraction_pdf) {
+    cdf += b->specular_pdf;
+    if (rnl < cdf) return sample_mf_reflection(b->roughness, normal, outgoing, rn);
+  }
+  if (b->metal_pdf) {
+    cdf += b->metal_pdf;
+    if (rnl < cdf) return sample_mf_reflection(b->roughness, normal, outgoing, rn);
+  }
+  if (b->transmission_pdf) {
+    cdf += b->transmission_pdf;
+    if (rnl < cdf) return sample_mf_transmission(b->roughness, normal, outgoing, rn);
+  }
+  if (b->refraction_pdf) {
+    cdf += b->refraction_pdf;
+    if (rnl < cdf) return sample_mf_refraction(b->ior, b->roughness, normal, outgoing, rnl, rn);
+  }
+  return V(0, 0, 0);
+}
+static v3 s_sample_delta(const sbrdf* b, v3 normal, v3 outgoing, float rnl) { /* pt:1178-1215 */
+  if (b->roughness) return V(0, 0, 0);
+  float cdf = 0.0f;
+  cdf += b->diffuse_pdf;
+  if (b->specular_pdf && !b->refraction_pdf) {
+    cdf += b->specular_pdf;
+    if (rnl < cdf) return (dot3(normal, outgoing) <= 0) ? V(0, 0, 0) : reflect3(outgoing, normal);
+  }
+  if (b->metal_pdf) {
+    cdf += b->metal_pdf;
+    if (rnl < cdf) return (dot3(normal, outgoing) <= 0) ? V(0, 0, 0) : reflect3(outgoing, normal);
+  }
+  if (b->transmission_pdf) {
+    cdf += b->transmission_pdf;
+    if (rnl < cdf) return (dot3(normal, outgoing) <= 0) ? V(0, 0, 0) : vneg(outgoing);
+  }
+  if (b->refraction_pdf) {
+    cdf += b->refraction_pdf;
+    if (rnl < cdf) return sample_delta_refraction(b->ior, normal, outgoing, rnl);
+  }
+  return V(0, 0, 0);
+}
+static float s_sample_brdfcos_pdf(const sbrdf* b, v3 normal, v3 outgoing, v3 incoming) { /* pt:1218-1255 */
+  if (!b->roughness) return 0;
+  float pdf = 0.0f;
+  if (b->diffuse_pdf) {
+    float ni = dot3(normal, incoming), no = dot3(normal, outgoing);
+    pdf += b->diffuse_pdf * ((ni <= 0 || no <= 0) ? 0 : ni / PIF);
+  }
+  if (b->specular_pdf && !b->refraction_pdf) pdf += b->specular_pdf * sample_mf_reflection_pdf(b->roughness, normal, outgoing, incoming);
+  if (b->metal_pdf) pdf += b->metal_pdf * sample_mf_reflection_pdf(b->roughness, normal, outgoing, incoming);
+  if (b->transmission_pdf) pdf += b->transmission_pdf * sample_mf_transmission_pdf(b->roughness, normal, outgoing, incoming);
+  if (b->refraction_pdf) pdf += b->refraction_pdf * sample_mf_refraction_pdf(b->ior, b->roughness, normal, outgoing, incoming);
+  return pdf;
+}
+static float s_sample_delta_pdf(const sbrdf* b, v3 normal, v3 outgoing, v3 incoming) { /* pt:1257-1280 */
+  if (b->roughness) return 0;
+  float pdf = 0.0f;
+  float ni = dot3(normal, incoming), no = dot3(normal, outgoing);
+  if (b->specular_pdf && !b->refraction_pdf) pdf += b->specular_pdf * ((ni <= 0 || no <= 0) ? 0.0f : 1.0f);
+  if (b->metal_pdf) pdf += b->metal_pdf * ((ni <= 0 || no <= 0) ? 0.0f : 1.0f);
+  if (b->transmission_pdf) pdf += b->transmission_pdf * ((ni >= 0 || no <= 0) ? 0.0f : 1.0f);
+  if (b->refraction_pdf) pdf += b->refraction_pdf * sample_delta_refraction_pdf(b->ior, normal, outgoing, incoming);
+  return pdf;
+}
+/* volumes: ym:4757-4812, pt:1360-1378 */
+static float sample_transmittance(v3 density, float max_distance, float rl, float rd) {
+  int   channel = clampi((int)(rl * 3), 0, 2);
+  float dc = comp(density, channel);
+  float distance = (dc == 0) ? FLT_MAXF : -logf(1 - rd) / dc;
+  return fminr(distance, max_distance);
+}
+static v3 eval_transmittance(v3 density, float distance) {
+  v3 a = vs(vneg(density), distance);
+  return V(expf(a.x), expf(a.y), expf(a.z));
+}
+static float sample_transmittance_pdf(v3 density, float distance, float max_distance) {
+  if (distance < max_distance) {
+    v3 e = vmul(density, eval_transmittance(density, distance));
+    return (e.x + e.y + e.z) / 3;
+  }
+  v3 e = eval_transmittance(density, max_distance);
+  return (e.x + e.y + e.z) / 3;
+}
+static float eval_phasefunction(float anisotropy, v3 outgoing, v3 incoming) {
+  float cosine = -dot3(outgoing, incoming);
+  float denom = 1 + anisotropy * anisotropy - 2 * anisotropy * cosine;
+  return (1 - anisotropy * anisotropy) / (4 * PIF * denom * sqrtf(denom));
+}
+static v3 sample_phasefunction(float anisotropy, v3 outgoing, v2 rn) {
+  float cos_theta = 0.0f;
+  if (absr(anisotropy) < 1e-3f) {
+    cos_theta = 1 - 2 * rn.y;
+  } else {
+    float square = (1 - anisotropy * anisotropy) / (1 + anisotropy - 2 * anisotropy * rn.y);
+    cos_theta = (1 + anisotropy * anisotropy - square * square) / (2 * anisotropy);
+  }
+  float sin_theta = sqrtf(fmaxr(0.0f, 1 - cos_theta * cos_theta));
+  float phi = 2 * PIF * rn.x;
+  fr3   basis = basis_fromz(vneg(outgoing));
+  return xf_vector(&basis, V(sin_theta * cosf(phi), sin_theta * sinf(phi), cos_theta));
+}
+
 static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_params* params, float out[4]) {
   v3  radiance = V(0, 0, 0), weight = V(1, 1, 1);
   int hit = 0;
@@ -1053,6 +1458,9 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
   int max_bounces = params->bounces;
   if (shader == YH_SHADER_EYELIGHT) max_bounces = params->bounces > 4 ? params->bounces : 4; /* max(bounces, 4) */
   if (shader == YH_SHADER_NORMAL) max_bounces = 1;
+  vsdf_t vol; /* the volume stack never holds more than one entry, pt:1460-1467 */
+  int    in_vol = 0;
+  memset(&vol, 0, sizeof(vol));
   for (int bounce = 0; bounce < max_bounces; bounce++) {
     int   object = -1, element = -1;
     v2    uv = {0, 0};
@@ -1062,15 +1470,44 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
       if (shader == YH_SHADER_NORMAL) hit = 1; /* trace_normal returns alpha 1 on a miss too */
       break;
     }
+    v3 outgoing = vneg(ray.d);
+    /* transmittance through the current volume (trace_path only), pt:1403-1414 */
+    int scatter_event = 0;
+    if (shader == YH_SHADER_PATH && in_vol) {
+      float rd = rng_1f(rng), rl = rng_1f(rng); /* arguments evaluated right to left */
+      float distance = sample_transmittance(vol.density, dist, rl, rd);
+      weight = vmul(weight, vds(eval_transmittance(vol.density, distance), sample_transmittance_pdf(vol.density, distance, dist)));
+      scatter_event = distance < dist;
+      dist = distance;
+    }
+    if (scatter_event) { /* pt:1470-1497 */
+      v3 position = vadd(ray.o, vs(ray.d, dist));
+      hit = 1;
+      v3 incoming;
+      if (rng_1f(rng) < 0.5f) {
+        v2    rn = rng_2f(rng);
+        float rnl = rng_1f(rng);
+        (void)rnl;
+        incoming = nonzero3(vol.density) ? sample_phasefunction(vol.anisotropy, outgoing, rn) : V(0, 0, 0);
+      } else {
+        v2    ruv = rng_2f(rng);
+        float rel = rng_1f(rng), rl = rng_1f(rng);
+        incoming = sample_lights(sc, position, rl, rel, ruv);
+      }
+      v3    f = nonzero3(vol.density) ? vs(vmul(vol.scatter, vol.density), eval_phasefunction(vol.anisotropy, outgoing, incoming)) : V(0, 0, 0);
+      float spdf = nonzero3(vol.density) ? eval_phasefunction(vol.anisotropy, outgoing, incoming) : 0;
+      weight = vmul(weight, vds(f, 0.5f * spdf + 0.5f * sample_lights_pdf(sc, position, incoming)));
+      ray_t nr = {position, incoming, RAY_EPS, FLT_MAXF};
+      ray = nr;
+    } else {
     const obj_t*   ob = &sc->objs[object];
     const shape_t* sh = &sc->shapes[ob->shape];
     const mat_t*   mat = &sc->mats[ob->material];
     int   is_hair = sh->nlines != 0;
-    v3    outgoing = vneg(ray.d);
     v3    position = eval_position(sc, object, element, uv);
     v3    normal; /* eval_shading_normal, pt:350-369 */
     if (!is_hair) {
-      normal = eval_normal(sc, object, element, uv);
+      normal = mat->normal_tex >= 0 ? eval_normalmap(sc, object, element, uv, mat->normal_tex) : eval_normal(sc, object, element, uv);
       if (mat->thin) normal = dot3(normal, outgoing) >= 0 ? normal : vneg(normal);
     } else {
       normal = orthonorm(outgoing, eval_normal(sc, object, element, uv));
@@ -1080,15 +1517,25 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
       hit = 1;
       break;
     }
-    v3 emission = vmul(mat->emission, V(1, 1, 1)); /* no emission texture */
-    /* eval_brdf, pt:405-492, with specular = metallic = transmission = 0 */
-    v3    diffuse = vmul(vs(vs(vs(vs(V(1, 1, 1), 1 - 0.0f), 1 - 0.0f), 1 - 0.0f * 1.0f), 1 - 0.0f), vmul(mat->color, V(1, 1, 1)));
-    float opacity = mat->opacity * ((1.0f + 1.0f + 1.0f) / 3);
+    /* eval_emission pt:397-402 and the factors of eval_brdf pt:409-424 (a missing texture is {1,1,1}; the
+     * transmission factor comes from the slot the caller filled with the reference's choice, its emission texture) */
+    v2    texcoord = eval_texcoord(sc, object, element, uv);
+    v3    emission = vmul(mat->emission, eval_texture(sc, mat->emission_tex, texcoord));
+    v3    base = vmul(mat->color, eval_texture(sc, mat->color_tex, texcoord));
+    float specular = mat->specular * eval_texture(sc, mat->specular_tex, texcoord).x;
+    float metallic = mat->metallic * eval_texture(sc, mat->metallic_tex, texcoord).x;
+    float roughness = mat->roughness * eval_texture(sc, mat->roughness_tex, texcoord).x;
+    float transmission = mat->transmission * eval_texture(sc, mat->transmission_tex, texcoord).x;
+    v3    otex = eval_texture(sc, mat->opacity_tex, texcoord);
+    float opacity = mat->opacity * ((otex.x + otex.y + otex.z) / 3);
+    int   thin = mat->thin || !mat->transmission;
     if (opacity > 0.999f) opacity = 1;
-    float diffuse_pdf = max3(diffuse);
-    if (diffuse_pdf) diffuse_pdf /= diffuse_pdf + 0.0f + 0.0f + 0.0f + 0.0f;
+    sbrdf sb;
     hbrdf hb;
+    memset(&sb, 0, sizeof(sb));
     if (is_hair) hb = hair_brdf_make(&mat->hair, uv.y, normal, eval_normal(sc, object, element, uv));
+    else sb = eval_sbrdf(base, specular, metallic, roughness, mat->ior, transmission, thin, normal, outgoing);
+    int delta = !is_hair && !sb.roughness; /* is_delta, pt:495 */
     if (opacity < 1 && rng_1f(rng) >= opacity) { /* pt:1429-1433 */
       ray_t nr = {vadd(position, vs(ray.d, 1e-2f)), ray.d, RAY_EPS, FLT_MAXF};
       ray = nr;
@@ -1097,57 +1544,62 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
     }
     hit      = 1;
     radiance = vadd(radiance, vmul(weight, emission));
-    if (shader == YH_SHADER_EYELIGHT) { /* pt:1617-1622: light at the eye, then break (never delta here) */
-      v3 f;
-      if (is_hair) {
-        f = hair_eval(&hb, outgoing, outgoing);
-      } else {
-        float no = dot3(normal, outgoing);
-        f = V(0, 0, 0);
-        if (nonzero3(diffuse)) f = vadd(f, vmul(diffuse, (no <= 0) ? V(0, 0, 0) : vs(vds(V(1, 1, 1), PIF), no)));
-      }
-      radiance = vadd(radiance, vmul(vs(weight, PIF), f));
-      break;
-    }
-    /* MIS one-sample model, pt:1441-1451 (trace_naive always samples the BSDF, pt:1548-1551).
-     * GCC evaluates call arguments right to left: rand2f first. */
     v3 incoming;
-    if (shader == YH_SHADER_NAIVE || rng_1f(rng) < 0.5f) {
-      v2    rn = rng_2f(rng);
-      float rnl = rng_1f(rng);
-      if (is_hair) {
-        incoming = hair_sample(&hb, outgoing, rn);
+    if (shader == YH_SHADER_EYELIGHT) { /* pt:1617-1626: light at the eye; delta surfaces are followed */
+      v3 f = is_hair ? hair_eval(&hb, outgoing, outgoing) : s_eval_brdfcos(&sb, normal, outgoing, outgoing);
+      radiance = vadd(radiance, vmul(vs(weight, PIF), f));
+      if (!delta) break;
+      incoming = s_sample_delta(&sb, normal, outgoing, rng_1f(rng));
+      weight = vmul(weight, vds(s_eval_delta(&sb, normal, outgoing, incoming), s_sample_delta_pdf(&sb, normal, outgoing, incoming)));
+      if ((weight.x == 0 && weight.y == 0 && weight.z == 0) || !finite3(weight)) break;
+      ray_t nr = {position, incoming, RAY_EPS, FLT_MAXF};
+      ray = nr;
+      continue;
+    }
+    if (delta) { /* pt:1452-1456 */
+      incoming = s_sample_delta(&sb, normal, outgoing, rng_1f(rng));
+      weight = vmul(weight, vds(s_eval_delta(&sb, normal, outgoing, incoming), s_sample_delta_pdf(&sb, normal, outgoing, incoming)));
+    } else {
+      /* MIS one-sample model, pt:1441-1451 (trace_naive always samples the BSDF, pt:1548-1551).
+       * GCC evaluates call arguments right to left: rand2f first. */
+      if (shader == YH_SHADER_NAIVE || rng_1f(rng) < 0.5f) {
+        v2    rn = rng_2f(rng);
+        float rnl = rng_1f(rng);
+        incoming = is_hair ? hair_sample(&hb, outgoing, rn) : s_sample_brdfcos(&sb, normal, outgoing, rnl, rn);
       } else {
-        incoming = V(0, 0, 0);
-        if (diffuse_pdf && rnl < diffuse_pdf && !(dot3(normal, outgoing) <= 0)) { /* sample_hemisphere_cos, ym:4873-4879 */
-          float z = sqrtf(rn.y), r = sqrtf(1 - z * z), phi = 2 * PIF * rn.x;
-          fr3   basis = basis_fromz(normal);
-          incoming = xf_direction(&basis, V(r * cosf(phi), r * sinf(phi), z));
-        }
+        v2    ruv = rng_2f(rng);
+        float rel = rng_1f(rng), rl = rng_1f(rng);
+        incoming = sample_lights(sc, position, rl, rel, ruv);
       }
-    } else {
-      v2    ruv = rng_2f(rng);
-      float rel = rng_1f(rng), rl = rng_1f(rng);
-      incoming = sample_lights(sc, position, rl, rel, ruv);
+      v3    brdfcos;
+      float brdf_pdf;
+      if (is_hair) brdfcos = hair_eval(&hb, outgoing, incoming), brdf_pdf = hair_pdf(&hb, outgoing, incoming);
+      else brdfcos = s_eval_brdfcos(&sb, normal, outgoing, incoming), brdf_pdf = s_sample_brdfcos_pdf(&sb, normal, outgoing, incoming);
+      if (shader == YH_SHADER_NAIVE) {
+        weight = vmul(weight, vds(brdfcos, brdf_pdf));
+      } else {
+        float light_pdf = sample_lights_pdf(sc, position, incoming);
+        weight = vmul(weight, vds(brdfcos, 0.5f * brdf_pdf + 0.5f * light_pdf));
+      }
     }
-    v3    brdfcos;
-    float brdf_pdf;
-    if (is_hair) {
-      brdfcos = hair_eval(&hb, outgoing, incoming), brdf_pdf = hair_pdf(&hb, outgoing, incoming);
-    } else { /* diffuse lobe, ym:4427-4431, :4572-4576 */
-      float ni = dot3(normal, incoming), no = dot3(normal, outgoing);
-      brdfcos = V(0, 0, 0), brdf_pdf = 0;
-      if (nonzero3(diffuse)) brdfcos = vadd(brdfcos, vmul(diffuse, (ni <= 0 || no <= 0) ? V(0, 0, 0) : vs(vds(V(1, 1, 1), PIF), ni)));
-      if (diffuse_pdf) brdf_pdf += diffuse_pdf * ((ni <= 0 || no <= 0) ? 0 : ni / PIF);
-    }
-    if (shader == YH_SHADER_NAIVE) {
-      weight = vmul(weight, vds(brdfcos, brdf_pdf));
-    } else {
-      float light_pdf = sample_lights_pdf(sc, position, incoming);
-      weight = vmul(weight, vds(brdfcos, 0.5f * brdf_pdf + 0.5f * light_pdf));
+    /* update the volume stack, pt:1458-1467 (trace_path only) */
+    if (shader == YH_SHADER_PATH && !mat->thin && mat->transmission && dot3(normal, outgoing) * dot3(normal, incoming) < 0) {
+      if (!in_vol) { /* eval_vsdf, pt:505-526 */
+        v3 scattering = vmul(mat->scattering, eval_texture(sc, mat->scattering_tex, texcoord));
+        vol.density = V(0, 0, 0);
+        if (transmission && !thin) {
+          v3 l = V(logf(clampr(base.x, 0.0001f, 1.0f)), logf(clampr(base.y, 0.0001f, 1.0f)), logf(clampr(base.z, 0.0001f, 1.0f)));
+          vol.density = vds(vneg(l), mat->trdepth);
+        }
+        vol.scatter = scattering, vol.anisotropy = mat->scanisotropy;
+        in_vol = 1;
+      } else {
+        in_vol = 0;
+      }
     }
     ray_t nr = {position, incoming, RAY_EPS, FLT_MAXF};
     ray = nr;
+    }
     if ((weight.x == 0 && weight.y == 0 && weight.z == 0) || !finite3(weight)) break;
     if (bounce > 3) { /* russian roulette, pt:1503-1507 */
       float rr = fminr((float)0.99, max3(weight));

@@ -209,3 +209,60 @@ def test_port_other_shaders_bit_exact_vs_reference(shader, port, refo):
             assert np.array_equal(bits(a1), bits(a2)) and np.array_equal(s1, s2) and np.array_equal(g1, g2)
             for x in (sr, sp, rr, rp):
                 x.close()
+
+
+def textured_materials_scene():
+    """surface_lobes_scene with a float texture in every material slot the tracer reads, vertex texcoords on the
+    quads, normal maps, and a scattering sphere with textured albedo / density (same construction as
+    tests/test_trace_gpu.py::test_material_textures_bit_identical)."""
+    from yocto_hair_b200.scene import Object, Texture
+    scene, cam = synth.surface_lobes_scene(1_500, volumes=False)
+    vol, _ = synth.surface_lobes_scene(500, volumes=True)
+    rng = np.random.default_rng(5)
+
+    def tex(lo, hi, size=(12, 20)):
+        scene.textures.append(Texture(colorf=rng.uniform(lo, hi, (*size, 3)).astype(np.float32)))
+        return len(scene.textures) - 1
+
+    scene.shapes[2].texcoords = np.array([[-0.4, 0.1], [2.7, 0.1], [-0.4, 3.3], [2.7, 3.3]], np.float32)
+    m = dict(zip(["hair", "floor"] + list(synth.SURFACE_MATERIALS) + ["light"], scene.materials))
+    m["floor"].color_tex, m["floor"].normal_tex = tex(0.2, 1.0), tex(0.25, 0.75)
+    m["coated"].color_tex, m["coated"].roughness_tex, m["coated"].specular_tex = tex(0.1, 1.0), tex(0.3, 1.0), tex(0.0, 1.0)
+    m["gold"].metallic_tex, m["gold"].roughness_tex = tex(0.0, 1.0), tex(0.0, 1.0)
+    m["mirror"].normal_tex = tex(0.4, 0.6)
+    m["frosted"].emission = (0.3, 0.2, 0.1)
+    m["frosted"].emission_tex = m["frosted"].transmission_tex = tex(0.0, 1.0)
+    m["veil"].opacity_tex, m["veil"].color_tex = tex(0.0, 1.0), tex(0.2, 0.9)
+    m["light"].emission_tex = tex(0.5, 1.0)
+    m["hair"].opacity, m["hair"].opacity_tex = 0.9, tex(0.6, 1.0)
+    wax = vol.materials[2 + list(synth.VOLUME_MATERIALS).index("wax")]
+    wax.scattering_tex, wax.color_tex = tex(0.3, 1.0), tex(0.4, 1.0)
+    scene.materials.append(wax)
+    scene.objects.append(Object(shape=1, material=len(scene.materials) - 1, frame=(1, 0, 0, 0, 1, 0, 0, 0, 1, 0.4, 0.38, 1.6)))
+    return scene, cam
+
+
+MATERIAL_SCENES = {
+    "lobes": lambda: synth.surface_lobes_scene(1_500),
+    "refraction_volumes": lambda: synth.surface_lobes_scene(1_500, volumes=True),
+    "textures": textured_materials_scene,
+}
+
+
+@pytest.mark.parametrize("shader", [1, 0, 2], ids=["path", "naive", "eyelight"])
+@pytest.mark.parametrize("name", sorted(MATERIAL_SCENES))
+def test_port_material_model_bit_exact_vs_reference(name, shader, port, refo):
+    """SURVEY 8f N3 in the plain-C restatement: surface lobes and their delta forms, refraction, homogeneous
+    volumes, material textures and normal maps (yocto_pathtrace.cpp:294-531, :1069-1280, :1360-1497;
+    yocto_math.h:4215-4812) - renders bit-identical to the reference build, RNG state included."""
+    scene, cam = MATERIAL_SCENES[name]()
+    p = make_params(resolution=96, shader=shader)
+    rr, rp = refo.scene(scene), port.scene(scene)
+    sr, sp = rr.state(cam, p), rp.state(cam, p)
+    sr.trace_samples(3), sp.trace_samples(3)
+    (_, a1, s1, g1), (_, a2, s2, g2) = sr.download(), sp.download()
+    assert np.array_equal(s1, s2) and np.array_equal(g1, g2)
+    diff = np.nonzero((bits(a1) != bits(a2)).any(axis=-1))
+    assert diff[0].size == 0, "first differing pixels (y, x): %s" % list(zip(diff[0][:8], diff[1][:8]))
+    for x in (sr, sp, rr, rp):
+        x.close()

@@ -407,8 +407,6 @@ def test_surface_lobes_bit_identical(shader, ref):
     """specular / metal / thin-transmission lobes, their delta forms and opacity on the
     triangles around the hair (yh_surface.cuh) against the reference build: renders bit-identical, all
     three shaders that evaluate materials."""
-    if ref.kind != "reference":
-        pytest.skip("the plain-C port restates the hair path only; these lobes are checked against the reference build")
     scene, cam = synth.surface_lobes_scene()
     p = make_params(resolution=144, shader=shader)
     rs = ref.scene(scene)
@@ -432,8 +430,6 @@ def test_refraction_and_volumes_bit_identical(shader, ref):
     homogeneous volume trace_path opens behind them: transmittance sampling, Henyey-Greenstein scattering events
     with light MIS, the one-entry volume stack (yocto_pathtrace.cpp:1403-1414, :1458-1497).  The hair block stands
     among the spheres, so hair vertices are also reached from inside media."""
-    if ref.kind != "reference":
-        pytest.skip("checked against the reference build (the plain-C port restates the hair path only)")
     scene, cam = synth.surface_lobes_scene(volumes=True)
     cam2 = Camera.from_lookat((0.4, 0.38, 0.05), (2.0, 0.6, 0.0), (0, 1, 0), lens=0.03, aspect=1.5)  # starts INSIDE the wax sphere
     for c, res in ((cam, 144), (cam2, 72)):
@@ -459,8 +455,6 @@ def test_material_textures_bit_identical(shader, ref):
     metallic, roughness, opacity, scattering, and the transmission factor it reads from the EMISSION texture,
     yocto_pathtrace.cpp:397-424, :505-526), with vertex texcoords (tiled, negative) on the quads and the
     element-uv fallback on the spheres (eval_texcoord, :294-309)."""
-    if ref.kind != "reference":
-        pytest.skip("checked against the reference build (the plain-C port restates the hair path only)")
     from yocto_hair_b200.scene import Texture
     scene, cam = synth.surface_lobes_scene(volumes=False)
     vol, _ = synth.surface_lobes_scene(volumes=True)
