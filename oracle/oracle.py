@@ -209,5 +209,8 @@ class PortOracle(_Oracle):
 
 
 def best_oracle() -> _Oracle:
-    """The reference build when it travelled with the snapshot, else the port."""
+    """The reference build when it travelled with the snapshot, else the port (YH_ORACLE=port forces the port)."""
+    import os
+    if os.environ.get("YH_ORACLE") == "port":
+        return PortOracle()
     return RefOracle() if REF_LIB.exists() else PortOracle()
