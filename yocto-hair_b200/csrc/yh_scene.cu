@@ -230,6 +230,28 @@ __global__ void k_rotate(int n, const int* sorted_ref, const ref_bounds* refs, i
       if (g0 > best_gain) best_gain = g0, best_side = side, best_opt = 0, best_box = m0;
       if (g1 > best_gain) best_gain = g1, best_side = side, best_opt = 1, best_box = m1;
     }
+    // both children inner: the two other pairings of the four grandchildren {a, b | c, d} -> {a, c | b, d}, {a, d | b, c}
+    if (child[0] >= 0 && child[1] >= 0) {
+      int L = child[0], Rn = child[1];
+      int a = __ldcg(left + L), b = __ldcg(right + L), c = __ldcg(left + Rn), d = __ldcg(right + Rn);
+      ref_bounds ba = box(a), bb = box(b), bc = box(c), bd = box(d);
+      float      cost0 = box_area(box(L)) + box_area(box(Rn));
+      ref_bounds ac = box_merge(ba, bc), bdm = box_merge(bb, bd), ad = box_merge(ba, bd), bcm = box_merge(bb, bc);
+      float      g1 = cost0 - (box_area(ac) + box_area(bdm)), g2 = cost0 - (box_area(ad) + box_area(bcm));
+      if (g1 > best_gain && g1 >= g2) {
+        right[L] = c, left[Rn] = b;
+        set_parent(c, L), set_parent(b, Rn);
+        node_box[L] = ac, node_box[Rn] = bdm;
+        atomicAdd(rotations, 1);
+        best_side = -1;
+      } else if (g2 > best_gain) {
+        right[L] = d, right[Rn] = b;  // L' = {a, d}, R' = {c, b}
+        set_parent(d, L), set_parent(b, Rn);
+        node_box[L] = ad, node_box[Rn] = bcm;
+        atomicAdd(rotations, 1);
+        best_side = -1;
+      }
+    }
     if (best_side >= 0) {
       int A = child[best_side], B = child[best_side ^ 1];
       int b0 = __ldcg(left + B), b1 = __ldcg(right + B);
@@ -738,7 +760,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   }
   k_refit<<<G(R), B>>>(R, ids_out.ptr, refs.ptr, left.ptr, right.ptr, parent_inner.ptr, parent_leaf.ptr, flags.ptr, node_box.ptr);
   YH_CUDA(cudaGetLastError());
-  // quality passes over the radix tree: 3 rounds of rotations (0.3 ms each at a million segments) take 2.8 % off
+  // quality passes over the radix tree: 3 rounds of k_rotate (0.3 ms each at a million segments) take 4.6 % off
   // the node visits per ray on C3 (YH_ROTATE_PASSES overrides the count; each round can deepen a path by one level,
   // which the traversal stack - 96 entries against a radix-tree depth of at most 91 - has room for)
   if (quality == 0) {
