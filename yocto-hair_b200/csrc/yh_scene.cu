@@ -268,6 +268,15 @@ __global__ void k_rotate(int n, const int* sorted_ref, const ref_bounds* refs, i
   }
 }
 
+// Depth of the deepest leaf (inner nodes above it): the traversal stack holds one entry per level.
+__global__ void k_max_depth(int n, const int* parent_inner, const int* parent_leaf, int* max_depth) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int depth = 0;
+  for (int node = parent_leaf[j]; node >= 0; node = parent_inner[node]) depth++;
+  atomicMax(max_depth, depth);
+}
+
 // Quantises one box onto the shape's 16-bit grid, outwards, after padding it by `pad` grid steps
 // per axis (fold_pad_steps(): the traversal's plane decode moves all planes of an axis together
 // by up to about half a step, yh_traverse.cuh slab_consts).
@@ -768,6 +777,9 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
     if (const char* e = getenv("YH_ROTATE_PASSES")) passes = std::min(4, std::max(0, atoi(e)));
     dev_buffer<int> rotations;
     YH_CUDA(rotations.alloc(1));
+    // a rotation moves one subtree a level down; k_max_depth checks the result against the traversal stack and,
+    // should an input ever drive a path past the limit, the build falls back to the plain radix tree
+    const int kDepthLimit = 92;  // kStackShared + kStackLocal = 96 entries (yh_traverse.cuh)
     for (int pass = 0; pass < passes; pass++) {
       YH_CUDA(cudaMemset(flags.ptr, 0, flags.bytes()));
       YH_CUDA(cudaMemset(rotations.ptr, 0, 4));
@@ -778,6 +790,19 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
         int nrot = 0;
         YH_CUDA(cudaMemcpy(&nrot, rotations.ptr, 4, cudaMemcpyDeviceToHost));
         fprintf(stderr, "  bvh rotation pass %d: %d rotations\n", pass, nrot);
+      }
+    }
+    if (passes > 0) {
+      int depth = 0;
+      YH_CUDA(cudaMemset(rotations.ptr, 0, 4));
+      k_max_depth<<<G(R), B>>>(R, parent_inner.ptr, parent_leaf.ptr, rotations.ptr);
+      YH_CUDA(cudaMemcpy(&depth, rotations.ptr, 4, cudaMemcpyDeviceToHost));
+      if (timing) fprintf(stderr, "  bvh depth after the rotations: %d\n", depth);
+      if (depth > kDepthLimit) {  // rebuild the untouched radix tree
+        YH_CUDA(cudaMemset(flags.ptr, 0, flags.bytes()));
+        k_hierarchy<<<G(ni), B>>>(keys_out.ptr, R, left.ptr, right.ptr, first.ptr, last.ptr, parent_inner.ptr, parent_leaf.ptr);
+        k_refit<<<G(R), B>>>(R, ids_out.ptr, refs.ptr, left.ptr, right.ptr, parent_inner.ptr, parent_leaf.ptr, flags.ptr, node_box.ptr);
+        YH_CUDA(cudaGetLastError());
       }
     }
   }
