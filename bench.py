@@ -362,7 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-step", type=int, default=16, help="samples per pixel per step (CUDA arm)")
+    ap.add_argument("--spp-step", type=int, default=64, help="samples per pixel per step (CUDA arm): one yh_trace_samples call per rank")
     ap.add_argument("--ref-spp-step", type=int, default=2, help="samples per pixel per step (reference arm)")
     ap.add_argument("--max-split", type=int, default=0)
     ap.add_argument("--shard", default="auto", choices=["auto", "tiles", "samples"],
