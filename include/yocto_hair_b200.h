@@ -236,7 +236,11 @@ yh_status yh_shard_pixels(int width, int height, int rank, int world,
  * camera, params), yocto_pathtrace.cpp:1992-2026: every owned pixel gains
  * exactly `num_samples` samples, drawn in the reference's per-pixel order.
  * `stop` may be null; it is polled between wavefront iterations
- * (reference: std::atomic<bool>* stop, :2009-2026).                         */
+ * (reference: std::atomic<bool>* stop, :2009-2026).  Once it reads non-zero no
+ * pixel starts another sample; the samples already in flight are finished, so
+ * every pixel still holds WHOLE samples of its stream (per-pixel counts may then
+ * differ by the samples not started: read them with yh_state_download) and the
+ * state can be traced further.  yh_trace_stats::samples reports what was traced. */
 yh_status yh_trace_samples(yh_state* state, int num_samples,
     const volatile int* stop);
 
@@ -271,6 +275,50 @@ yh_status yh_state_buffers_dev(yh_state* state, float** accum_dev,
     int** samples_dev);
 /* Dump / restore of the per-pixel RNG (2 x uint64 per pixel: state, inc).   */
 yh_status yh_state_download_rng(const yh_state* state, uint64_t* rng);
+
+/* Several GPUs of one node in ONE process ---------------------------------
+ * Replaces, across the GPUs of a box, what parallel_for does across host
+ * threads for the reference (yocto_pathtrace.cpp:1954-1989): the scene is
+ * replicated in every GPU's HBM, each GPU renders its shard with its own state,
+ * and yh_group_download sums the fp32 accumulation / count buffers on the first
+ * GPU and resolves the image in ONE kernel that loads the peers' buffers over
+ * NVLink (peer access; copies without it), or with ncclReduce (YH_REDUCE_NCCL:
+ * libnccl.so.2 is loaded on demand, communicators from ncclCommInitAll).
+ *   yh_group_create      = yh_scene_create + yh_scene_init_bvh + yh_scene_init_lights
+ *                          on every device (devices == NULL: 0 .. num_devices - 1; a
+ *                          device listed k times carries k ranks); the host part of the
+ *                          build runs once and is shared
+ *   yh_group_init_state  = init_state (:1931-1946) on every device + the shard:
+ *                          YH_SHARD_TILES   yh_state_set_shard: image tiles, the reference's
+ *                                           RNG streams; the summed image is bit-identical
+ *                                           to one GPU and to the reference
+ *                          YH_SHARD_SAMPLES yh_state_set_sample_shard: every GPU renders all
+ *                                           pixels for its sample indices (counter mode)
+ *   yh_group_trace_samples  `num_samples` more samples per pixel over the whole group
+ *                          (a multiple of the device count for YH_SHARD_SAMPLES)
+ *   yh_group_download    totals over the group: render / accum / samples as yh_state_download
+ * The calling thread's current device is preserved.                          */
+typedef struct yh_group yh_group;
+enum { YH_SHARD_TILES = 0, YH_SHARD_SAMPLES = 1 };
+enum { YH_REDUCE_PEER = 0, YH_REDUCE_NCCL = 1 };
+yh_status yh_group_create(const yh_scene_desc* desc, const yh_bvh_params* bvh,
+    const int* devices, int num_devices, yh_group** group);
+void      yh_group_destroy(yh_group* group);
+yh_status yh_group_num_devices(const yh_group* group, int* num_devices);
+/* The replica of rank `rank` and the device it lives on (make it current with
+ * yh_set_device before handing the scene to yh_intersect_batch).             */
+yh_status yh_group_scene(const yh_group* group, int rank, const yh_scene** scene, int* device);
+yh_status yh_group_init_state(yh_group* group, const yh_camera_desc* camera,
+    const yh_trace_params* params, int shard);
+yh_status yh_group_set_reduce(yh_group* group, int mode);
+yh_status yh_group_size(const yh_group* group, int* width, int* height);
+yh_status yh_group_trace_samples(yh_group* group, int num_samples,
+    const volatile int* stop);
+/* Summed counters of the last yh_group_trace_samples (device_ms = the slowest
+ * device) and the CUDA-event time of the last reduce + resolve.              */
+yh_status yh_group_stats(const yh_group* group, yh_trace_stats* stats, float* reduce_ms);
+yh_status yh_group_download(yh_group* group, float* render, float* accum,
+    int* samples);
 
 /* Hair BSDF, batched (test + measurement entry points) -------------------- */
 

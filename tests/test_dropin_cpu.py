@@ -1,12 +1,12 @@
 """Drop-in plumbing on CPU: the harness writes a synthetic hair scene in the
 reference's own on-disk formats (scene JSON + binary PLY polylines), the drop-in
-command line host/_build/yscenetrace_b200 loads it through the reference's
-unmodified yocto_sceneio and renders it with `--backend cpu` (the reference's
-own functions).  The image must equal, bit for bit, the render of the same
+A/B test tool host/_build/yscenetrace_ab (the drop-in command line compiled with
+-DYH_AB_TOOL) loads it through the reference's unmodified yocto_sceneio and renders
+it with `--backend cpu` (the reference's own functions).  The image must equal, bit for bit, the render of the same
 scene handed to the reference IN MEMORY — which pins the file writers, the
 io -> ptr scene conversion of the app and the flattened C-ABI description to
-each other.  (`--backend cuda` is compared with `--backend cpu` in
-tests/test_dropin_gpu.py.)"""
+each other.  (The product binary yscenetrace_b200 is compared with it in
+tests/test_dropin_gpu.py; it has no CPU backend, which is tested here too.)"""
 import subprocess
 from pathlib import Path
 
@@ -19,6 +19,7 @@ from yocto_hair_b200.scene import make_params
 
 ROOT = Path(__file__).resolve().parent.parent
 APP = ROOT / "yocto-hair_b200" / "host" / "_build" / "yscenetrace_b200"
+AB = ROOT / "yocto-hair_b200" / "host" / "_build" / "yscenetrace_ab"
 
 
 def need_app():
@@ -38,7 +39,7 @@ def test_files_roundtrip_through_the_reference_loader(name, make, tmp_path):
     scene, cam = make()
     js = scenefiles.write_scene(tmp_path, name, scene, cam)
     out = tmp_path / "cpu.pfm"
-    run = subprocess.run([str(APP), "--backend", "cpu", "-s", "2", "-r", "72", "-o", str(out), str(js)],
+    run = subprocess.run([str(AB), "--backend", "cpu", "-s", "2", "-r", "72", "-o", str(out), str(js)],
                          capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
     img = scenefiles.read_pfm(out)
@@ -57,10 +58,22 @@ def test_app_rejects_out_of_scope_scenes_loudly(tmp_path):
     scene, cam = synth.curly_hair_scene(500, sky=False)
     scene.materials[0].specular = 0.5
     js = scenefiles.write_scene(tmp_path, "spec", scene, cam)
-    run = subprocess.run([str(APP), "--backend", "cuda", "-s", "1", "-r", "32", "-o", str(tmp_path / "x.pfm"), str(js)],
+    run = subprocess.run([str(APP), "-s", "1", "-r", "32", "-o", str(tmp_path / "x.pfm"), str(js)],
                          capture_output=True, text=True, timeout=600)
     assert run.returncode != 0  # no device here -> YH_ERR_NO_DEVICE; on a GPU box -> YH_ERR_UNSUPPORTED; never a silent CPU render
     assert not (tmp_path / "x.pfm").exists()
+
+
+def test_product_binary_has_no_cpu_backend(tmp_path):
+    """north_star: no CPU fallback.  The product command line does not know `--backend`; only the A/B test tool does."""
+    need_app()
+    scene, cam = synth.curly_hair_scene(500, sky=False)
+    js = scenefiles.write_scene(tmp_path, "nocpu", scene, cam)
+    run = subprocess.run([str(APP), "--backend", "cpu", "-s", "1", "-r", "32", "-o", str(tmp_path / "x.pfm"), str(js)],
+                         capture_output=True, text=True, timeout=600)
+    assert run.returncode != 0 and not (tmp_path / "x.pfm").exists()
+    syms = subprocess.run(["nm", "-C", str(APP)], capture_output=True, text=True).stdout
+    assert "reference_backend" not in syms
 
 
 # ---- scene files as first-class inputs (SURVEY 8f N2): host/yh_sceneio (bulk PLY reader + restated

@@ -1,7 +1,8 @@
 """The drop-in command line on a B200: host/_build/yscenetrace_b200 (reference CLI +
-reference JSON/PLY/HDR loaders + the C++ host shim over the C ABI) renders a scene
-with `--backend cuda` and with `--backend cpu` (the reference's own functions);
-the saved .pfm images must be bit-identical."""
+reference JSON/PLY/HDR loaders + the C++ host shim over the C ABI; CUDA only, no CPU
+path) renders a scene, and the TEST tool host/_build/yscenetrace_ab (same source with
+-DYH_AB_TOOL) renders it with `--backend cpu` (the reference's own functions); the
+saved .pfm images must be bit-identical."""
 import subprocess
 from pathlib import Path
 
@@ -13,10 +14,18 @@ from yocto_hair_b200 import scenefiles, synth
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 APP = ROOT / "yocto-hair_b200" / "host" / "_build" / "yscenetrace_b200"
+AB = ROOT / "yocto-hair_b200" / "host" / "_build" / "yscenetrace_ab"
 
 
 def run_app(*args):
-    run = subprocess.run([str(APP), *map(str, args)], capture_output=True, text=True, timeout=900)
+    """`--backend cuda ...` runs the product binary (which has no such flag: it is CUDA only),
+    `--backend cpu ...` the A/B test tool."""
+    args = [str(a) for a in args]
+    exe = APP
+    if args[:1] == ["--backend"]:
+        exe = AB if args[1] == "cpu" else APP
+        args = args[2:] if args[1] == "cuda" else args
+    run = subprocess.run([str(exe), *args], capture_output=True, text=True, timeout=900)
     assert run.returncode == 0, run.stdout[-2000:] + run.stderr[-2000:]
     return run.stdout
 
@@ -142,3 +151,25 @@ def test_interactive_session_headless(tmp_path):
         a, b = scenefiles.read_pfm(tmp_path / "cuda" / name), scenefiles.read_pfm(tmp_path / "cpu" / name)
         assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
     assert scenefiles.read_pfm(tmp_path / "cuda" / "preview.pfm").shape[1] == 128 // 8  # params.pratio = 8
+
+
+def test_app_on_two_gpus_is_bit_identical(tmp_path):
+    """`--gpus 2`: one process, two replicas, tile shards summed on the first GPU over NVLink (yh_group_*) - the image
+    equals the one-GPU image bit for bit; `--shard samples` renders the same scene in counter mode."""
+    import ctypes as C
+    from yocto_hair_b200 import _capi as capi
+    if not APP.exists():
+        pytest.skip("host/_build/yscenetrace_b200 not built")
+    have = C.c_int()
+    capi.check(capi.load().yh_device_count(C.byref(have)))
+    if have.value < 2:
+        pytest.skip("needs two GPUs")
+    scene, cam = synth.curly_hair_scene(30_000)
+    js = scenefiles.write_scene(tmp_path, "two", scene, cam)
+    run_app("-s", 4, "-r", 160, "-o", tmp_path / "one.pfm", js)
+    run_app("--gpus", 2, "-s", 4, "-r", 160, "-o", tmp_path / "two.pfm", js)
+    a, b = scenefiles.read_pfm(tmp_path / "one.pfm"), scenefiles.read_pfm(tmp_path / "two.pfm")
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    run_app("--gpus", 2, "--shard", "samples", "-s", 4, "-r", 160, "-o", tmp_path / "cnt.pfm", js)
+    c = scenefiles.read_pfm(tmp_path / "cnt.pfm")
+    assert c.shape == a.shape and abs(float(c.mean()) / float(a.mean()) - 1) < 0.1

@@ -856,9 +856,9 @@ yh_status yh_scene::sync_ties() const {
   if (!ties_pending) return YH_OK;
   for (auto s : shapes) {
     if (!s->tie_future.valid()) continue;
-    host_shape::tie_tables t = s->tie_future.get();
-    YH_CUDA(s->d_ref_pos.upload(t.ref_pos.data(), t.ref_pos.size()));
-    YH_CUDA(s->d_tie_nodes.upload(t.tie_nodes.data(), t.tie_nodes.size()));
+    std::shared_ptr<const host_shape::tie_tables> t = s->tie_future.get();
+    YH_CUDA(s->d_ref_pos.upload(t->ref_pos.data(), t->ref_pos.size()));
+    YH_CUDA(s->d_tie_nodes.upload(t->tie_nodes.data(), t->tie_nodes.size()));
   }
   ties_pending = false;
   return upload_tables(const_cast<yh_scene*>(this));  // the shape table carries the new pointers
@@ -899,11 +899,10 @@ static yh_status upload_tables(yh_scene* sc) {
   return YH_OK;
 }
 
-extern "C" {
-
-yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
+yh_status yh::scene_create(const yh_scene_desc* d, const yh_scene* ties_from, yh_scene** out) {
   YH_REQUIRE_DEVICE();
   if (!d || !out) return fail(YH_ERR_INVALID, "yh_scene_create: null argument");
+  if (ties_from && (int)ties_from->shapes.size() != d->num_shapes) return fail(YH_ERR_INVALID, "yh_scene_create: replica of a different scene");
   *out = nullptr;
   // ---- validate: anything outside the hot-path scope fails loudly ----
   for (int i = 0; i < d->num_materials; i++) {
@@ -965,13 +964,19 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
             hs->is_lines() ? hs->lines.size() : hs->triangles.size()) != cudaSuccess)
       return bail(fail(YH_ERR_CUDA, "shape %d: device upload failed: %s", i, cudaGetErrorString(cudaGetLastError())));
   }
-  for (auto hs : sc->shapes)
-    if (hs->num_elems() > 0)
-      hs->tie_future = std::async(std::launch::async, [hs]() {
-        host_shape::tie_tables t;
-        reference_tree_order(*hs, t.ref_pos, t.tie_nodes);
-        return t;
-      });
+  for (size_t i = 0; i < sc->shapes.size(); i++) {
+    auto hs = sc->shapes[i];
+    if (hs->num_elems() == 0) continue;
+    if (ties_from) {
+      hs->tie_future = ties_from->shapes[i]->tie_future;
+      continue;
+    }
+    hs->tie_future = std::async(std::launch::async, [hs]() -> std::shared_ptr<const host_shape::tie_tables> {
+      auto t = std::make_shared<host_shape::tie_tables>();
+      reference_tree_order(*hs, t->ref_pos, t->tie_nodes);
+      return t;
+    }).share();
+  }
   sc->ties_pending = true;
   for (int i = 0; i < d->num_textures; i++) {
     auto& t = d->textures[i];
@@ -1020,6 +1025,10 @@ yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
   return YH_OK;
 }
 
+extern "C" {
+
+yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) { return yh::scene_create(d, nullptr, out); }
+
 void yh_scene_destroy(yh_scene* scene) { delete scene; }
 
 yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
@@ -1042,6 +1051,10 @@ yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
     o.bbox = s->num_refs ? transform_bbox_padded(o.frame, s->root_bbox)
                          : bbox3f{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   }
+  sc->world_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+  for (auto& o : sc->objects)
+    if (o.bbox.min.x <= o.bbox.max.x) sc->world_bbox = {min3(sc->world_bbox.min, o.bbox.min), max3(sc->world_bbox.max, o.bbox.max)};
+  if (!(sc->world_bbox.min.x <= sc->world_bbox.max.x)) sc->world_bbox = {{0, 0, 0}, {0, 0, 0}};
   sc->bvh_built = true;
   return upload_tables(sc);
 }

@@ -144,7 +144,8 @@ struct host_shape {
     std::vector<int>  ref_pos;
     std::vector<int4> tie_nodes;
   };
-  std::future<tie_tables> tie_future;
+  // shared: the replicas of one scene on several devices (yh_group) compute the tables once
+  std::shared_future<std::shared_ptr<const tie_tables>> tie_future;
   ~host_shape() {
     if (tie_future.valid()) tie_future.wait();
   }
@@ -172,6 +173,7 @@ struct yh_scene {
   bool bvh_built = false, lights_built = false;
   bool has_volumes = false;  // some material is refractive (!thin && transmission): paths carry a volume state
   int  device = 0;
+  yh::bbox3f   world_bbox{{0, 0, 0}, {0, 0, 0}};  // union of the objects' padded bounds (yh_scene_init_bvh)
   yh_bvh_stats stats{};
   yh::dev_scene view() const;
   // joins the host threads that compute the reference leaf order and uploads their tables (once); every entry
@@ -181,3 +183,9 @@ struct yh_scene {
   mutable bool       ties_pending = false;
   ~yh_scene();
 };
+
+namespace yh {
+// yh_scene_create; with `ties_from` (a scene created from the SAME description, on any device) the reference leaf
+// order is not computed again but shared with it
+yh_status scene_create(const yh_scene_desc* desc, const yh_scene* ties_from, yh_scene** out);
+}

@@ -213,13 +213,14 @@ struct wavefront_io {  // by value: references to kernel parameters would force 
 #ifndef YH_INTERSECT_BLOCKS
 #define YH_INTERSECT_BLOCKS 7
 #endif
-__global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur) {
+__global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur,
+    const int* active) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
   int            n = q.count[cur];
   unsigned long long nv = 0, pt = 0;
   __shared__ int smem_park[kParkSlots * kTraceBlock];
   __shared__ int smem_cold[kColdWords * kTraceBlock];
-  wavefront_io   io{sc, ps, q, q.active[cur]};
+  wavefront_io   io{sc, ps, q, active};
   trace_persistent(sc, io, n, q.count + 5, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x, false,
       &nv, &pt);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.stats + 0, (unsigned long long)n);
@@ -500,6 +501,19 @@ __global__ void __launch_bounds__(kTraceBlock, YH_SHADE_BLOCKS) k_shade(dev_scen
   if (light_rays) atomicAdd(q.stats + 1, (unsigned long long)light_rays);
 }
 
+// stop request: no slot starts another sample; the samples in flight finish, so every pixel still holds whole samples
+// of its stream.  cancelled += the samples that will not be traced.
+__global__ void k_cancel_remaining(path_state ps, int num_slots, unsigned long long* cancelled) {
+  int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  int left = 0;
+  if (slot < num_slots) {
+    left = ld_stream(&ps.remaining[slot]);
+    if (left > 0) st_stream(&ps.remaining[slot], 0);
+  }
+  for (int d = 16; d > 0; d >>= 1) left += __shfl_down_sync(0xffffffffu, left, d);
+  if ((threadIdx.x & 31) == 0 && left > 0) atomicAdd(cancelled, (unsigned long long)left);
+}
+
 __global__ void k_reset_counts(int* count, int next) {
   count[next] = 0;
   count[2] = count[3] = count[4] = count[5] = 0;
@@ -657,7 +671,13 @@ struct yh_state {
         accum.ptr, samples.ptr, vol_density.ptr ? vol_density.ptr + first : nullptr,
         vol_scatter.ptr ? vol_scatter.ptr + first : nullptr, hit_dist.ptr ? hit_dist.ptr + first : nullptr};
   }
+  void drain() {  // nothing of this state is in flight afterwards
+    for (auto g : groups)
+      if (g->stream) cudaStreamSynchronize(g->stream);
+    if (stream) cudaStreamSynchronize(stream);
+  }
   void clear_groups() {
+    drain();
     for (auto g : groups) delete g;
     groups.clear();
   }
@@ -740,6 +760,7 @@ static yh_status assign_slots(yh_state* st) {
     YH_CUDA(grp->q_hair.alloc(m));
     YH_CUDA(grp->q_count.alloc(8));
     YH_CUDA(grp->stats.alloc(8));
+
     YH_CUDA(cudaStreamCreateWithFlags(&grp->stream, cudaStreamNonBlocking));
     YH_CUDA(cudaEventCreateWithFlags(&grp->ev_done, cudaEventDisableTiming));
     grp->host_counts = pinned_acquire();
@@ -766,8 +787,10 @@ yh_status yh_state_create(const yh_scene* scene, const yh_camera_desc* camera, c
     return fail(YH_ERR_INVALID, "shader %d: sampler unknown", params->shader);
   if (!scene->bvh_built || !scene->lights_built)
     return fail(YH_ERR_STATE, "yh_state_create: call yh_scene_init_bvh and yh_scene_init_lights first");
-  if (scene->lights.empty())
-    return fail(YH_ERR_INVALID, "scene has no lights (the reference's sample_lights is undefined then)");
+  // only trace_path reads the lights (sample_lights / sample_lights_pdf, :1441-1451); the other shaders render
+  // emitter-less scenes as the reference does
+  if (scene->lights.empty() && params->shader == YH_SHADER_PATH)
+    return fail(YH_ERR_INVALID, "scene has no lights (the reference's sample_lights is undefined then); use the eyelight, naive or normal shader");
   if (params->resolution <= 0 || params->bounces < 0) return fail(YH_ERR_INVALID, "bad trace params");
   auto st    = new yh_state{};
   st->scene  = scene;
@@ -852,8 +875,17 @@ yh_status yh_state_set_profiling(yh_state* st, int enabled) {
   return YH_OK;
 }
 
+static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatile int* stop);
 yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* stop) {
   YH_REQUIRE_DEVICE();
+  yh_status status = trace_samples_impl(st, num_samples, stop);
+  // An error return leaves kernels and copies in flight on the groups' (non-blocking) streams; buffers are handed
+  // back to the pool through the legacy stream, which does not order against them.  Drain before the caller can
+  // destroy or re-shard the state.
+  if (status != YH_OK && st) st->drain();
+  return status;
+}
+static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatile int* stop) {
   if (!st || num_samples < 0) return fail(YH_ERR_INVALID, "yh_trace_samples: bad argument");
   st->last = yh_trace_stats{};
   if (num_samples == 0 || st->num_slots == 0) return YH_OK;
@@ -913,7 +945,7 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
       int          next = g->cur ^ 1;
       k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
       if (prof) ev(s);
-      k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur);
+      k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur]);
       if (prof) ev(s);
       k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
       switch (tc.shader) {
@@ -954,14 +986,18 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
         if (g->host_counts[g->cur] == 0) g->done = true;
       }
     }
-    if (stop && *stop) {
+    if (stop && *stop && !stopped) {  // finish the samples in flight, start no new ones
       stopped = true;
-      break;
+      for (auto g : st->groups)
+        if (!g->done && g->num_slots > 0) {
+          k_cancel_remaining<<<(g->num_slots + 255) / 256, 256, 0, stream_of(g)>>>(st->ps(g->first_slot), g->num_slots, g->stats.ptr + 5);
+          launches++;
+        }
+      min_iters = rounds;  // poll the counts from now on
     }
     if (rounds > (int64_t)num_samples * (st->params.bounces + 2) * 64 + 1024)
       return fail(YH_ERR_STATE, "yh_trace_samples: wavefront did not drain after %lld rounds", (long long)rounds);
   }
-  (void)stopped;
   // end: the first group's stream waits for the others, then ev_end
   for (auto g : st->groups) {
     cudaStream_t s = stream_of(g);
@@ -981,7 +1017,7 @@ yh_status yh_trace_samples(yh_state* st, int num_samples, const volatile int* st
   }
   float ms = 0;
   YH_CUDA(cudaEventElapsedTime(&ms, st->ev_begin, st->ev_end));
-  st->last.samples    = (int64_t)st->num_slots * num_samples;
+  st->last.samples    = (int64_t)st->num_slots * num_samples - (int64_t)tot[5];  // less the samples a stop request cancelled
   st->last.rays       = (int64_t)tot[0];
   st->last.light_rays = (int64_t)tot[1];
   st->last.iterations = iterations;

@@ -14,13 +14,19 @@ namespace yocto::pathtrace_b200 {
 
 namespace {
 
+// device copies of one ptr::scene: a scene on one device, or a group of replicas (device_options::devices)
+struct scene_record {
+  yh_scene* scene = nullptr;
+  yh_group* group = nullptr;
+};
 struct state_record {
-  yh_state*          handle = nullptr;
+  yh_state*          handle = nullptr;  // one device ...
+  yh_group*          group  = nullptr;  // ... or the group the states live in
   const ptr::scene*  scene  = nullptr;
   ptr::camera        camera{};
 };
 std::mutex                                            table_mutex;
-std::unordered_map<const ptr::scene*, yh_scene*>      scene_table;
+std::unordered_map<const ptr::scene*, scene_record>   scene_table;
 std::unordered_map<const ptr::state*, state_record>   state_table;
 device_options                                        options{};
 
@@ -31,11 +37,21 @@ void check(yh_status status, const char* what) {
 }
 void put_frame(float* out, const math::frame3f& f) { memcpy(out, &f, 48); }
 
-yh_scene* find_scene(const ptr::scene* scene) {
+scene_record find_scene_record(const ptr::scene* scene) {
   std::lock_guard<std::mutex> lock(table_mutex);
   auto it = scene_table.find(scene);
   if (it == scene_table.end()) throw std::runtime_error("yocto_pathtrace_b200: call init_bvh(scene) first");
   return it->second;
+}
+// the scene handle of one device (a group: its first replica, made current)
+yh_scene* find_scene(const ptr::scene* scene) {
+  scene_record rec = find_scene_record(scene);
+  if (!rec.group) return rec.scene;
+  const yh_scene* first = nullptr;
+  int             device = 0;
+  check(yh_group_scene(rec.group, 0, &first, &device), "yh_group_scene");
+  check(yh_set_device(device), "yh_set_device");
+  return const_cast<yh_scene*>(first);
 }
 state_record& find_state(const ptr::state* state) {
   std::lock_guard<std::mutex> lock(table_mutex);
@@ -47,7 +63,7 @@ state_record& find_state(const ptr::state* state) {
 // ptr::scene -> yh_scene_desc.  Vertex arrays are passed in place (vec3f is 3
 // packed floats); textures are expanded to linear float RGB with the
 // reference's own conversion (lookup_texture, yocto_pathtrace.cpp:148-164).
-yh_scene* upload(const ptr::scene* scene) {
+scene_record upload(const ptr::scene* scene, const yh_bvh_params& bvh) {
   auto index_of = [](const auto& items, const auto* item) -> int {
     if (!item) return -1;
     for (size_t i = 0; i < items.size(); i++)
@@ -146,9 +162,13 @@ yh_scene* upload(const ptr::scene* scene) {
   }
   yh_scene_desc desc{shapes.data(), textures.data(), materials.data(), objects.data(), environments.data(),
       (int)shapes.size(), (int)textures.size(), (int)materials.size(), (int)objects.size(), (int)environments.size()};
-  yh_scene* handle = nullptr;
-  check(yh_scene_create(&desc, &handle), "yh_scene_create");
-  return handle;
+  scene_record rec{};
+  if (options.devices.size() > 1) {  // replicas on several GPUs: scene + BVH + light tables in one call
+    check(yh_group_create(&desc, &bvh, options.devices.data(), (int)options.devices.size(), &rec.group), "yh_group_create");
+  } else {
+    check(yh_scene_create(&desc, &rec.scene), "yh_scene_create");
+  }
+  return rec;
 }
 
 yh_trace_params to_params(const ptr::trace_params& p) {
@@ -161,28 +181,31 @@ void set_device_options(const device_options& o) { options = o; }
 
 void init_bvh(ptr::scene* scene, const ptr::trace_params& params, ptr::progress_callback progress_cb) {
   if (progress_cb) progress_cb("build bvh", 0, 2);
-  check(yh_set_device(options.device), "yh_set_device");
+  check(yh_set_device(options.devices.size() == 1 ? options.devices[0] : options.device), "yh_set_device");
   release(scene);
-  yh_scene* handle = upload(scene);
-  if (progress_cb) progress_cb("build bvh", 1, 2);
   yh_bvh_params bp{};
   bp.max_split = options.max_split;
-  yh_status st = yh_scene_init_bvh(handle, &bp);
-  if (st != YH_OK) {
-    std::string msg = yh_last_error();
-    yh_scene_destroy(handle);
-    throw std::runtime_error("yh_scene_init_bvh: " + msg);
+  scene_record rec = upload(scene, bp);
+  if (progress_cb) progress_cb("build bvh", 1, 2);
+  if (rec.scene) {
+    yh_status st = yh_scene_init_bvh(rec.scene, &bp);
+    if (st != YH_OK) {
+      std::string msg = yh_last_error();
+      yh_scene_destroy(rec.scene);
+      throw std::runtime_error("yh_scene_init_bvh: " + msg);
+    }
   }
   {
     std::lock_guard<std::mutex> lock(table_mutex);
-    scene_table[scene] = handle;
+    scene_table[scene] = rec;
   }
   if (progress_cb) progress_cb("build bvh", 2, 2);
 }
 
 void init_lights(ptr::scene* scene, const ptr::trace_params& params, ptr::progress_callback progress_cb) {
   if (progress_cb) progress_cb("build light", 0, 1);
-  check(yh_scene_init_lights(find_scene(scene)), "yh_scene_init_lights");
+  scene_record rec = find_scene_record(scene);
+  if (rec.scene) check(yh_scene_init_lights(rec.scene), "yh_scene_init_lights");  // a group built them in yh_group_create
   if (progress_cb) progress_cb("build light", 1, 1);
 }
 
@@ -194,14 +217,20 @@ void init_state(ptr::state* state, const ptr::scene* scene, const ptr::camera* c
   cam.focus = camera->focus, cam.aperture = camera->aperture;
   yh_trace_params p = to_params(params);
   yh_state*       handle = nullptr;
-  check(yh_state_create(find_scene(scene), &cam, &p, &handle), "yh_state_create");
-  if (options.world > 1) check(yh_state_set_shard(handle, options.rank, options.world), "yh_state_set_shard");
+  scene_record    rec = find_scene_record(scene);
   int w = 0, h = 0;
-  check(yh_state_size(handle, &w, &h), "yh_state_size");
+  if (rec.group) {
+    check(yh_group_init_state(rec.group, &cam, &p, options.sample_shard ? YH_SHARD_SAMPLES : YH_SHARD_TILES), "yh_group_init_state");
+    check(yh_group_size(rec.group, &w, &h), "yh_group_size");
+  } else {
+    check(yh_state_create(rec.scene, &cam, &p, &handle), "yh_state_create");
+    if (options.world > 1) check(yh_state_set_shard(handle, options.rank, options.world), "yh_state_set_shard");
+    check(yh_state_size(handle, &w, &h), "yh_state_size");
+  }
   state->pixels.assign({w, h}, ptr::pixel{});
   state->render.assign({w, h}, math::zero4f);
   std::lock_guard<std::mutex> lock(table_mutex);
-  state_table[state] = {handle, scene, *camera};
+  state_table[state] = {handle, rec.group, scene, *camera};
 }
 
 void trace_samples(ptr::state* state, const ptr::scene* scene, const ptr::camera* camera, const ptr::trace_params& params,
@@ -210,6 +239,18 @@ void trace_samples(ptr::state* state, const ptr::scene* scene, const ptr::camera
   if (rec.scene != scene) throw std::runtime_error("yocto_pathtrace_b200: state was initialised for another scene");
   if (memcmp(&rec.camera, camera, sizeof(ptr::camera)) != 0)
     throw std::runtime_error("yocto_pathtrace_b200: the camera changed since init_state; call init_state again");
+  if (rec.group) {
+    // sample sharding deals whole samples to the GPUs: a pass is one sample per GPU
+    int step = 1;
+    if (options.sample_shard) check(yh_group_num_devices(rec.group, &step), "yh_group_num_devices");
+    if (stop) {
+      for (int s = 0; s < num_samples && !*stop; s += step) check(yh_group_trace_samples(rec.group, step, nullptr), "yh_group_trace_samples");
+    } else {
+      check(yh_group_trace_samples(rec.group, (num_samples + step - 1) / step * step, nullptr), "yh_group_trace_samples");
+    }
+    check(yh_group_download(rec.group, (float*)state->render.data(), nullptr, nullptr), "yh_group_download");
+    return;
+  }
   if (stop) {  // the reference polls `stop` per image row inside a 1-spp pass; here between 1-spp passes
     for (int s = 0; s < num_samples && !*stop; s++) check(yh_trace_samples(rec.handle, 1, nullptr), "yh_trace_samples");
   } else {
@@ -260,8 +301,12 @@ void sync_pixels(ptr::state* state) {
   std::vector<float>    accum(4 * n);
   std::vector<int>      samples(n);
   std::vector<uint64_t> rng(2 * n);
-  check(yh_state_download(rec.handle, nullptr, accum.data(), samples.data()), "yh_state_download");
-  check(yh_state_download_rng(rec.handle, rng.data()), "yh_state_download_rng");
+  if (rec.group) {  // totals over the group; the per-pixel generators stay on their devices (rng reads 0)
+    check(yh_group_download(rec.group, nullptr, accum.data(), samples.data()), "yh_group_download");
+  } else {
+    check(yh_state_download(rec.handle, nullptr, accum.data(), samples.data()), "yh_state_download");
+    check(yh_state_download_rng(rec.handle, rng.data()), "yh_state_download_rng");
+  }
   for (size_t i = 0; i < n; i++) {
     auto& px = state->pixels.data()[i];
     memcpy(&px.accumulated, &accum[4 * i], 16);
@@ -272,7 +317,9 @@ void sync_pixels(ptr::state* state) {
 
 trace_stats last_stats(const ptr::state* state) {
   yh_trace_stats s{};
-  check(yh_state_stats(find_state(state).handle, &s), "yh_state_stats");
+  auto&          rec = find_state(state);
+  if (rec.group) check(yh_group_stats(rec.group, &s, nullptr), "yh_group_stats");
+  else check(yh_state_stats(rec.handle, &s), "yh_state_stats");
   return {s.samples, s.rays, s.light_rays, s.launches, s.device_ms};
 }
 
@@ -280,17 +327,22 @@ void release(const ptr::state* state) {
   std::lock_guard<std::mutex> lock(table_mutex);
   auto it = state_table.find(state);
   if (it == state_table.end()) return;
-  yh_state_destroy(it->second.handle);
+  if (it->second.handle) yh_state_destroy(it->second.handle);  // a group owns its states
   state_table.erase(it);
 }
 void release(const ptr::scene* scene) {
   std::lock_guard<std::mutex> lock(table_mutex);
   for (auto it = state_table.begin(); it != state_table.end();)
-    if (it->second.scene == scene) yh_state_destroy(it->second.handle), it = state_table.erase(it);
-    else ++it;
+    if (it->second.scene == scene) {
+      if (it->second.handle) yh_state_destroy(it->second.handle);
+      it = state_table.erase(it);
+    } else {
+      ++it;
+    }
   auto it = scene_table.find(scene);
   if (it == scene_table.end()) return;
-  yh_scene_destroy(it->second);
+  if (it->second.group) yh_group_destroy(it->second.group);
+  if (it->second.scene) yh_scene_destroy(it->second.scene);
   scene_table.erase(it);
 }
 

@@ -21,6 +21,7 @@
 
 #include <atomic>
 #include <functional>
+#include <vector>
 
 namespace yocto::pathtrace_b200 {
 
@@ -34,6 +35,12 @@ struct device_options {
   int device    = 0;  // CUDA device of this process (one process per GPU)
   int max_split = 0;  // references per long segment
   int rank = 0, world = 1;  // image-tile shard rendered by this process
+  // Two or more entries: ONE process drives these GPUs (yh_group_*): the scene is replicated on each, the image is
+  // sharded over them and summed on the first one over NVLink.  Tiles (default) keep the reference's RNG streams -
+  // the image is bit-identical to one GPU and to the CPU reference; sample_shard = true gives every GPU all pixels
+  // for its own sample indices (counter-mode streams, full-width wavefront, statistically equivalent image).
+  std::vector<int> devices;
+  bool             sample_shard = false;
 };
 void set_device_options(const device_options& options);
 

@@ -3,12 +3,13 @@
 // through the reference's own yocto_sceneio, same image writers) with the
 // per-sample hot path running in the CUDA library behind include/yocto_hair_b200.h.
 //
-//   yscenetrace_b200 [--backend cuda|cpu] [--loader fast|reference] [--spp-batch N] [--seed S] [--device D]
+//   yscenetrace_b200 [--loader fast|reference] [--spp-batch N] [--seed S] [--device D] [--gpus N] [--shard tiles|samples]
 //                    [--camera NAME] [-r RES] [-s SAMPLES] [-t path] [-b BOUNCES]
 //                    [--clamp C] [--save-batch] [-o out.pfm] scene.json
 //
-// `--backend cpu` runs the reference's own functions on the same scene, for an
-// A/B comparison of the two backends on identical inputs (tests/test_dropin_gpu.py).
+// The product binary has ONE backend, the CUDA library: there is no CPU path in it.  The same source compiled
+// with -DYH_AB_TOOL gives host/_build/yscenetrace_ab, a TEST tool whose extra `--backend cpu` runs the reference's
+// own functions on the same scene for the A/B comparisons of tests/test_dropin_gpu.py.
 #include <yocto/yocto_commonio.h>
 #include <yocto/yocto_image.h>
 #include <yocto/yocto_sceneio.h>
@@ -189,6 +190,7 @@ struct device_backend {
     else gpu::trace_samples(st, sc, cam, p);
   }
 };
+#ifdef YH_AB_TOOL
 struct reference_backend {
   int samples_done(ptr::state* st) const { return st->pixels.empty() ? 0 : st->pixels[{0, 0}].samples; }
   void init_state(ptr::state* st, const ptr::scene* sc, const ptr::camera* cam, const ptr::trace_params& p) const {
@@ -200,6 +202,7 @@ struct reference_backend {
     else ptr::trace_samples(st, sc, cam, p);
   }
 };
+#endif
 
 int main(int argc, const char* argv[]) {
   auto params      = ptr::trace_params{};
@@ -214,12 +217,18 @@ int main(int argc, const char* argv[]) {
   auto loader      = "fast"s;
   auto session_dir = ""s;
   auto stop_after  = 2;
+  auto gpus        = 1;
+  auto shard       = "tiles"s;
 
   auto cli = cli::make_cli("yscenetrace_b200", "Offline hair path tracing on B200");
-  add_option(cli, "--backend", backend, "cuda (B200 library) or cpu (the reference's own code).");
+#ifdef YH_AB_TOOL
+  add_option(cli, "--backend", backend, "cuda (B200 library) or cpu (the reference's own code; test tool only).");
+#endif
   add_option(cli, "--spp-batch", spp_batch, "Samples per pixel per device call.");
   add_option(cli, "--loader", loader, "fast (bulk PLY reader, yh_sceneio) or reference (yocto_sceneio).");
-  add_option(cli, "--device", device, "CUDA device.");
+  add_option(cli, "--device", device, "CUDA device (the first one with --gpus).");
+  add_option(cli, "--gpus", gpus, "GPUs of this node driven by this process (scene replicated, image sharded, summed over NVLink).");
+  add_option(cli, "--shard", shard, "With --gpus: tiles (reference RNG streams, bit-identical image) or samples (counter-mode streams).");
   add_option(cli, "--interactive-check", session_dir, "Run the headless interactive session and write its images here.");
   add_option(cli, "--stop-after", stop_after, "Interactive session: passes before the simulated camera edit.");
   add_option(cli, "--seed", seed, "Render seed (trace_params::seed).");
@@ -256,20 +265,30 @@ int main(int argc, const char* argv[]) {
   try {
     ptr::init_subdivs(scene.get(), params, cli::print_progress);  // host tesselation, the reference's own (both backends)
     if (on_gpu) {
+      if (shard != "tiles" && shard != "samples") cli::print_fatal("unknown shard mode " + shard);
       auto opts   = gpu::device_options{};
       opts.device = device;
+      if (gpus > 1) {
+        for (int k = 0; k < gpus; k++) opts.devices.push_back(device + k);
+        opts.sample_shard = shard == "samples";
+      }
       gpu::set_device_options(opts);
       gpu::init_bvh(scene.get(), params, cli::print_progress);
       gpu::init_lights(scene.get(), params, cli::print_progress);
       gpu::init_state(state.get(), scene.get(), camera, params);
     } else {
+#ifdef YH_AB_TOOL
       ptr::init_bvh(scene.get(), params, cli::print_progress);
       ptr::init_lights(scene.get(), params, cli::print_progress);
       ptr::init_state(state.get(), scene.get(), camera, params);
+#endif
     }
     if (!session_dir.empty()) {
-      int rc = on_gpu ? interactive_session(device_backend{}, scene.get(), camera, params, session_dir, stop_after, true)
-                      : interactive_session(reference_backend{}, scene.get(), camera, params, session_dir, stop_after, false);
+      int rc = 0;
+      if (on_gpu) rc = interactive_session(device_backend{}, scene.get(), camera, params, session_dir, stop_after, true);
+#ifdef YH_AB_TOOL
+      else rc = interactive_session(reference_backend{}, scene.get(), camera, params, session_dir, stop_after, false);
+#endif
       if (on_gpu) gpu::release(scene.get());
       return rc;
     }
@@ -279,7 +298,9 @@ int main(int argc, const char* argv[]) {
       cli::print_progress("render image", sample, params.samples);
       auto n = std::min(spp_batch, params.samples - sample);
       if (on_gpu) gpu::trace_samples(state.get(), scene.get(), camera, params, n);
+#ifdef YH_AB_TOOL
       else ptr::trace_samples(state.get(), scene.get(), camera, params);
+#endif
       sample += n;
       if (save_batch) {
         auto dot  = imfilename.rfind('.');  // <name>-s<k>.<ext>, as the reference names its batches

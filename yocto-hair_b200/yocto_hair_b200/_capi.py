@@ -14,6 +14,8 @@ c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int)
 
 YH_OK, YH_ERR_INVALID, YH_ERR_UNSUPPORTED, YH_ERR_NO_DEVICE, YH_ERR_CUDA, YH_ERR_STATE = range(6)
+YH_SHARD_TILES, YH_SHARD_SAMPLES = 0, 1
+YH_REDUCE_PEER, YH_REDUCE_NCCL = 0, 1
 
 
 class ShapeDesc(C.Structure):
@@ -140,6 +142,16 @@ PROTOTYPES = {
     "yh_state_download": (C.c_int, [_P, _P, _P, _P]),
     "yh_state_buffers_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "yh_state_download_rng": (C.c_int, [_P, _P]),
+    "yh_group_create": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BvhParams), c_int_p, C.c_int, C.POINTER(_P)]),
+    "yh_group_destroy": (None, [_P]),
+    "yh_group_num_devices": (C.c_int, [_P, c_int_p]),
+    "yh_group_scene": (C.c_int, [_P, C.c_int, C.POINTER(_P), c_int_p]),
+    "yh_group_init_state": (C.c_int, [_P, C.POINTER(CameraDesc), C.POINTER(TraceParams), C.c_int]),
+    "yh_group_set_reduce": (C.c_int, [_P, C.c_int]),
+    "yh_group_size": (C.c_int, [_P, c_int_p, c_int_p]),
+    "yh_group_trace_samples": (C.c_int, [_P, C.c_int, _P]),
+    "yh_group_stats": (C.c_int, [_P, C.POINTER(TraceStats), c_float_p]),
+    "yh_group_download": (C.c_int, [_P, _P, _P, _P]),
     "yh_hair_brdf_batch": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "yh_hair_eval_batch": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
     "yh_hair_sample_batch": (C.c_int, [_P, _P, _P, C.c_int64, _P]),

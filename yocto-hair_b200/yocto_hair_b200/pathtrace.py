@@ -186,3 +186,69 @@ def trace_image(scene: Scene, camera: Camera, params: capi.TraceParams | None = 
     st.close()
     ds.close()
     return img
+
+
+class DeviceGroup:
+    """Several GPUs of one node in one process (yh_group_*): replicated scene, one state per
+    GPU, fused peer-memory reduce + resolve on download."""
+
+    def __init__(self, scene: Scene, devices=None, num_devices: int | None = None, max_split: int = 0, quality: int = 0):
+        self.lib = capi.load()
+        desc, keep = scene.to_desc()
+        bp = capi.BvhParams()
+        bp.max_split, bp.quality = max_split, quality
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            n = len(devices)
+        else:
+            arr, n = None, int(num_devices or 1)
+        self.handle = _P()
+        capi.check(self.lib.yh_group_create(C.byref(desc), C.byref(bp), arr, n, C.byref(self.handle)))
+        del keep
+        self.num_devices = n
+        self.width = self.height = 0
+
+    def close(self):
+        if self.handle:
+            self.lib.yh_group_destroy(self.handle)
+            self.handle = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def init_state(self, camera: Camera, params: capi.TraceParams | None = None, shard: str = "tiles") -> "DeviceGroup":
+        cam = camera.to_desc()
+        params = params or make_params()
+        mode = {"tiles": capi.YH_SHARD_TILES, "samples": capi.YH_SHARD_SAMPLES}[shard]
+        capi.check(self.lib.yh_group_init_state(self.handle, C.byref(cam), C.byref(params), mode))
+        w, h = C.c_int(), C.c_int()
+        capi.check(self.lib.yh_group_size(self.handle, C.byref(w), C.byref(h)))
+        self.width, self.height = w.value, h.value
+        return self
+
+    def set_reduce(self, mode: str) -> "DeviceGroup":
+        capi.check(self.lib.yh_group_set_reduce(self.handle, {"peer": capi.YH_REDUCE_PEER, "nccl": capi.YH_REDUCE_NCCL}[mode]))
+        return self
+
+    def trace_samples(self, num_samples: int = 1) -> capi.TraceStats:
+        capi.check(self.lib.yh_group_trace_samples(self.handle, num_samples, None))
+        return self.stats()[0]
+
+    def stats(self):
+        s, ms = capi.TraceStats(), C.c_float()
+        capi.check(self.lib.yh_group_stats(self.handle, C.byref(s), C.byref(ms)))
+        return s, ms.value
+
+    def download(self, render=True, accum=True, samples=True):
+        r = np.zeros((self.height, self.width, 4), np.float32) if render else None
+        a = np.zeros((self.height, self.width, 4), np.float32) if accum else None
+        s = np.zeros((self.height, self.width), np.int32) if samples else None
+        p = lambda x: x.ctypes.data_as(_P) if x is not None else None  # noqa: E731
+        capi.check(self.lib.yh_group_download(self.handle, p(r), p(a), p(s)))
+        return r, a, s
+
+    def download_into(self, render: np.ndarray) -> None:
+        capi.check(self.lib.yh_group_download(self.handle, render.ctypes.data_as(_P), None, None))
