@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define YH_ABI_VERSION 1
+#define YH_ABI_VERSION 2
 
 typedef int yh_status;
 enum {
@@ -53,6 +53,12 @@ typedef struct yh_shape_desc {
   const int*   triangles; /* 3 * num_triangles                              */
   int num_positions, num_normals, num_texcoords, num_radius;
   int num_lines, num_triangles;
+  /* point shapes (yocto_pathtrace.h:341, intersect_point yocto_math.h:3405): one
+   * vertex index per point, per-vertex radius; shaded with the surface lobes and
+   * the normal -outgoing (eval_shading_normal :364).  A shape holds ONE kind of
+   * primitive (points, lines or triangles).                                   */
+  int        num_points;
+  const int* points; /* num_points                                           */
 } yh_shape_desc;
 
 /* yocto::pathtrace::texture, yocto_pathtrace.h:282-287 (float RGB only).    */
@@ -74,8 +80,13 @@ typedef struct yh_texture_desc {
  * are expanded by the caller: sRGB-decoded for emission / color / scattering,
  * linear for the other slots (normal_tex: tangent-space normal map on
  * triangles, eval_normalmap :326-347).  spectint_tex is never evaluated.
- * yh_scene_create refuses (YH_ERR_UNSUPPORTED): specular / metallic /
- * transmission on a line shape.                                              */
+ * On a line shape the hair lobe replaces eval / sample / pdf of every surface
+ * lobe (brdf.hair, :474-490), but is_delta (:495) still reads the surface
+ * roughness: yh_scene_create refuses (YH_ERR_UNSUPPORTED) a line shape whose
+ * material has transmission, or specular / metallic with roughness 0 or a
+ * roughness texture (the reference would then run its delta-surface branch on
+ * hair); specular / metallic with a plain non-zero roughness are accepted and,
+ * as in the reference, have no effect on hair.                                */
 typedef struct yh_material_desc {
   float emission[3];
   float color[3];

@@ -233,6 +233,7 @@ void* ref_scene_create(const yh_scene_desc* d) {
     }
     if (s.num_radius)
       ptr::set_radius(sh, std::vector<float>(s.radius, s.radius + s.num_radius));
+    if (s.num_points) ptr::set_points(sh, std::vector<int>(s.points, s.points + s.num_points));
     if (s.num_lines) {
       auto v = std::vector<vec2i>(s.num_lines);
       memcpy(v.data(), s.lines, 8 * (size_t)s.num_lines);

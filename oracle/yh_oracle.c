@@ -517,6 +517,17 @@ int yho_hardware_concurrency(void) {
 /* ========================================================= ray primitives == */
 typedef struct { v3 o, d; float tmin, tmax; } ray_t;
 
+static int hit_point(const ray_t* ray, v3 p, float r, v2* uv, float* dist) { /* intersect_point, ym:3405-3423 */
+  v3    w = vsub(p, ray->o);
+  float t = dot3(w, ray->d) / dot3(ray->d, ray->d);
+  if (t < ray->tmin || t > ray->tmax) return 0;
+  v3 rp = vadd(ray->o, vs(ray->d, t));
+  v3 prp = vsub(p, rp);
+  if (dot3(prp, prp) > r * r) return 0;
+  uv->x = 0, uv->y = 0;
+  *dist = t;
+  return 1;
+}
 static int hit_line(const ray_t* ray, v3 p0, v3 p1, float r0, float r1, v2* uv, float* dist) { /* ym:3426-3469 */
   v3    u = ray->d, v = vsub(p1, p0), w = vsub(ray->o, p0);
   float a = dot3(u, u), b = dot3(u, v), c = dot3(v, v), d = dot3(u, w), e = dot3(v, w);
@@ -635,8 +646,8 @@ typedef struct {
   v3 *pos, *nrm;
   v2* tex;
   float* rad;
-  int *lines, *tris;
-  int   npos, nnrm, ntex, nlines, ntris;
+  int *lines, *tris, *points;
+  int   npos, nnrm, ntex, nlines, ntris, npoints; /* one kind per shape */
   tree_t bvh;
 } shape_t;
 typedef struct {
@@ -661,10 +672,14 @@ static void* dup_mem(const void* p, size_t bytes) {
   return r;
 }
 static void init_shape_bvh(shape_t* s) { /* pt:721-752 */
-  int      n = s->nlines ? s->nlines : s->ntris;
+  int      n = s->npoints ? s->npoints : s->nlines ? s->nlines : s->ntris;
   bprim_t* p = (bprim_t*)malloc(sizeof(bprim_t) * (size_t)(n ? n : 1));
   for (int i = 0; i < n; i++) {
-    if (s->nlines) { /* line_bounds, ym:3037 */
+    if (s->npoints) { /* point_bounds(p, r), ym:3030-3033, pt:715-721 */
+      int a = s->points[i];
+      v3  lo = vsubs(s->pos[a], s->rad[a]), hi = vadds(s->pos[a], s->rad[a]);
+      p[i].box.lo = vmin(lo, hi), p[i].box.hi = vmax(lo, hi);
+    } else if (s->nlines) { /* line_bounds, ym:3037 */
       int a = s->lines[2 * i], b = s->lines[2 * i + 1];
       p[i].box.lo = vmin(vsubs(s->pos[a], s->rad[a]), vsubs(s->pos[b], s->rad[b]));
       p[i].box.hi = vmax(vadds(s->pos[a], s->rad[a]), vadds(s->pos[b], s->rad[b]));
@@ -747,7 +762,10 @@ void* yho_scene_create(const yh_scene_desc* d) {
     t->rad = (float*)dup_mem(s->radius, 4 * (size_t)s->num_radius);
     t->lines = (int*)dup_mem(s->lines, 8 * (size_t)t->nlines);
     t->tris = (int*)dup_mem(s->triangles, 12 * (size_t)t->ntris);
+    t->npoints = s->num_points;
+    t->points = (int*)dup_mem(s->points, 4 * (size_t)t->npoints);
     if (t->nlines) t->ntris = 0; /* the reference tests lines before triangles only after points; keep one kind */
+    if (t->npoints) t->nlines = 0, t->ntris = 0;
     init_shape_bvh(t);
   }
   sc->texs = (tex_t*)calloc((size_t)sc->ntexs + 1, sizeof(tex_t));
@@ -793,7 +811,7 @@ void yho_scene_destroy(void* h) {
   if (!sc) return;
   for (int i = 0; i < sc->nshapes; i++) {
     shape_t* s = &sc->shapes[i];
-    free(s->pos), free(s->nrm), free(s->tex), free(s->rad), free(s->lines), free(s->tris), free(s->bvh.nodes), free(s->bvh.prims);
+    free(s->pos), free(s->nrm), free(s->tex), free(s->rad), free(s->lines), free(s->tris), free(s->points), free(s->bvh.nodes), free(s->bvh.prims);
   }
   for (int i = 0; i < sc->ntexs; i++) free(sc->texs[i].px);
   for (int i = 0; i < sc->nlights; i++) free(sc->lights[i].cdf);
@@ -817,6 +835,11 @@ static int walk_shape(const shape_t* s, const ray_t* ray_, int* element, v2* uv,
     if (nd->internal) {
       if (dsign[(int)nd->axis]) stack[top++] = nd->start, stack[top++] = nd->start + 1;
       else stack[top++] = nd->start + 1, stack[top++] = nd->start;
+    } else if (s->npoints) { /* pt:894-903 */
+      for (int i = nd->start; i < nd->start + nd->num; i++) {
+        int e = t->prims[i], a = s->points[e];
+        if (hit_point(&ray, s->pos[a], s->rad[a], uv, distance)) hit = 1, *element = e, ray.tmax = *distance;
+      }
     } else if (s->nlines) {
       for (int i = nd->start; i < nd->start + nd->num; i++) {
         int e = t->prims[i], a = s->lines[2 * e], b = s->lines[2 * e + 1];
@@ -904,6 +927,8 @@ static v3 eval_position(const scene_t* sc, int object, int element, v2 uv) { /* 
     return xf_point(&ob->frame, vadd(vadd(vs(p0, 1 - uv.x - uv.y), vs(p1, uv.x)), vs(p2, uv.y)));
   } else if (s->nlines) {
     return xf_point(&ob->frame, lerp3(s->pos[s->lines[2 * element]], s->pos[s->lines[2 * element + 1]], uv.x));
+  } else if (s->npoints) {
+    return xf_point(&ob->frame, s->pos[s->points[element]]);
   }
   return V(0, 0, 0);
 }
@@ -915,6 +940,8 @@ static v3 eval_element_normal(const scene_t* sc, int object, int element) { /* p
     return xf_direction(&ob->frame, norm3(cross3(vsub(p1, p0), vsub(p2, p0))));
   } else if (s->nlines) {
     return xf_direction(&ob->frame, norm3(vsub(s->pos[s->lines[2 * element + 1]], s->pos[s->lines[2 * element]])));
+  } else if (s->npoints) {
+    return V(0, 0, 1);
   }
   return V(0, 0, 0);
 }
@@ -927,6 +954,8 @@ static v3 eval_normal(const scene_t* sc, int object, int element, v2 uv) { /* pt
     return xf_direction(&ob->frame, norm3(vadd(vadd(vs(n0, 1 - uv.x - uv.y), vs(n1, uv.x)), vs(n2, uv.y))));
   } else if (s->nlines) {
     return xf_direction(&ob->frame, norm3(lerp3(s->nrm[s->lines[2 * element]], s->nrm[s->lines[2 * element + 1]], uv.x)));
+  } else if (s->npoints) {
+    return xf_direction(&ob->frame, norm3(s->nrm[s->points[element]]));
   }
   return V(0, 0, 0);
 }
@@ -1074,6 +1103,7 @@ static v2 eval_texcoord(const scene_t* sc, int object, int element, v2 uv) { /* 
     r.x = t0.x * w + t1.x * uv.x + t2.x * uv.y, r.y = t0.y * w + t1.y * uv.x + t2.y * uv.y;
     return r;
   }
+  if (s->npoints) return s->tex[s->points[element]];
   v2 t0 = s->tex[s->lines[2 * element]], t1 = s->tex[s->lines[2 * element + 1]];
   r.x = t0.x * (1 - uv.x) + t1.x * uv.x, r.y = t0.y * (1 - uv.x) + t1.y * uv.x;
   return r;
@@ -1506,7 +1536,9 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
     int   is_hair = sh->nlines != 0;
     v3    position = eval_position(sc, object, element, uv);
     v3    normal; /* eval_shading_normal, pt:350-369 */
-    if (!is_hair) {
+    if (sh->npoints) {
+      normal = vneg(outgoing); /* pt:364-365 */
+    } else if (!is_hair) {
       normal = mat->normal_tex >= 0 ? eval_normalmap(sc, object, element, uv, mat->normal_tex) : eval_normal(sc, object, element, uv);
       if (mat->thin) normal = dot3(normal, outgoing) >= 0 ? normal : vneg(normal);
     } else {

@@ -28,7 +28,7 @@ def test_header_symbols_are_exported_and_bound(lib):
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in capi.PROTOTYPES, f"{n} has no ctypes prototype"
     assert sorted(capi.PROTOTYPES) == names  # and nothing undeclared is bound
-    assert lib.yh_abi_version() == 1
+    assert lib.yh_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header(tmp_path):

@@ -266,3 +266,27 @@ def test_port_material_model_bit_exact_vs_reference(name, shader, port, refo):
     assert diff[0].size == 0, "first differing pixels (y, x): %s" % list(zip(diff[0][:8], diff[1][:8]))
     for x in (sr, sp, rr, rp):
         x.close()
+
+
+@pytest.mark.parametrize("shader", [1, 0, 2, 3], ids=["path", "naive", "eyelight", "normal"])
+def test_port_point_shapes_bit_exact_vs_reference(shader, port, refo):
+    """Point primitives in the plain-C restatement (point_bounds yocto_math.h:3030, intersect_point :3405, the leaf
+    loop yocto_pathtrace.cpp:894-903, shading normal -outgoing :364): hit records and renders equal the reference's."""
+    scene, cam = synth.points_scene(3_000, 1_000)
+    rr, rp = refo.scene(scene), port.scene(scene)
+    if shader == 1:
+        rays = np.concatenate([synth.random_rays(scene, 20_000), synth.camera_rays(cam, 256, 256, 20_000)])
+        h1 = rr.intersect(rays.view(np.float32).reshape(-1, 8), threads=8)
+        h2 = rp.intersect(rays.view(np.float32).reshape(-1, 8), threads=8)
+        assert (h1["object"][h1["hit"] == 1] == 0).mean() > 0.05
+        for k in ("hit", "object", "element"):
+            assert np.array_equal(h1[k], h2[k])
+        h = h1["hit"] == 1
+        assert np.array_equal(bits(h1["distance"][h]), bits(h2["distance"][h])) and np.array_equal(bits(h1["uv"][h]), bits(h2["uv"][h]))
+    p = make_params(resolution=72, shader=shader)
+    sr, sp = rr.state(cam, p), rp.state(cam, p)
+    sr.trace_samples(2), sp.trace_samples(2)
+    (_, a1, s1, g1), (_, a2, s2, g2) = sr.download(), sp.download()
+    assert np.array_equal(s1, s2) and np.array_equal(g1, g2) and np.array_equal(bits(a1), bits(a2))
+    for x in (sr, sp, rr, rp):
+        x.close()

@@ -293,6 +293,106 @@ def test_errors_are_loud():
     assert lib.yh_last_error()
 
 
+@pytest.mark.parametrize("shader", [0, 2, 3])
+def test_scene_without_lights_renders_with_the_other_shaders(shader, ref):
+    """Only trace_path reads the lights: naive / eyelight / normal render an emitter-less hair model as the reference
+    does (eyelight is its usual preview)."""
+    sc, cam = synth.curly_hair_scene(8_000, sky=False)
+    sc.environments.clear()
+    p = make_params(resolution=96, shader=shader)
+    rs = ref.scene(sc)
+    sr = rs.state(cam, p)
+    sr.trace_samples(2)
+    ds = DeviceScene(sc).init_bvh().init_lights()
+    sd = ds.init_state(cam, p)
+    sd.trace_samples(2)
+    assert np.array_equal(sr.download()[1].view(np.uint32), sd.download()[1].view(np.uint32))
+    if shader != 0:
+        assert sd.download()[0][..., :3].max() > 0
+    sd.close(); ds.close(); sr.close(); rs.close()
+
+
+def test_stop_request_leaves_whole_samples(ref):
+    """A raised stop flag: no pixel starts another sample, the samples in flight finish, the state stays on the
+    reference's per-pixel streams and can be traced further."""
+    import ctypes as C
+    sc, cam = synth.curly_hair_scene(20_000)
+    p = make_params(resolution=128)
+    ds = DeviceScene(sc).init_bvh().init_lights()
+    sd = ds.init_state(cam, p)
+    flag = C.c_int(1)  # raised before the call: the first wavefront round is already queued when the flag is read, so
+    capi.check(sd.lib.yh_trace_samples(sd.handle, 50, C.addressof(flag)))  # a pixel finishes one or two samples, not 50
+    st = sd.stats()
+    _, a1, s1 = sd.download()
+    assert st.samples == int(s1.sum()) and s1.min() >= 1 and s1.max() <= 3
+    rs = ref.scene(sc)
+    sr = rs.state(cam, p)
+    ref_accum = {}
+    for k in range(1, 7):
+        sr.trace_samples(1)
+        ref_accum[k] = sr.download()[1]
+
+    def equals_reference(accum, count):  # every pixel holds exactly the first count[pixel] samples of its stream
+        for k in np.unique(count):
+            m = count == k
+            if not np.array_equal(ref_accum[int(k)][m].view(np.uint32), accum[m].view(np.uint32)):
+                return False
+        return True
+
+    assert equals_reference(a1, s1)
+    sd.trace_samples(2)  # and the state continues on the reference's streams
+    _, a3, s3 = sd.download()
+    assert np.array_equal(s3, s1 + 2) and equals_reference(a3, s3)
+    sd.close(); ds.close(); sr.close(); rs.close()
+
+
+@pytest.mark.parametrize("shader", [1, 2, 0])
+def test_point_shapes_bit_identical(shader, ref):
+    """Point primitives: bounds :715-721, intersect_point (yocto_math.h:3405) in the leaf loop :894-903,
+    shaded with the surface lobes and the normal -outgoing (:364).  Hit records and renders equal the reference's."""
+    scene, cam = synth.points_scene()
+    rs = ref.scene(scene)
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    if shader == 1:
+        rays = ray_set(scene, cam, 150_000, 100_000)
+        hr, hd = rs.intersect(rays.view(np.float32).reshape(-1, 8), threads=8), ds.intersect(rays)
+        assert (hr["object"][hr["hit"] == 1] == 0).mean() > 0.05  # the cloud is hit
+        assert_hits_identical(hr, hd)
+    p = make_params(resolution=144, shader=shader)
+    sr, sd = rs.state(cam, p), ds.init_state(cam, p)
+    sr.trace_samples(3), sd.trace_samples(3)
+    _, a_r, s_r, rng_r = sr.download()
+    _, a_d, s_d = sd.download()
+    assert np.array_equal(s_r, s_d) and np.array_equal(a_r.view(np.uint32), a_d.view(np.uint32))
+    assert np.array_equal(rng_r, sd.rng())
+    sd.close(); ds.close(); sr.close(); rs.close()
+
+
+def test_point_shape_variants_bit_identical(ref):
+    """One-point shape (root leaf), points without normals, with texcoords + a colour texture, a delta (mirror) cloud."""
+    from yocto_hair_b200.scene import Texture
+    for variant in ("single", "no_normals", "textured", "mirror"):
+        kw = dict(color=(0.9, 0.9, 0.9), metallic=1, roughness=0) if variant == "mirror" else {}
+        scene, cam = synth.points_scene(3_000, 1_000, **kw)
+        if variant == "single":
+            scene.shapes[0] = Shape(positions=[[0.5, 0.5, 0.5]], radius=[0.4], points=[0])
+        elif variant == "no_normals":
+            scene.shapes[0] = synth.make_point_cloud(3_000, normals=False)
+        elif variant == "textured":
+            scene.shapes[0] = synth.make_point_cloud(3_000, texcoords=True)
+            rng = np.random.default_rng(1)
+            scene.textures.append(Texture(rng.uniform(0.1, 1, (16, 16, 3)).astype(np.float32)))
+            scene.materials[0].color_tex = len(scene.textures) - 1
+        p = make_params(resolution=96)
+        rs, ds = ref.scene(scene), DeviceScene(scene).init_bvh().init_lights()
+        rays = ray_set(scene, cam, 20_000, 20_000)
+        assert_hits_identical(rs.intersect(rays.view(np.float32).reshape(-1, 8), threads=8), ds.intersect(rays))
+        sr, sd = rs.state(cam, p), ds.init_state(cam, p)
+        sr.trace_samples(2), sd.trace_samples(2)
+        assert np.array_equal(sr.download()[1].view(np.uint32), sd.download()[1].view(np.uint32)), variant
+        sd.close(); ds.close(); sr.close(); rs.close()
+
+
 def test_full_size_properties(ref):
     """BASELINE configs[2] geometry (1M curly segments): oracle agreement on a
     ray subset, and shard-union == whole image at the bench resolution's tile grid."""

@@ -11,6 +11,19 @@ struct ray3f {
   float tmin, tmax;
 };
 
+// intersect_point, yocto_math.h:3405-3423 (approximate: closest approach of the ray to the centre).  uv = {0, 0}.
+YH_HD bool intersect_point(const ray3f& ray, const vec3f& p, float r, vec2f& uv, float& dist) {
+  vec3f w = p - ray.o;
+  float t = div_(dot(w, ray.d), dot(ray.d, ray.d));
+  if (t < ray.tmin || t > ray.tmax) return false;
+  vec3f rp  = ray.o + ray.d * t;
+  vec3f prp = p - rp;
+  if (dot(prp, prp) > r * r) return false;
+  uv   = {0, 0};
+  dist = t;
+  return true;
+}
+
 // intersect_line, yocto_math.h:3426-3469.  Closest approach of the ray line and
 // the segment line; not a true cylinder test.  uv = {s, sqrt(d2)/r}.
 YH_HD bool intersect_line(const ray3f& ray, const vec3f& p0, const vec3f& p1, float r0, float r1,
@@ -58,7 +71,8 @@ YH_HD bool intersect_triangle(const ray3f& ray, const vec3f& p0, const vec3f& p1
   return true;
 }
 
-// line_bounds / triangle_bounds, yocto_math.h:3037-3048
+// point_bounds / line_bounds / triangle_bounds, yocto_math.h:3030-3048
+YH_HD bbox3f point_bounds(const vec3f& p, float r) { return {min3(p - r, p + r), max3(p - r, p + r)}; }
 YH_HD bbox3f line_bounds(const vec3f& p0, const vec3f& p1, float r0, float r1) {
   return {min3(p0 - r0, p1 - r1), max3(p0 + r0, p1 + r1)};
 }

@@ -34,12 +34,13 @@ __device__ __forceinline__ int split_count(const vec3f& p0, const vec3f& p1, flo
   return k < 1 ? 1 : (k > max_split ? max_split : k);
 }
 
-__global__ void k_count_refs(int is_lines, const int* elems, const float* pos, const float* radius, int n,
+// kind: 0 triangles, 1 lines, 2 points (host_shape::kind())
+__global__ void k_count_refs(int kind, const int* elems, const float* pos, const float* radius, int n,
     int max_split, int* counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int k = 1;
-  if (is_lines) {
+  if (kind == 1) {
     int a = elems[2 * i], b = elems[2 * i + 1];
     k     = split_count(ldv(pos, a), ldv(pos, b), radius[a], radius[b], max_split);
   }
@@ -58,13 +59,19 @@ __device__ __forceinline__ void pad_box(vec3f& lo, vec3f& hi, float scale) {
   hi        = hi + eps;
 }
 
-__global__ void k_make_refs(int is_lines, const int* elems, const float* pos, const float* radius, int n,
+__global__ void k_make_refs(int kind, const int* elems, const float* pos, const float* radius, int n,
     const int* offsets, const int* counts, ref_bounds* refs, int* ref_prim, vec3f cmin, vec3f cinv, float scale,
     unsigned long long* keys, int* ref_ids) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int first = offsets[i], k = counts[i];
-  if (is_lines) {
+  if (kind == 2) {
+    int    a = elems[i];
+    bbox3f box = point_bounds(ldv(pos, a), radius[a]);
+    pad_box(box.min, box.max, scale);
+    refs[first]     = {make_float4(box.min.x, box.min.y, box.min.z, 0), make_float4(box.max.x, box.max.y, box.max.z, 0)};
+    ref_prim[first] = i;
+  } else if (kind == 1) {
     int   a = elems[2 * i], b = elems[2 * i + 1];
     vec3f p0 = ldv(pos, a), p1 = ldv(pos, b);
     float r0 = radius[a], r1 = radius[b];
@@ -291,7 +298,7 @@ __device__ __forceinline__ void quantise(const ref_bounds& b, const vec3f& g, co
 // Writes the packed tree (yh_scene.cuh "shape BVH"): one thread per inner node
 // of the radix tree emits its own 32-byte record at the slot its parent
 // reserved for it, and the primitive records of its leaf children next to it.
-__global__ void k_emit_packed(int is_lines, int n_inner, const int* left, const int* right, const int* parent_inner,
+__global__ void k_emit_packed(int kind, int n_inner, const int* left, const int* right, const int* parent_inner,
     const int* sorted_ref, const ref_bounds* refs, const ref_bounds* node_box, const int* ref_prim, const int* elems,
     const float* pos, const float* radius, vec3f g, vec3f inv_s, vec3f pad, uint4* slots, int* slot_elem) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -313,10 +320,14 @@ __global__ void k_emit_packed(int is_lines, int n_inner, const int* left, const 
       // the leaf child is the primitive itself
       int    prim = ref_prim[sr];
       size_t slot = (size_t)(1 + 2 * i + c);
-      if (is_lines) {
+      if (kind == 1) {
         int a = elems[2 * prim], b = elems[2 * prim + 1];
         slots[2 * slot]     = make_uint4(__float_as_uint(pos[3 * a]), __float_as_uint(pos[3 * a + 1]), __float_as_uint(pos[3 * a + 2]), __float_as_uint(radius[a]));
         slots[2 * slot + 1] = make_uint4(__float_as_uint(pos[3 * b]), __float_as_uint(pos[3 * b + 1]), __float_as_uint(pos[3 * b + 2]), __float_as_uint(radius[b]));
+      } else if (kind == 2) {
+        int a = elems[prim];
+        slots[2 * slot]     = make_uint4(__float_as_uint(pos[3 * a]), __float_as_uint(pos[3 * a + 1]), __float_as_uint(pos[3 * a + 2]), __float_as_uint(radius[a]));
+        slots[2 * slot + 1] = make_uint4(0, 0, 0, 0);
       } else {
         slots[2 * slot]     = make_uint4((unsigned)prim, 0, 0, 0);
         slots[2 * slot + 1] = make_uint4(0, 0, 0, 0);
@@ -438,7 +449,10 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
   chunks([&](int i0, int i1) {
     for (int i = i0; i < i1; i++) {
       bbox3f b;
-      if (lines) {
+      if (sh.is_points()) {
+        int a = sh.points[i];
+        b     = point_bounds(P(a), sh.radius[a]);  // :715-721
+      } else if (lines) {
         int a = sh.lines[2 * i], c = sh.lines[2 * i + 1];
         b     = line_bounds(P(a), P(c), sh.radius[a], sh.radius[c]);
       } else {
@@ -609,6 +623,7 @@ static void sah_build(const std::vector<ref_bounds>& refs, sah_topology& t) {
 
 static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   bool lines = sh.is_lines();
+  int  kind  = sh.kind();
   int  n     = sh.num_elems();
   sh.root_leaf = 0, sh.num_refs = 0, sh.num_nodes = 0;
   sh.root_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
@@ -631,7 +646,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   dev_buffer<int> counts, offsets;
   YH_CUDA(counts.alloc(n));
   YH_CUDA(offsets.alloc(n));
-  k_count_refs<<<G(n), B>>>(lines, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, n, max_split, counts.ptr);
+  k_count_refs<<<G(n), B>>>(kind, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, n, max_split, counts.ptr);
   YH_CUDA(cudaGetLastError());
   size_t            tmp_bytes = 0;
   dev_buffer<char>  tmp;
@@ -683,7 +698,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   YH_CUDA(ids_out.alloc(R));
   YH_CUDA(keys_in.alloc(R));
   YH_CUDA(keys_out.alloc(R));
-  k_make_refs<<<G(n), B>>>(lines, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, n, offsets.ptr,
+  k_make_refs<<<G(n), B>>>(kind, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, n, offsets.ptr,
       counts.ptr, refs.ptr, ref_prim.ptr, cmin, cinv, sh.scale, keys_in.ptr, ids_in.ptr);
   YH_CUDA(cudaGetLastError());
   tmp_bytes = 0;
@@ -710,7 +725,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   vec3f pad_steps = {fold_pad_steps(glo.x, ghi.x, inv_step.x), fold_pad_steps(glo.y, ghi.y, inv_step.y),
       fold_pad_steps(glo.z, ghi.z, inv_step.z)};
   sh.num_refs    = R;
-  if (!lines) {
+  if (kind == 0) {
     YH_CUDA(sh.d_prims.alloc((size_t)n * 3));
     k_emit_triangles<<<G(n), B>>>(n, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_prims.ptr);
     YH_CUDA(cudaGetLastError());
@@ -731,6 +746,10 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
       int a = sh.lines[0], b = sh.lines[1];
       float v[8] = {sh.positions[3 * a], sh.positions[3 * a + 1], sh.positions[3 * a + 2], sh.radius[a],
           sh.positions[3 * b], sh.positions[3 * b + 1], sh.positions[3 * b + 2], sh.radius[b]};
+      memcpy(rec, v, 32);
+    } else if (kind == 2) {
+      int a = sh.points[0];
+      float v[8] = {sh.positions[3 * a], sh.positions[3 * a + 1], sh.positions[3 * a + 2], sh.radius[a], 0, 0, 0, 0};
       memcpy(rec, v, 32);
     }
     int zero = 0;
@@ -806,7 +825,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
       }
     }
   }
-  k_emit_packed<<<G(ni), B>>>(lines, ni, left.ptr, right.ptr, parent_inner.ptr, ids_out.ptr, refs.ptr, node_box.ptr,
+  k_emit_packed<<<G(ni), B>>>(kind, ni, left.ptr, right.ptr, parent_inner.ptr, ids_out.ptr, refs.ptr, node_box.ptr,
       ref_prim.ptr, sh.d_elems.ptr, sh.d_positions.ptr, sh.d_radius.ptr, sh.grid_origin, inv_step, pad_steps, sh.d_slots.ptr,
       sh.d_slot_elem.ptr);
   YH_CUDA(cudaGetLastError());
@@ -882,7 +901,7 @@ static yh_status upload_tables(yh_scene* sc) {
     dev_shape d{};
     d.slots = s->d_slots.ptr, d.tris = s->d_prims.ptr, d.slot_elem = s->d_slot_elem.ptr;
     d.ref_pos = s->d_ref_pos.ptr, d.tie_nodes = s->d_tie_nodes.ptr, d.num_tie_nodes = (int)s->d_tie_nodes.count;
-    d.root_leaf = s->root_leaf, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0;
+    d.root_leaf = s->root_leaf, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0, d.is_points = s->is_points() ? 1 : 0;
     d.scale = s->scale, d.grid_origin = s->grid_origin, d.grid_step = s->grid_step;
     d.has_normals = s->normals.empty() ? 0 : 1;
     d.positions = s->d_positions.ptr, d.normals = s->d_normals.ptr, d.elems = s->d_elems.ptr;
@@ -916,20 +935,31 @@ yh_status yh::scene_create(const yh_scene_desc* d, const yh_scene* ties_from, yh
     auto& o = d->objects[i];
     if (o.shape < 0 || o.shape >= d->num_shapes || o.material < 0 || o.material >= d->num_materials)
       return fail(YH_ERR_INVALID, "object %d: shape/material index out of range", i);
-    // the hair kernel assumes the hair lobe alone: a line shape whose material also has surface lobes would make
-    // is_delta() (yocto_pathtrace.cpp:495) depend on them
+    // On a line shape the hair lobe replaces eval / sample / pdf of all surface lobes (brdf.hair, :474-490), so
+    // specular / metallic have no effect - unless they make is_delta() (:495) true: with diffuse == 0 and roughness == 0
+    // the reference runs its delta-SURFACE branch on hair.  The hair kernel carries no surface lobes, so that corner
+    // (and refraction, which would open a volume behind a fibre, :1458-1467) is refused.
     auto& m = d->materials[o.material];
-    if (d->shapes[o.shape].num_lines > 0 && (m.specular != 0 || m.metallic != 0 || m.transmission != 0))
-      return fail(YH_ERR_UNSUPPORTED, "object %d: specular / metallic / transmission on a line shape is not built", i);
+    if (d->shapes[o.shape].num_lines > 0 && d->shapes[o.shape].num_points == 0) {
+      if (m.transmission != 0)
+        return fail(YH_ERR_UNSUPPORTED, "object %d: transmission on a line shape is not built", i);
+      if ((m.specular != 0 || m.metallic != 0) && (m.roughness == 0 || m.roughness_tex >= 0))
+        return fail(YH_ERR_UNSUPPORTED, "object %d: specular / metallic with zero or textured roughness on a line shape is not built", i);
+    }
   }
   for (int i = 0; i < d->num_environments; i++)
     if (d->environments[i].emission_tex >= d->num_textures)
       return fail(YH_ERR_INVALID, "environment %d: texture index out of range", i);
   for (int i = 0; i < d->num_shapes; i++) {
     auto& s = d->shapes[i];
-    if (s.num_lines && s.num_triangles) return fail(YH_ERR_INVALID, "shape %d has both lines and triangles", i);
-    if (s.num_lines && s.num_radius != s.num_positions)
-      return fail(YH_ERR_INVALID, "shape %d: lines need one radius per vertex", i);
+    // the reference dispatches points > lines > triangles in its traversal but triangles > lines > points when it
+    // shades (:232-310, :894-925): a shape with two kinds is something its loaders never produce
+    if ((s.num_lines > 0) + (s.num_triangles > 0) + (s.num_points > 0) > 1)
+      return fail(YH_ERR_INVALID, "shape %d mixes points / lines / triangles", i);
+    if ((s.num_lines || s.num_points) && s.num_radius != s.num_positions)
+      return fail(YH_ERR_INVALID, "shape %d: points and lines need one radius per vertex", i);
+    for (int k = 0; k < s.num_points; k++)
+      if (s.points[k] < 0 || s.points[k] >= s.num_positions) return fail(YH_ERR_INVALID, "shape %d: point index out of range", i);
     if (s.num_normals && s.num_normals != s.num_positions)
       return fail(YH_ERR_INVALID, "shape %d: normals/positions size mismatch", i);
     if (s.num_texcoords && s.num_texcoords != s.num_positions)
@@ -954,14 +984,14 @@ yh_status yh::scene_create(const yh_scene_desc* d, const yh_scene* ties_from, yh
     if (s.num_normals) hs->normals.assign(s.normals, s.normals + 3 * (size_t)s.num_normals);
     if (s.num_radius) hs->radius.assign(s.radius, s.radius + s.num_radius);
     if (s.num_texcoords) hs->texcoords.assign(s.texcoords, s.texcoords + 2 * (size_t)s.num_texcoords);
+    if (s.num_points) hs->points.assign(s.points, s.points + s.num_points);
     if (s.num_lines) hs->lines.assign(s.lines, s.lines + 2 * (size_t)s.num_lines);
     if (s.num_triangles) hs->triangles.assign(s.triangles, s.triangles + 3 * (size_t)s.num_triangles);
     if (hs->d_positions.upload(hs->positions.data(), hs->positions.size()) != cudaSuccess ||
         hs->d_normals.upload(hs->normals.data(), hs->normals.size()) != cudaSuccess ||
         hs->d_radius.upload(hs->radius.data(), hs->radius.size()) != cudaSuccess ||
         hs->d_texcoords.upload(hs->texcoords.data(), hs->texcoords.size()) != cudaSuccess ||
-        hs->d_elems.upload(hs->is_lines() ? hs->lines.data() : hs->triangles.data(),
-            hs->is_lines() ? hs->lines.size() : hs->triangles.size()) != cudaSuccess)
+        hs->d_elems.upload(hs->elems().data(), hs->elems().size()) != cudaSuccess)
       return bail(fail(YH_ERR_CUDA, "shape %d: device upload failed: %s", i, cudaGetErrorString(cudaGetLastError())));
   }
   for (size_t i = 0; i < sc->shapes.size(); i++) {

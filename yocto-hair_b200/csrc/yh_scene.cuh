@@ -11,6 +11,7 @@
 //                        w7 = bit 31: child 0 is a leaf, bit 30: child 1 is a leaf
 //                    or a leaf = ONE primitive reference:
 //                        line     : {p0.xyz, r0, p1.xyz, r1}  (the segment itself)
+//                        point    : {p.xyz, r, -, -, -, -}
 //                        triangle : w0 = element id (vertices in tris[3 * id ..])
 //                  Siblings share a 64-byte line, a leaf needs no second fetch, and
 //                  the whole tree of 1M segments is 64-106 MB instead of 160 MB.
@@ -53,11 +54,12 @@ struct dev_shape {
   int           num_refs;
   float         scale;      // largest |coordinate| of the shape: boxes are padded by 2e-6 * scale
   int           is_lines;
+  int           is_points;  // point shape (intersect_point; shaded with the surface lobes, normal = -outgoing)
   int           has_normals;
   const float*  positions;  // xyz
   const float*  normals;    // xyz (hair tangents for lines)
   const float*  texcoords;  // uv per vertex, or null (eval_texcoord then returns the element uv)
-  const int*    elems;      // lines: 2 ints, triangles: 3 ints
+  const int*    elems;      // points: 1 int, lines: 2 ints, triangles: 3 ints
   int           num_elems;
 };
 
@@ -124,7 +126,7 @@ struct dev_scene {
 // Host-side copy of one shape (kept for light CDFs and BVH set-up).
 struct host_shape {
   std::vector<float> positions, normals, radius, texcoords;
-  std::vector<int>   lines, triangles;
+  std::vector<int>   points, lines, triangles;
   dev_buffer<float>  d_positions, d_normals, d_radius, d_texcoords;
   dev_buffer<int>    d_elems;
   dev_buffer<uint4>  d_slots;
@@ -135,8 +137,12 @@ struct host_shape {
   float              scale = 0;
   vec3f              grid_origin{0, 0, 0}, grid_step{1, 1, 1};
   bbox3f             root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
-  int  num_elems() const { return is_lines() ? (int)lines.size() / 2 : (int)triangles.size() / 3; }
-  bool is_lines() const { return !lines.empty(); }
+  // one primitive kind per shape; the reference's traversal looks at points, then lines, then triangles (:894-925)
+  int  num_elems() const { return is_points() ? (int)points.size() : is_lines() ? (int)lines.size() / 2 : (int)triangles.size() / 3; }
+  bool is_points() const { return !points.empty(); }
+  bool is_lines() const { return points.empty() && !lines.empty(); }
+  int  kind() const { return is_points() ? 2 : is_lines() ? 1 : 0; }  // 0 triangles, 1 lines, 2 points
+  const std::vector<int>& elems() const { return is_points() ? points : is_lines() ? lines : triangles; }
   // The reference's leaf order (tie tables) is a host computation of ~25 ms per million primitives: it starts in
   // yh_scene_create, runs beside the uploads, the device BVH build, the light tables and the state set-up, and
   // is joined by the first call that traverses (yh_scene::sync_ties()).

@@ -18,6 +18,7 @@ __device__ __forceinline__ vec3f ldp(const float* p, int i) {
 __device__ __forceinline__ vec3f eval_position(const dev_scene& sc, int object, int element, const vec2f& uv) {
   const dev_object& ob = sc.objects[object];
   const dev_shape&  sh = sc.shapes[ob.shape];
+  if (sh.is_points) return transform_point(ob.frame, ldp(sh.positions, __ldg(sh.elems + element)));
   if (!sh.is_lines) {
     int   a = __ldg(sh.elems + 3 * element), b = __ldg(sh.elems + 3 * element + 1), c = __ldg(sh.elems + 3 * element + 2);
     vec3f p = ldp(sh.positions, a) * (1 - uv.x - uv.y) + ldp(sh.positions, b) * uv.x + ldp(sh.positions, c) * uv.y;
@@ -31,6 +32,7 @@ __device__ __forceinline__ vec3f eval_position(const dev_scene& sc, int object, 
 __device__ __forceinline__ vec3f eval_element_normal(const dev_scene& sc, int object, int element) {
   const dev_object& ob = sc.objects[object];
   const dev_shape&  sh = sc.shapes[ob.shape];
+  if (sh.is_points) return {0, 0, 1};  // :264-265
   if (!sh.is_lines) {
     int   a = __ldg(sh.elems + 3 * element), b = __ldg(sh.elems + 3 * element + 1), c = __ldg(sh.elems + 3 * element + 2);
     vec3f p0 = ldp(sh.positions, a), p1 = ldp(sh.positions, b), p2 = ldp(sh.positions, c);
@@ -44,6 +46,7 @@ __device__ __forceinline__ vec3f eval_normal(const dev_scene& sc, int object, in
   const dev_object& ob = sc.objects[object];
   const dev_shape&  sh = sc.shapes[ob.shape];
   if (!sh.has_normals) return eval_element_normal(sc, object, element);
+  if (sh.is_points) return transform_direction(ob.frame, normalize(ldp(sh.normals, __ldg(sh.elems + element))));  // :286-288
   if (!sh.is_lines) {
     int   a = __ldg(sh.elems + 3 * element), b = __ldg(sh.elems + 3 * element + 1), c = __ldg(sh.elems + 3 * element + 2);
     vec3f n = ldp(sh.normals, a) * (1 - uv.x - uv.y) + ldp(sh.normals, b) * uv.x + ldp(sh.normals, c) * uv.y;
@@ -78,6 +81,7 @@ __device__ __forceinline__ vec2f eval_texcoord(const dev_scene& sc, int object, 
   const dev_shape& sh = sc.shapes[sc.objects[object].shape];
   if (!sh.texcoords) return uv;
   auto ldt = [&](int i) -> vec2f { return {__ldg(sh.texcoords + 2 * i), __ldg(sh.texcoords + 2 * i + 1)}; };
+  if (sh.is_points) return ldt(__ldg(sh.elems + element));  // :306-307
   if (!sh.is_lines) {
     int   a = __ldg(sh.elems + 3 * element), b = __ldg(sh.elems + 3 * element + 1), c = __ldg(sh.elems + 3 * element + 2);
     vec2f t0 = ldt(a), t1 = ldt(b), t2 = ldt(c);

@@ -327,6 +327,8 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
   if (HAIR) {
     tangent = eval_normal(sc, object, element, uv);
     normal  = orthonormalize(outgoing, tangent);
+  } else if (sc.shapes[ob.shape].is_points) {
+    normal = -outgoing;  // :364-365
   } else {
     normal = mat.normal_tex >= 0 ? eval_normalmap(sc, object, element, uv, mat.normal_tex) : eval_normal(sc, object, element, uv);
     if (mat.thin) normal = dot(normal, outgoing) >= 0 ? normal : -normal;

@@ -139,10 +139,13 @@ __device__ __forceinline__ bool line_certain_miss(const vec3f& o, const vec3f& u
 
 // The primitive in leaf slot `slot` against the ray: certain-miss test, then
 // the reference's exact test.
-__device__ __forceinline__ bool test_leaf_slot(const dev_shape& sh, bool is_lines, const ray3f& ray, float uu, float mo,
+// kind: 1 lines, 2 points, 0 triangles
+__device__ __forceinline__ bool test_leaf_slot(const dev_shape& sh, int kind, const ray3f& ray, float uu, float mo,
     int slot, vec2f& uv, float& t) {
   const slot_words s = ld_slot(sh.slots, slot);
-  if (is_lines) {
+  if (kind == 2)
+    return intersect_point(ray, {__uint_as_float(s.w0), __uint_as_float(s.w1), __uint_as_float(s.w2)}, __uint_as_float(s.w3), uv, t);
+  if (kind == 1) {
     const float4 a = {__uint_as_float(s.w0), __uint_as_float(s.w1), __uint_as_float(s.w2), __uint_as_float(s.w3)};
     const float4 b = {__uint_as_float(s.w4), __uint_as_float(s.w5), __uint_as_float(s.w6), __uint_as_float(s.w7)};
     if (line_certain_miss(ray.o, ray.d, uu, mo, a, b)) return false;
@@ -358,7 +361,7 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
   shape_ray sr = make_shape_ray(sh, ray.o, ray.d);
   if (!sr.valid) return false;
   bool     hit      = false;
-  bool     is_lines = sh.is_lines != 0;
+  int      kind     = sh.is_lines ? 1 : (sh.is_points ? 2 : 0);
   unsigned dsign    = ray_dsign(ray.d);
   float    uu = __fmaf_rn(ray.d.x, ray.d.x, __fmaf_rn(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
   float    mo = fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z);
@@ -366,7 +369,7 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
     vec2f uvc;
     float tc;
     YH_STAT(if (prims_tested)(*prims_tested)++;)
-    if (test_leaf_slot(sh, is_lines, ray, uu, mo, slot, uvc, tc)) accept_hit(sh, dsign, slot, uvc, tc, hit, ref, uv, ray.tmax);
+    if (test_leaf_slot(sh, kind, ray, uu, mo, slot, uvc, tc)) accept_hit(sh, dsign, slot, uvc, tc, hit, ref, uv, ray.tmax);
   };
   if (sh.root_leaf) {
     leaf(0);
@@ -497,7 +500,7 @@ enum cold_word {
   CW_TMIN, CW_TMAX, CW_T0,                    // its range; box distances are measured from o + t0 d
   CW_HANDLE, CW_OBJ, CW_REF, CW_U, CW_V,      // ray handle, object index, best leaf slot of this shape, its uv
   CW_BOBJ, CW_BELEM, CW_BU, CW_BV, CW_BDIST,  // best hit over the objects closed so far
-  CW_FLAGS,                                    // bit 0 shape_hit, 1 best.hit, 2 is_lines, 4..6 dsign
+  CW_FLAGS,                                    // bit 0 shape_hit, 1 best.hit, 2 is_lines, 3 is_points, 4..6 dsign
   CW_SHAPE_LO, CW_SHAPE_HI,
   CW_COUNT
 };
@@ -574,7 +577,8 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         float uu = __fmaf_rn(ray.d.x, ray.d.x, __fmaf_rn(ray.d.y, ray.d.y, ray.d.z * ray.d.z));
         float mo = fabsf(ray.o.x) + fabsf(ray.o.y) + fabsf(ray.o.z);
         int   flags = cw(CW_FLAGS), ref = cw(CW_REF);
-        bool  shape_hit = flags & 1, is_lines = (flags & 4) != 0;
+        bool  shape_hit = flags & 1;
+        int   kind = (flags & 4) ? 1 : ((flags & 8) ? 2 : 0);
         unsigned dsign = (flags >> 4) & 7;
         vec2f uv = {cwf(CW_U), cwf(CW_V)};
         const dev_shape& sh = *shape_ptr();
@@ -584,7 +588,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
           vec2f uvc;
           float tc;
           YH_STAT(if (prims_tested)(*prims_tested)++;)
-          if (test_leaf_slot(sh, is_lines, ray, uu, mo, slot, uvc, tc))
+          if (test_leaf_slot(sh, kind, ray, uu, mo, slot, uvc, tc))
             accept_hit(sh, dsign, slot, uvc, tc, shape_hit, ref, uv, ray.tmax);
         }
         park_top = park_base;
@@ -632,7 +636,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         put(CW_T0, sr.t0);
         cw(CW_SHAPE_LO) = (int)(unsigned)((unsigned long long)&sh);
         cw(CW_SHAPE_HI) = (int)(unsigned)((unsigned long long)&sh >> 32);
-        flags = (flags & 3) | (sh.is_lines ? 4 : 0) | (int)(ray_dsign(d) << 4);
+        flags = (flags & 3) | (sh.is_lines ? 4 : 0) | (sh.is_points ? 8 : 0) | (int)(ray_dsign(d) << 4);
         slots = sh.slots;
         cw(CW_REF) = -1;
         if (sh.root_leaf) smem_park[0] = 0, park_top = park_base + kStackStride, cur = kTraverseDone;  // the whole shape is one leaf

@@ -74,7 +74,6 @@ scene_record upload(const ptr::scene* scene, const yh_bvh_params& bvh) {
   for (size_t i = 0; i < shapes.size(); i++) {
     auto  s = scene->shapes[i];
     auto& d = shapes[i];
-    if (!s->points.empty()) throw std::runtime_error("yocto_pathtrace_b200: point shapes are outside the hair hot path");
     d = yh_shape_desc{};
     d.positions = (const float*)s->positions.data(), d.num_positions = (int)s->positions.size();
     d.normals = (const float*)s->normals.data(), d.num_normals = (int)s->normals.size();
@@ -84,6 +83,7 @@ scene_record upload(const ptr::scene* scene, const yh_bvh_params& bvh) {
     // for intersection; a shape with both is not something its loaders produce
     d.lines = (const int*)s->lines.data(), d.num_lines = (int)s->lines.size();
     d.triangles = (const int*)s->triangles.data(), d.num_triangles = (int)s->triangles.size();
+    d.points = s->points.data(), d.num_points = (int)s->points.size();
   }
   std::vector<std::vector<float>> texels(scene->textures.size());
   std::vector<yh_texture_desc>    textures(scene->textures.size());

@@ -24,6 +24,7 @@ class ShapeDesc(C.Structure):
         ("radius", c_float_p), ("lines", c_int_p), ("triangles", c_int_p),
         ("num_positions", C.c_int), ("num_normals", C.c_int), ("num_texcoords", C.c_int),
         ("num_radius", C.c_int), ("num_lines", C.c_int), ("num_triangles", C.c_int),
+        ("num_points", C.c_int), ("points", c_int_p),
     ]
 
 

@@ -52,6 +52,7 @@ class Shape:
     radius: Optional[np.ndarray] = None
     lines: Optional[np.ndarray] = None
     triangles: Optional[np.ndarray] = None
+    points: Optional[np.ndarray] = None
 
     def __post_init__(self):
         self.positions = _f32(self.positions, 3)
@@ -60,6 +61,7 @@ class Shape:
         self.radius = _f32(self.radius, 1) if self.radius is not None else np.zeros((0,), np.float32)
         self.lines = _i32(self.lines, 2) if self.lines is not None else np.zeros((0, 2), np.int32)
         self.triangles = _i32(self.triangles, 3) if self.triangles is not None else np.zeros((0, 3), np.int32)
+        self.points = np.ascontiguousarray(self.points, dtype=np.int32).reshape(-1) if self.points is not None else np.zeros((0,), np.int32)
 
 
 @dataclass
@@ -181,6 +183,7 @@ class Scene:
             d.radius, d.num_radius = fptr(s.radius), len(s.radius)
             d.lines, d.num_lines = iptr(s.lines), len(s.lines)
             d.triangles, d.num_triangles = iptr(s.triangles), len(s.triangles)
+            d.points, d.num_points = iptr(s.points), len(s.points)
         textures = (capi.TextureDesc * max(1, len(self.textures)))()
         for d, t in zip(textures, self.textures):
             d.colorf, d.height, d.width = fptr(t.colorf), t.colorf.shape[0], t.colorf.shape[1]

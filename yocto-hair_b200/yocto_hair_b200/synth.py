@@ -351,3 +351,40 @@ def camera_rays(camera: Camera, width: int, height: int, n: int, seed=5):
     q = np.stack([camera.film[0] * (0.5 - uv[:, 0]), camera.film[1] * (uv[:, 1] - 0.5), np.full(n, camera.lens)], axis=1).astype(F)
     d = _normalize(-_normalize(q) @ fr[:3])
     return make_rays(np.tile(fr[3], (n, 1)), d)
+
+
+def make_point_cloud(num_points=20_000, seed=9, radius=(0.004, 0.02), normals=True, texcoords=False) -> Shape:
+    """A ball of points with per-vertex radius (the reference's point primitive: yocto_math.h:3405)."""
+    rng = np.random.default_rng(seed)
+    d = _normalize(rng.normal(0, 1, (num_points, 3)).astype(F))
+    pos = (d * rng.uniform(0, 1, (num_points, 1)).astype(F) ** F(1 / 3) * F(0.5)).astype(F) + np.array([0.5, 0.5, 0.5], F)
+    rad = rng.uniform(radius[0], radius[1], num_points).astype(F)
+    return Shape(positions=pos, normals=d if normals else None, radius=rad,
+                 texcoords=rng.uniform(0, 1, (num_points, 2)).astype(F) if texcoords else None,
+                 points=np.arange(num_points, dtype=np.int32))
+
+
+def points_scene(num_points=20_000, num_segments=6_000, seed=9, sky=True, **point_material):
+    """SURVEY 8f N3 leftover: a point cloud (surface lobes, normal = -outgoing) beside a hair block on a diffuse
+    floor, one area light and the sky.  `point_material` overrides the cloud's material fields."""
+    sc = Scene()
+    sc.shapes.append(make_point_cloud(num_points, seed))                  # 0
+    sc.shapes.append(make_hair_block(num_segments, seed))                 # 1
+    sc.shapes.append(make_arealight_quad())                               # 2
+    mat = dict(color=(0.7, 0.3, 0.2), specular=0.5, roughness=0.3)
+    mat.update(point_material)
+    sc.materials.append(Material(**mat))
+    sc.materials.append(Material(eumelanin=1.3))
+    sc.materials.append(Material(color=(0.7, 0.7, 0.7)))
+    sc.materials.append(Material(emission=(20, 20, 20)))
+    sc.objects.append(Object(shape=0, material=0, frame=(1.2, 0, 0, 0, 1.2, 0, 0, 0, 1.2, -1.6, 0.05, -0.3)))
+    sc.objects.append(Object(shape=1, material=1, frame=(1, 0, 0, 0, 0, 1, 0, -1, 0, 0.4, 1, -0.5)))
+    sc.objects.append(Object(shape=2, material=2, frame=(1, 0, 0, 0, 0, -1, 0, 1, 0, 0, 0, 0)))
+    sc.objects.append(Object(shape=2, material=3, frame=lookat_frame((3, 6, 5), (0, 0.5, 0), (0, 1, 0), inv_xz=True)))
+    if sky:
+        sc.textures.append(make_sky_texture())
+        sc.environments.append(Environment(emission=(1, 1, 1), emission_tex=0))
+    else:
+        sc.environments.append(Environment(emission=(1, 1, 1)))
+    cam = Camera.from_lookat((0.0, 1.6, 5.0), (0.0, 0.6, 0.0), (0, 1, 0), lens=0.05, aspect=1.5)
+    return sc, cam
