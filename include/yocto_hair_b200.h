@@ -284,6 +284,10 @@ yh_status yh_state_download(const yh_state* state, float* render, float* accum,
  * (int/pixel) buffers, for a collective over NVLink.                        */
 yh_status yh_state_buffers_dev(yh_state* state, float** accum_dev,
     int** samples_dev);
+/* render = accumulated / samples (:1688) on device buffers that did not come
+ * out of one state - the sum a collective left on the root rank.  Synchronous. */
+yh_status yh_resolve_dev(const float* accum_dev, const int* samples_dev,
+    int64_t num_pixels, float* render_dev);
 /* Dump / restore of the per-pixel RNG (2 x uint64 per pixel: state, inc).   */
 yh_status yh_state_download_rng(const yh_state* state, uint64_t* rng);
 

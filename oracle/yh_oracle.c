@@ -1481,6 +1481,17 @@ static v3 sample_phasefunction(float anisotropy, v3 outgoing, v2 rn) {
   return xf_vector(&basis, V(sin_theta * cosf(phi), sin_theta * sinf(phi), cos_theta));
 }
 
+/* diagnostics (yho_debug_pixel): every path ray of the samples traced by this thread and what it hit */
+typedef struct { yh_ray* rays; yh_hit* hits; int max, count; } path_log_t;
+static __thread path_log_t* g_path_log = NULL;
+static void log_path_ray(const ray_t* ray, int hit, int object, int element, v2 uv, float dist) {
+  path_log_t* l = g_path_log;
+  if (!l || l->count >= l->max) return;
+  yh_ray r = {{ray->o.x, ray->o.y, ray->o.z}, {ray->d.x, ray->d.y, ray->d.z}, ray->tmin, ray->tmax};
+  yh_hit h = {object, element, {uv.x, uv.y}, dist, hit};
+  l->rays[l->count] = r, l->hits[l->count] = h, l->count++;
+}
+
 static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_params* params, float out[4]) {
   v3  radiance = V(0, 0, 0), weight = V(1, 1, 1);
   int hit = 0;
@@ -1495,7 +1506,9 @@ static void trace_path(const scene_t* sc, ray_t ray, rng_t* rng, const yh_trace_
     int   object = -1, element = -1;
     v2    uv = {0, 0};
     float dist = 0;
-    if (!walk_scene(sc, &ray, &object, &element, &uv, &dist, 0)) {
+    int found = walk_scene(sc, &ray, &object, &element, &uv, &dist, 0);
+    if (g_path_log) log_path_ray(&ray, found, object, element, uv, dist);
+    if (!found) {
       radiance = vadd(radiance, vmul(weight, eval_environment(sc, ray.d)));
       if (shader == YH_SHADER_NORMAL) hit = 1; /* trace_normal returns alpha 1 on a miss too */
       break;
@@ -1669,6 +1682,17 @@ static void* row_worker(void* arg) { /* parallel_for, pt:1954-1970: dynamic rows
     for (int i = 0; i < st->w; i++) trace_pixel(st, i, j);
   }
   return NULL;
+}
+
+/* Diagnostics: traces `nsamples` MORE samples of pixel (i, j) of this state (the pixel's accumulation and RNG advance as
+ * in a normal pass) and records the path rays with their hit records; returns the number of records written. */
+int yho_debug_pixel(void* h, int i, int j, int nsamples, yh_ray* rays, yh_hit* hits, int max_records) {
+  state_t*   st = (state_t*)h;
+  path_log_t log = {rays, hits, max_records, 0};
+  g_path_log = &log;
+  for (int s = 0; s < nsamples; s++) trace_pixel(st, i, j);
+  g_path_log = NULL;
+  return log.count;
 }
 
 void* yho_state_create(void* scene, const yh_camera_desc* c, const yh_trace_params* p) { /* init_state, pt:1931-1946 */

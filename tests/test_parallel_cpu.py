@@ -32,7 +32,10 @@ WORKER = textwrap.dedent("""
     mine_s = torch.from_numpy(np.where(mask, samples, 0).astype(np.int32))
     counts = torch.tensor([int(mask.sum())]); dist.all_reduce(counts)
     assert counts.item() == st.width * st.height
-    parallel.reduce_image(mine_a, mine_s, 0)
+    kept_a = mine_a.clone()
+    mine_a_in, mine_s_in = mine_a, mine_s
+    mine_a, mine_s = parallel.reduce_image(mine_a_in, mine_s_in, 0)
+    assert torch.equal(mine_a_in, kept_a)  # the inputs are left untouched: the sum goes to scratch
     if rank == 0:
         assert np.array_equal(mine_s.numpy(), samples)
         assert np.array_equal(mine_a.numpy().view(np.uint32), accum.view(np.uint32))

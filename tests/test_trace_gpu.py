@@ -393,6 +393,38 @@ def test_point_shape_variants_bit_identical(ref):
         sd.close(); ds.close(); sr.close(); rs.close()
 
 
+@pytest.mark.parametrize("side,coincident", [((2, 2, 2), 3), ((3, 2, 1), 6), ((10, 10, 10), 12)])
+def test_many_instances_follow_the_reference_scene_tree(side, coincident, ref):
+    """The top-level tree over the objects is the reference's own (build_bvh over the object bounds :793-814, walked as
+    :960-1028): more than four objects, lattice positions that sit on its split planes, and coincident instances whose
+    hits tie exactly BETWEEN objects - the hit object must be the one the reference's visiting order keeps.  The largest
+    case has 1013 objects on one hair shape."""
+    scene, cam = synth.instanced_curls_scene(side, coincident=coincident)
+    assert len(scene.objects) > 4
+    rs = ref.scene(scene)
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    rays = ray_set(scene, cam, 60_000, 120_000)
+    # rays from inside the lattice, towards everywhere
+    rng = np.random.default_rng(5)
+    o = rng.uniform((-0.5, 0, -0.5), (side[0] - 0.5, 2.0 * side[1], side[2] - 0.5), (80_000, 3)).astype(np.float32)
+    d = rng.normal(0, 1, (80_000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([rays, make_rays(o, d)])
+    hr, hd = rs.intersect(rays.view(np.float32).reshape(-1, 8), threads=16), ds.intersect(rays)
+    assert hr["hit"].mean() > 0.02
+    doubled = set(range(side[0] * side[1] * side[2], len(scene.objects) - 1))
+    assert np.isin(hr["object"][hr["hit"] == 1], list(doubled)).any() or coincident == 0  # ties between objects occur
+    assert_hits_identical(hr, hd)
+    ha = ds.intersect(rays[:40_000], find_any=True)
+    assert np.array_equal(ha["hit"], hr["hit"][:40_000])
+    p = make_params(resolution=120)
+    sr, sd = rs.state(cam, p), ds.init_state(cam, p)
+    sr.trace_samples(2), sd.trace_samples(2)
+    assert np.array_equal(sr.download()[1].view(np.uint32), sd.download()[1].view(np.uint32))
+    assert np.array_equal(sr.download()[3], sd.rng())
+    sd.close(); ds.close(); sr.close(); rs.close()
+
+
 def test_full_size_properties(ref):
     """BASELINE configs[2] geometry (1M curly segments): oracle agreement on a
     ray subset, and shard-union == whole image at the bench resolution's tile grid."""

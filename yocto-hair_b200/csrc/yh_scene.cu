@@ -432,21 +432,24 @@ static std::vector<int4> reference_tree(ref_prim* prims, int start, int end, int
   append(right, rofs);
   return nodes;
 }
-static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos, std::vector<int4>& tie_nodes) {
+static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos, std::vector<int4>& tie_nodes, bbox3f& root_bbox) {
   bool lines = sh.is_lines();
   int  n     = sh.num_elems();
   auto P     = [&](int v) { return vec3f{sh.positions[3 * v], sh.positions[3 * v + 1], sh.positions[3 * v + 2]}; };
   // the two linear passes run in chunks on host threads (a million primitives: ~15 ms each on one core)
-  auto chunks = [n](auto&& body) {
-    const int nt = n > (1 << 16) ? 8 : 1;
+  const int nt = n > (1 << 16) ? 8 : 1;
+  auto chunks = [n, nt](auto&& body) {
     std::vector<std::future<void>> jobs;
     for (int t = 0; t < nt; t++)
       jobs.push_back(std::async(nt > 1 ? std::launch::async : std::launch::deferred,
-          [&body, n, nt, t]() { body((int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); }));
+          [&body, n, nt, t]() { body(t, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); }));
     for (auto& j : jobs) j.get();
   };
   std::vector<ref_prim> prims(n);
-  chunks([&](int i0, int i1) {
+  // the root box of the reference's tree is the union of the primitive bounds (:622-624; min / max: any order)
+  std::vector<bbox3f> part_box(nt, bbox3f{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}});
+  chunks([&](int t, int i0, int i1) {
+    bbox3f& acc = part_box[t];
     for (int i = i0; i < i1; i++) {
       bbox3f b;
       if (sh.is_points()) {
@@ -459,11 +462,14 @@ static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos
         b = triangle_bounds(P(sh.triangles[3 * i]), P(sh.triangles[3 * i + 1]), P(sh.triangles[3 * i + 2]));
       }
       prims[i] = {(b.min + b.max) / 2.0f, i};  // center(bbox), yocto_math.h:3008
+      acc = {min3(acc.min, b.min), max3(acc.max, b.max)};
     }
   });
+  root_bbox = part_box[0];
+  for (int t = 1; t < nt; t++) root_bbox = {min3(root_bbox.min, part_box[t].min), max3(root_bbox.max, part_box[t].max)};
   tie_nodes = reference_tree(prims.data(), 0, n, 0);
   ref_pos.assign(n, 0);
-  chunks([&](int i0, int i1) {
+  chunks([&](int, int i0, int i1) {
     for (int i = i0; i < i1; i++) ref_pos[prims[i].primitive] = i;
   });
 }
@@ -711,6 +717,14 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   float pad  = 2e-6f * sh.scale + 1e-30f;
   vec3f glo  = cmin - (rmax + pad), ghi = cmax + (rmax + pad);
   auto  step = [](float lo, float hi) { return fmax_((hi - lo) / 65534.0f, 1e-30f); };
+  // The boxes are padded by fold_pad_steps() grid steps and rounded outwards AFTER that; a box that touches the
+  // bounds of the shape must not lose that padding to the clamp at the ends of the grid (a ray grazing the outside
+  // face of a shape within half a step - every ray, for a flat shape such as a quad light - would miss it), so the grid
+  // extends past the padded bounds by the padding in space, 0.54 step + 0.53 (2 scale + extent) 2^-23, plus a step
+  // for the rounding, with some slack.
+  auto margin = [&](float lo, float hi) { return 2.0f * step(lo, hi) + 0.6f * (2.0f * sh.scale + (hi - lo)) / 8388608.0f; };
+  vec3f gm = {margin(glo.x, ghi.x), margin(glo.y, ghi.y), margin(glo.z, ghi.z)};
+  glo = glo - gm, ghi = ghi + gm;
   sh.grid_origin = glo;
   sh.grid_step   = {step(glo.x, ghi.x), step(glo.y, ghi.y), step(glo.z, ghi.z)};
   vec3f inv_step = {1.0f / sh.grid_step.x, 1.0f / sh.grid_step.y, 1.0f / sh.grid_step.z};
@@ -838,6 +852,18 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   return YH_OK;
 }
 
+// transform_bbox(frame, bbox), yocto_math.h:3172-3182: the exact form the reference feeds to its top-level builder
+static bbox3f transform_bbox_exact(const frame3f& f, const bbox3f& b) {
+  bbox3f out = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+  for (int c = 0; c < 8; c++) {  // corner order of the reference: x slowest ... any order gives the same min / max
+    vec3f p = {c & 4 ? b.max.x : b.min.x, c & 2 ? b.max.y : b.min.y, c & 1 ? b.max.z : b.min.z};
+    vec3f q = transform_point(f, p);
+    out.min = min3(out.min, q);
+    out.max = max3(out.max, q);
+  }
+  return out;
+}
+
 // transform_bbox(frame, bbox), yocto_math.h:3172-3182, plus padding
 static bbox3f transform_bbox_padded(const frame3f& f, const bbox3f& b) {
   bbox3f out = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
@@ -868,19 +894,76 @@ yh::dev_scene yh_scene::view() const {
   v.num_shapes = (int)shapes.size(), v.num_materials = (int)materials.size();
   v.num_objects = (int)objects.size(), v.num_textures = (int)textures.size();
   v.num_environments = (int)environments.size(), v.num_lights = (int)lights.size();
+  v.scene_nodes = d_scene_nodes.ptr, v.scene_prims = d_scene_prims.ptr, v.num_scene_nodes = (int)d_scene_nodes.count / 2;
   return v;
 }
+// The reference's top-level tree (init_bvh :793-814 -> build_bvh :601-650) over the objects: primitive = object,
+// bounds = transform_bbox(frame, root box of the shape's tree) or the invalid box for an empty shape, split_middle,
+// leaves of <= 4.  Only topology, split axes and leaf order are the reference's; the node boxes are unions of OUR
+// padded object bounds.
+static void build_scene_tree(const yh_scene* sc, std::vector<float4>& nodes, std::vector<int>& prims_out) {
+  int n = (int)sc->objects.size();
+  nodes.clear(), prims_out.clear();
+  if (n == 0) return;
+  std::vector<ref_prim> prims(n);
+  for (int i = 0; i < n; i++) {
+    const host_shape* s = sc->shapes[sc->objects[i].shape];
+    bbox3f b = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};  // invalidb3f
+    if (s->num_elems() > 0 && s->ties) b = transform_bbox_exact(sc->objects[i].frame, s->ties->root_bbox);
+    prims[i] = {(b.min + b.max) / 2.0f, i};
+  }
+  struct item { int node, start, end; };
+  std::vector<item> todo{{0, 0, n}};
+  nodes.resize(2);
+  while (!todo.empty()) {
+    item it = todo.back();
+    todo.pop_back();
+    bbox3f box = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
+    for (int i = it.start; i < it.end; i++) {
+      const bbox3f& ob = sc->objects[prims[i].primitive].bbox;
+      if (ob.min.x <= ob.max.x) box = {min3(box.min, ob.min), max3(box.max, ob.max)};
+    }
+    int a, b;
+    if (it.end - it.start > kRefLeafMax) {
+      int mid, axis;
+      reference_split(prims.data(), it.start, it.end, mid, axis);
+      a = (int)nodes.size() / 2, b = 0x100 | axis;
+      nodes.resize(nodes.size() + 4);
+      todo.push_back({a, it.start, mid});
+      todo.push_back({a + 1, mid, it.end});
+    } else {
+      a = it.start, b = (it.end - it.start) << 16;
+    }
+    auto bits = [](int v) { float f; memcpy(&f, &v, 4); return f; };
+    nodes[2 * it.node]     = make_float4(box.min.x, box.min.y, box.min.z, bits(a));
+    nodes[2 * it.node + 1] = make_float4(box.max.x, box.max.y, box.max.z, bits(b));
+  }
+  prims_out.resize(n);
+  for (int i = 0; i < n; i++) prims_out[i] = prims[i].primitive;
+}
+
 yh_status yh_scene::sync_ties() const {
   std::lock_guard<std::mutex> lock(tie_mutex);
-  if (!ties_pending) return YH_OK;
-  for (auto s : shapes) {
-    if (!s->tie_future.valid()) continue;
-    std::shared_ptr<const host_shape::tie_tables> t = s->tie_future.get();
-    YH_CUDA(s->d_ref_pos.upload(t->ref_pos.data(), t->ref_pos.size()));
-    YH_CUDA(s->d_tie_nodes.upload(t->tie_nodes.data(), t->tie_nodes.size()));
+  if (!ties_pending && !scene_tree_pending) return YH_OK;
+  auto self = const_cast<yh_scene*>(this);
+  if (ties_pending) {
+    for (auto s : shapes) {
+      if (!s->tie_future.valid()) continue;
+      s->ties = s->tie_future.get();
+      YH_CUDA(s->d_ref_pos.upload(s->ties->ref_pos.data(), s->ties->ref_pos.size()));
+      YH_CUDA(s->d_tie_nodes.upload(s->ties->tie_nodes.data(), s->ties->tie_nodes.size()));
+    }
+    ties_pending = false;
   }
-  ties_pending = false;
-  return upload_tables(const_cast<yh_scene*>(this));  // the shape table carries the new pointers
+  if (scene_tree_pending) {  // needs the objects' padded bounds (init_bvh) and the shapes' exact root boxes (tie tables)
+    std::vector<float4> nodes;
+    std::vector<int>    prims;
+    build_scene_tree(this, nodes, prims);
+    YH_CUDA(self->d_scene_nodes.upload(nodes.data(), nodes.size()));
+    YH_CUDA(self->d_scene_prims.upload(prims.data(), prims.size()));
+    scene_tree_pending = false;
+  }
+  return upload_tables(self);  // the tables carry the new pointers
 }
 
 yh_scene::~yh_scene() {
@@ -1003,7 +1086,7 @@ yh_status yh::scene_create(const yh_scene_desc* d, const yh_scene* ties_from, yh
     }
     hs->tie_future = std::async(std::launch::async, [hs]() -> std::shared_ptr<const host_shape::tie_tables> {
       auto t = std::make_shared<host_shape::tie_tables>();
-      reference_tree_order(*hs, t->ref_pos, t->tie_nodes);
+      reference_tree_order(*hs, t->ref_pos, t->tie_nodes, t->root_bbox);
       return t;
     }).share();
   }
@@ -1085,6 +1168,10 @@ yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
   for (auto& o : sc->objects)
     if (o.bbox.min.x <= o.bbox.max.x) sc->world_bbox = {min3(sc->world_bbox.min, o.bbox.min), max3(sc->world_bbox.max, o.bbox.max)};
   if (!(sc->world_bbox.min.x <= sc->world_bbox.max.x)) sc->world_bbox = {{0, 0, 0}, {0, 0, 0}};
+  {
+    std::lock_guard<std::mutex> lock(sc->tie_mutex);
+    sc->scene_tree_pending = true;  // its node boxes are unions of the bounds just computed
+  }
   sc->bvh_built = true;
   return upload_tables(sc);
 }

@@ -114,6 +114,15 @@ struct dev_light {
 };
 
 struct dev_scene {
+  // Top-level tree over the objects: the REFERENCE's topology (build_bvh over the objects' world bounds with
+  // split_middle, leaves of <= 4 objects, yocto_pathtrace.cpp:597-650, :793-814), so the traversal visits objects in
+  // the reference's order and an exact-t tie between two objects goes to the one it would keep.  Node k = two float4:
+  //   {box.min.xyz, a}, {box.max.xyz, b}   inner: a = first child (the second follows), b = 0x100 | split axis
+  //                                        leaf : a = first entry in scene_prims,       b = object count << 16
+  // Boxes are the unions of the objects' padded bounds (conservative).
+  const float4*          scene_nodes;
+  const int*             scene_prims;
+  int                    num_scene_nodes;
   const dev_shape*       shapes;
   const dev_material*    materials;
   const dev_object*      objects;
@@ -149,7 +158,9 @@ struct host_shape {
   struct tie_tables {
     std::vector<int>  ref_pos;
     std::vector<int4> tie_nodes;
+    bbox3f            root_bbox;  // the reference's shape->bvh->nodes[0].bbox: exact union of the primitive bounds
   };
+  std::shared_ptr<const tie_tables> ties;  // set once the future was joined (sync_ties)
   // shared: the replicas of one scene on several devices (yh_group) compute the tables once
   std::shared_future<std::shared_ptr<const tie_tables>> tie_future;
   ~host_shape() {
@@ -176,6 +187,9 @@ struct yh_scene {
   yh::dev_buffer<yh::dev_texture>     d_textures;
   yh::dev_buffer<yh::dev_environment> d_environments;
   yh::dev_buffer<yh::dev_light>       d_lights;
+  yh::dev_buffer<float4>              d_scene_nodes;  // top-level tree (dev_scene::scene_nodes)
+  yh::dev_buffer<int>                 d_scene_prims;
+  mutable bool                        scene_tree_pending = true;  // (re)built by sync_ties after init_bvh
   bool bvh_built = false, lights_built = false;
   bool has_volumes = false;  // some material is refractive (!thin && transmission): paths carry a volume state
   int  device = 0;

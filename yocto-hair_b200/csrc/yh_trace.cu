@@ -1062,6 +1062,17 @@ yh_status yh_state_download(const yh_state* cst, float* render, float* accum, in
   return YH_OK;
 }
 
+yh_status yh_resolve_dev(const float* accum_dev, const int* samples_dev, int64_t num_pixels, float* render_dev) {
+  YH_REQUIRE_DEVICE();
+  if (num_pixels < 0 || num_pixels > 0x7fffffff || (num_pixels > 0 && (!accum_dev || !samples_dev || !render_dev)))
+    return fail(YH_ERR_INVALID, "yh_resolve_dev: bad argument");
+  if (num_pixels == 0) return YH_OK;
+  k_resolve<<<(int)((num_pixels + 255) / 256), 256>>>((const float4*)accum_dev, samples_dev, (float4*)render_dev, (int)num_pixels);
+  YH_CUDA(cudaGetLastError());
+  YH_CUDA(cudaStreamSynchronize(0));
+  return YH_OK;
+}
+
 yh_status yh_state_buffers_dev(yh_state* st, float** accum_dev, int** samples_dev) {
   if (!st) return fail(YH_ERR_INVALID, "yh_state_buffers_dev: state is null");
   if (accum_dev) *accum_dev = (float*)st->accum.ptr;

@@ -1,5 +1,6 @@
-// Closest-hit traversal of the two-level scene: objects (linear, bounds
-// culled) -> shape LBVH (yh_scene.cuh layout).  Restates intersect_scene_bvh /
+// Closest-hit traversal of the two-level scene: objects (the reference's own
+// top-level tree, so objects are visited in its order) -> shape LBVH
+// (yh_scene.cuh layout).  Restates intersect_scene_bvh /
 // intersect_shape_bvh (yocto_pathtrace.cpp:821-1028): the ray is taken to
 // object space with inverse(frame, non_rigid = true), the direction is NOT
 // renormalised (t is preserved), and every primitive test is the reference's
@@ -66,6 +67,9 @@ struct trav_stack {
     limit = base + kStackShared * kStackStride;
     local = local_array;
   }
+  // `base` is the floor of the shape walk in progress; the entries between floor() and base belong to the walk over
+  // the top-level tree (scene nodes and objects still to visit), which only runs while no shape is open
+  __device__ __forceinline__ unsigned floor() const { return limit - kStackShared * kStackStride; }
   __device__ __forceinline__ bool     empty() const { return top == base; }
   __device__ __forceinline__ void     clear() { top = base; }
   __device__ __forceinline__ unsigned mark() const { return top; }
@@ -554,7 +558,17 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
           ray3f wr;
           int   handle;
           if (index < n && io.load(index, handle, wr)) {
-            have = true, cur = kTraverseDone, st.clear(), park_top = park_base;
+            have = true, cur = kTraverseDone, park_top = park_base;
+            // the walk over the top-level tree starts at its root; a tree that is ONE leaf (<= 4 objects, the hair
+            // scenes) is unrolled here: its objects in order, no box test of its own
+            st.base = st.top = st.floor();
+            if (sc.num_scene_nodes == 1) {
+              const int count = __float_as_int(__ldg(&sc.scene_nodes[1].w)) >> 16;
+              for (int k = count - 1; k >= 0; k--) st.push(~__ldg(sc.scene_prims + k));
+            } else if (sc.num_scene_nodes > 1) {
+              st.push(0);
+            }
+            st.base = st.top;
             put(CW_TMIN, wr.tmin), put(CW_TMAX, wr.tmax);
             cw(CW_HANDLE) = handle, cw(CW_OBJ) = -1, cw(CW_FLAGS) = 0;
             cw(CW_BOBJ) = -1, cw(CW_BELEM) = -1, put(CW_BU, 0), put(CW_BV, 0), put(CW_BDIST, 0);
@@ -616,14 +630,35 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         cw(CW_BOBJ) = obj, cw(CW_BELEM) = __ldg(shape_ptr()->slot_elem + cw(CW_REF));
         cw(CW_BU) = cw(CW_U), cw(CW_BV) = cw(CW_V), put(CW_BDIST, tmax);
         flags = (flags & ~1) | 2;
-        if (find_any) obj = sc.num_objects;
+        if (find_any) st.base = st.top = st.floor();  // any hit ends the walk
       }
       vec3f wo, wd;
       io.reload(handle, wo, wd);
       bool opened = false;
-      while (++obj < sc.num_objects) {
+      // intersect_scene_bvh, :960-1028: depth-first over the top-level tree, the child on the ray's near side of the
+      // split axis first, the objects of a leaf in order.  Entries >= 0 are nodes, < 0 objects (~index).
+      while (st.base != st.floor()) {
+        st.top = st.base;
+        const int entry = st.pop();
+        st.base = st.top;
+        ray3f wr = {wo, wd, tmin, tmax};
+        if (entry >= 0) {
+          const float4 lo = __ldg(&sc.scene_nodes[2 * entry]), hi = __ldg(&sc.scene_nodes[2 * entry + 1]);
+          if (!hits_box(wr, {{lo.x, lo.y, lo.z}, {hi.x, hi.y, hi.z}})) continue;
+          const int a = __float_as_int(lo.w), b = __float_as_int(hi.w);
+          if (b & 0x100) {
+            const int  axis = b & 3;
+            const float dc  = axis == 0 ? wd.x : (axis == 1 ? wd.y : wd.z);
+            if ((1.0f / dc) < 0) st.push(a), st.push(a + 1);  // :983-989
+            else st.push(a + 1), st.push(a);
+          } else {
+            for (int k = (b >> 16) - 1; k >= 0; k--) st.push(~__ldg(sc.scene_prims + a + k));
+          }
+          st.base = st.top;
+          continue;
+        }
+        obj = ~entry;
         const dev_object& ob = sc.objects[obj];
-        ray3f             wr = {wo, wd, tmin, tmax};
         if (!hits_box(wr, ob.bbox)) continue;
         const dev_shape& sh = sc.shapes[ob.shape];
         if (sh.num_refs == 0) continue;

@@ -142,6 +142,7 @@ PROTOTYPES = {
     "yh_state_set_profiling": (C.c_int, [_P, C.c_int]),
     "yh_state_download": (C.c_int, [_P, _P, _P, _P]),
     "yh_state_buffers_dev": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "yh_resolve_dev": (C.c_int, [_P, _P, C.c_int64, _P]),
     "yh_state_download_rng": (C.c_int, [_P, _P]),
     "yh_group_create": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BvhParams), c_int_p, C.c_int, C.POINTER(_P)]),
     "yh_group_destroy": (None, [_P]),

@@ -54,15 +54,28 @@ def state_tensors(state, device):
     return accum, samples
 
 
-def reduce_image(accum, samples, dst: int = 0):
-    """The one collective of a render: sum of the per-rank accumulation and
-    sample-count buffers on rank `dst` (every pixel is non-zero on exactly one
-    rank, so the sum is exact).  Works on CUDA tensors (nccl) and CPU tensors (gloo)."""
+def reduce_image(accum, samples, dst: int = 0, out=None):
+    """The one collective of a render: the per-rank accumulation and sample-count buffers summed on rank `dst`.
+    Tile shards: every pixel is non-zero on exactly one rank, so the sum is exact; sample shards: the sum of the
+    ranks' partial images.  The inputs (views of library-owned buffers) are left untouched - the sum goes into
+    scratch tensors (`out`, or fresh ones), so tracing on and reducing again does not count anything twice.
+    Works on CUDA tensors (nccl) and CPU tensors (gloo).  Returns (accum_sum, samples_sum), valid on `dst`."""
     import torch.distributed as dist
+    a, s = out if out is not None else (accum.clone(), samples.clone())
+    if out is not None:
+        a.copy_(accum), s.copy_(samples)
     if dist.is_initialized() and dist.get_world_size() > 1:
-        dist.reduce(accum, dst, op=dist.ReduceOp.SUM)
-        dist.reduce(samples, dst, op=dist.ReduceOp.SUM)
-    return accum, samples
+        dist.reduce(a, dst, op=dist.ReduceOp.SUM)
+        dist.reduce(s, dst, op=dist.ReduceOp.SUM)
+    return a, s
+
+
+def resolve_dev(accum, samples, render):
+    """state->render = accumulated / samples with the library's kernel (yh_resolve_dev) on CUDA tensors."""
+    import torch
+    torch.cuda.current_stream().synchronize()
+    capi.check(capi.load().yh_resolve_dev(accum.data_ptr(), samples.data_ptr(), samples.numel(), render.data_ptr()))
+    return render
 
 
 def resolve(accum, samples):

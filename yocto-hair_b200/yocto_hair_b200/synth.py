@@ -179,7 +179,7 @@ def _hair_camera():
 HAIR_FRAME = (-1, 0, 0, 0, 1, 0, 0, 0, -1, 0, 0, 0)  # object frame of both hair JSONs
 
 
-def straight_hair_scene(num_segments=250_000, seed=7, sky=True, area_lights=True, eumelanin=1.3):
+def straight_hair_scene(num_segments=250_000, seed=7, sky=True, area_lights=True, eumelanin=1.3, sky_size=(512, 256)):
     """Config C2.  sky=True uses the procedural sky texture (stand-in for sky.hdr)."""
     sc = Scene()
     sc.shapes.append(make_straight_hair(num_segments, seed))
@@ -191,21 +191,21 @@ def straight_hair_scene(num_segments=250_000, seed=7, sky=True, area_lights=True
         for eye in ((-5, 20, 10), (5, 20, 10)):
             sc.objects.append(Object(shape=1, material=1, frame=lookat_frame(eye, (0, 9.5, 0), (0, 1, 0), inv_xz=True)))
     if sky:
-        sc.textures.append(make_sky_texture())
+        sc.textures.append(make_sky_texture(*sky_size))
         sc.environments.append(Environment(emission=(1, 1, 1), emission_tex=0))
     else:
         sc.environments.append(Environment(emission=(1, 1, 1)))
     return sc, _hair_camera()
 
 
-def curly_hair_scene(num_segments=1_000_000, seed=7, sky=True, sigma_a=(0.06, 0.10, 0.20)):
+def curly_hair_scene(num_segments=1_000_000, seed=7, sky=True, sigma_a=(0.06, 0.10, 0.20), sky_size=(512, 256)):
     """Config C3 / C5: blonde curly hair under the sky environment."""
     sc = Scene()
     sc.shapes.append(make_curly_hair(num_segments, seed))
     sc.materials.append(Material(sigma_a=sigma_a))
     sc.objects.append(Object(shape=0, material=0, frame=HAIR_FRAME))
     if sky:
-        sc.textures.append(make_sky_texture())
+        sc.textures.append(make_sky_texture(*sky_size))
         sc.environments.append(Environment(emission=(2.5, 2.5, 2.5), emission_tex=0))
     else:
         sc.environments.append(Environment(emission=(2.5, 2.5, 2.5)))
@@ -387,4 +387,40 @@ def points_scene(num_points=20_000, num_segments=6_000, seed=9, sky=True, **poin
     else:
         sc.environments.append(Environment(emission=(1, 1, 1)))
     cam = Camera.from_lookat((0.0, 1.6, 5.0), (0.0, 0.6, 0.0), (0, 1, 0), lens=0.05, aspect=1.5)
+    return sc, cam
+
+
+def instanced_curls_scene(side=(10, 10, 10), num_segments=1_500, coincident=3, seed=7, sky=True):
+    """Instance-heavy scene (sloth / bold-man scale in object count): side[0] x side[1] x side[2] objects share ONE hair
+    lock on an exact lattice - centres coincide with the split planes of the reference's top-level tree, the case in
+    which its visiting order decides - and `coincident` of them are doubled by objects with IDENTICAL frames but other
+    materials, so every hit on those is an exact-t tie BETWEEN objects (the reference keeps the one its scene tree
+    visits last, yocto_pathtrace.cpp:1003-1011)."""
+    sc = Scene()
+    sc.shapes.append(make_hair_curl(num_segments, seed))
+    sc.shapes.append(make_arealight_quad())
+    for mat in (dict(eumelanin=8.0), dict(pheomelanin=2.0), dict(eumelanin=1.3), dict(eumelanin=0.3)):
+        sc.materials.append(Material(**mat))
+    sc.materials.append(Material(emission=(20, 20, 20)))
+    k = 0
+    frames = []
+    for ix in range(side[0]):
+        for iy in range(side[1]):
+            for iz in range(side[2]):
+                s = 0.25
+                frames.append((s, 0, 0, 0, s, 0, 0, 0, s, 1.0 * ix, 2.0 * iy, 1.0 * iz))
+    for f in frames:
+        sc.objects.append(Object(shape=0, material=k % 4, frame=f))
+        k += 1
+    rng = np.random.default_rng(seed)
+    for j in rng.choice(len(frames), size=min(coincident, len(frames)), replace=False):
+        sc.objects.append(Object(shape=0, material=(sc.objects[int(j)].material + 1) % 4, frame=frames[int(j)]))
+    cx, cy, cz = (side[0] - 1) / 2, side[1] - 0.1, (side[2] - 1) / 2
+    sc.objects.append(Object(shape=1, material=4, frame=lookat_frame((cx, 2.0 * side[1] + 6, cz + 4), (cx, cy, cz), (0, 1, 0), inv_xz=True)))
+    if sky:
+        sc.textures.append(make_sky_texture())
+        sc.environments.append(Environment(emission=(1, 1, 1), emission_tex=0))
+    else:
+        sc.environments.append(Environment(emission=(1, 1, 1)))
+    cam = Camera.from_lookat((cx + 1.3 * side[0], 1.4 * side[1] + 2, cz + 2.2 * side[2] + 4), (cx, side[1] * 0.9, cz), (0, 1, 0), lens=0.05, aspect=1.5)
     return sc, cam
