@@ -236,6 +236,15 @@ yh_status yh_state_set_shard(yh_state* state, int rank, int world);
  * world = 1 counter-mode image up to fp32 summation order.  world = 1 is valid
  * (counter mode on one device).  Resets the accumulation.                     */
 yh_status yh_state_set_sample_shard(yh_state* state, int rank, int world);
+/* Counter mode only: `slots_per_pixel` path slots per pixel (0 = as many as fill
+ * the device, <= 8).  Samples of one pixel are independent in counter mode, so
+ * lane k of a pixel traces the sample ordinals k, k + S, ... concurrently with
+ * the other lanes - the wavefront is S times wider, which is what a small image
+ * (or a GPU's share of one) needs to fill 148 SMs.  Every lane adds into its own
+ * partial image; the partials are folded into the accumulation buffer in lane
+ * order after each yh_trace_samples call, so results are deterministic (they
+ * equal the one-slot image up to fp32 summation order).  Resets the accumulation. */
+yh_status yh_state_set_sample_slots(yh_state* state, int slots_per_pixel);
 /* The ownership map behind yh_state_set_shard, host only (needs no device):
  * writes the image pixel indices (j * width + i) owned by `rank` of `world`,
  * in slot order, to `pixels` (may be null) and their number to `count`.

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Batched hair-BSDF, PCG32 and libm entry points of the C ABI (test and
 // measurement surface for rows E1-E15 / M1 of SURVEY.md section 8a).
 #include <cmath>
@@ -46,6 +47,10 @@ void pool_keep_memory() {
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   done_for = dev;
+}
+bool plain_allocations() {
+  static const bool plain = getenv("YH_NO_POOL") != nullptr;
+  return plain;
 }
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
@@ -448,6 +453,7 @@ yh_status yh_dev_free(void* ptr) {
 yh_status yh_dev_upload(void* dst_dev, const void* src_host, int64_t bytes) {
   YH_REQUIRE_DEVICE();
   YH_CUDA(cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+  YH_CUDA(cudaStreamSynchronize(0));  // pageable source: the DMA may still be in flight when cudaMemcpy returns
   return YH_OK;
 }
 yh_status yh_dev_download(void* dst_host, const void* src_dev, int64_t bytes) {

@@ -30,6 +30,9 @@ bool         require_device();
 
 // raises the release threshold of the current device's default memory pool (once per device)
 void pool_keep_memory();
+// YH_NO_POOL=1: cudaMalloc / cudaFree instead of the stream-ordered pool (diagnostics: compute-sanitizer then sees
+// the bounds of every buffer)
+bool plain_allocations();
 
 // device buffer with RAII (host-side owner)
 template <typename T>
@@ -45,7 +48,10 @@ struct dev_buffer {
   // keeps freed blocks (see pool_keep_memory()), so re-creating a scene or state does not pay
   // cudaMalloc / cudaFree's map / unmap cost again (they were seen to take 100s of ms).
   void release() {
-    if (ptr) cudaFreeAsync(ptr, 0);
+    if (ptr) {
+      if (plain_allocations()) cudaFree(ptr);
+      else cudaFreeAsync(ptr, 0);
+    }
     ptr   = nullptr;
     count = 0;
   }
@@ -53,6 +59,7 @@ struct dev_buffer {
     release();
     count = n;
     if (n == 0) return cudaSuccess;
+    if (plain_allocations()) return cudaMalloc((void**)&ptr, n * sizeof(T));  // exact bounds for compute-sanitizer
     pool_keep_memory();
     cudaError_t e = cudaMallocAsync((void**)&ptr, n * sizeof(T), 0);
     if (e != cudaSuccess) return e;
@@ -61,7 +68,13 @@ struct dev_buffer {
   cudaError_t upload(const T* host, size_t n) {
     cudaError_t e = alloc(n);
     if (e != cudaSuccess || n == 0) return e;
-    return cudaMemcpy(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    e = cudaMemcpy(ptr, host, n * sizeof(T), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    // cudaMemcpy from PAGEABLE host memory returns once the data sits in the driver's staging buffers; the DMA into
+    // `ptr` is ordered only against the legacy stream.  The consumers here launch on cudaStreamNonBlocking streams,
+    // which do not wait for it (seen: k_init_slots reading the pixel map of a 720 x 405 state before it had landed),
+    // so drain the legacy stream before anyone may use the buffer.
+    return cudaStreamSynchronize(0);
   }
   size_t bytes() const { return count * sizeof(T); }
 };

@@ -769,6 +769,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
     int zero = 0;
     YH_CUDA(cudaMemcpy(sh.d_slots.ptr, rec, 32, cudaMemcpyHostToDevice));
     YH_CUDA(cudaMemcpy(sh.d_slot_elem.ptr, &zero, 4, cudaMemcpyHostToDevice));
+    YH_CUDA(cudaStreamSynchronize(0));
     return YH_OK;
   }
   sh.root_leaf = 0;

@@ -52,7 +52,15 @@ struct path_state {
   float4*             vol_density;  // vsdf.density.xyz, vsdf.anisotropy
   float4*             vol_scatter;  // vsdf.scatter.xyz, 1 while the path is inside the volume (0: stack empty)
   float*              hit_dist;     // intersection.distance of the current vertex
+  // only with several slots per pixel (counter mode, yh_state_set_sample_slots; else null): lane k of a pixel draws the
+  // sample ordinals k, k + S, ... and adds into its own partial image, folded into accum in lane order after the call
+  int*                ordinal;          // next sample ordinal of the slot
+  float4*             partial;          // S x image
+  int*                partial_samples;  // S x image
+  int                 num_pixels;
 };
+// pixel[slot] = image pixel | lane << 24
+constexpr int kPixelMask = 0x00ffffff;
 
 struct queues {
   int* active[2];  // slot ids
@@ -71,6 +79,7 @@ struct trace_consts {
   // counter mode (yh_state_set_sample_shard): sample s of a pixel draws from its own PCG32
   // stream make_rng(seed, seq_pixel + (s << 31)); this state renders s = srank, srank + sworld, ...
   int                counter, srank, sworld;
+  int                slots;  // slots per pixel (1 unless yh_state_set_sample_slots)
   unsigned long long seed;
   int                shader;  // YH_SHADER_*: trace_naive / trace_path / trace_eyelight / trace_normal (:1380-1657)
 };
@@ -119,12 +128,16 @@ __device__ __forceinline__ void start_sample(const path_state& ps, const dev_cam
   if (tc.counter) {
     // make_rng(seed, seq) (yocto_math.h:1419-1427) in closed form: inc = (seq << 1) | 1,
     // state = (inc + seed) * mult + inc; seq = seq_pixel + (s << 31) shifts inc by s << 32
+    if (ps.ordinal) {  // this slot's own ordinals: k, k + S, ...
+      samples_done = ld_stream(&ps.ordinal[slot]);
+      st_stream(&ps.ordinal[slot], samples_done + tc.slots);
+    }
     unsigned long long sidx = (unsigned long long)tc.srank + (unsigned long long)tc.sworld * (unsigned long long)samples_done;
     rng.inc   = ld_stream(&ps.rng_base[slot]) + (sidx << 32);
     rng.state = (rng.inc + tc.seed) * 6364136223846793005ULL + rng.inc;
     st_stream(&ps.rng_inc[slot], rng.inc);
   }
-  ray3f ray       = camera_ray(cam, tc, ld_stream(&ps.pixel[slot]), rng);
+  ray3f ray       = camera_ray(cam, tc, ld_stream(&ps.pixel[slot]) & kPixelMask, rng);
   st_stream(&ps.ray_o[slot], make_float4(ray.o.x, ray.o.y, ray.o.z, 0));
   st_stream(&ps.ray_d[slot], make_float4(ray.d.x, ray.d.y, ray.d.z, 0));
   st_stream(&ps.weight[slot], make_float4(1, 1, 1, 0));
@@ -138,12 +151,18 @@ __device__ __forceinline__ bool finish_sample(const path_state& ps, const dev_ca
   if (!isfinite3(radiance)) radiance = {0, 0, 0};
   float m = max3(radiance);
   if (m > tc.clamp) radiance = radiance * div_(tc.clamp, m);
-  int    px = ld_stream(&ps.pixel[slot]);
-  float4 a  = ld_stream(&ps.accum[px]);
+  int     px      = ld_stream(&ps.pixel[slot]);
+  float4* accum   = ps.accum;
+  int*    samples = ps.samples;
+  if (ps.partial) {  // lane (px >> 24) of the pixel owns one image of the partial stack
+    size_t lane = (size_t)(px >> 24) * (size_t)ps.num_pixels;
+    accum = ps.partial + lane, samples = ps.partial_samples + lane, px &= kPixelMask;
+  }
+  float4 a  = ld_stream(&accum[px]);
   a.x += radiance.x, a.y += radiance.y, a.z += radiance.z, a.w += alpha;
-  st_stream(&ps.accum[px], a);
-  int done = ld_stream(&ps.samples[px]) + 1;
-  st_stream(&ps.samples[px], done);
+  st_stream(&accum[px], a);
+  int done = ld_stream(&samples[px]) + 1;
+  st_stream(&samples[px], done);
   int left = ld_stream(&ps.remaining[slot]);
   if (left > 0) {
     st_stream(&ps.remaining[slot], left - 1);
@@ -154,28 +173,38 @@ __device__ __forceinline__ bool finish_sample(const path_state& ps, const dev_ca
 }
 
 __global__ void __launch_bounds__(256) k_start(path_state ps, queues q, dev_camera cam, trace_consts tc,
-    int num_slots, int num_samples) {
+    int num_slots, int num_samples, int ordinal_base) {
   int  slot = blockIdx.x * blockDim.x + threadIdx.x;
   bool live = slot < num_slots && num_samples > 0;
+  if (live && ps.ordinal) {  // lane k of a pixel takes the ordinals base + k, base + k + S, ... < base + num_samples
+    int lane    = ld_stream(&ps.pixel[slot]) >> 24;
+    num_samples = num_samples > lane ? (num_samples - lane + tc.slots - 1) / tc.slots : 0;
+    st_stream(&ps.ordinal[slot], ordinal_base + lane);
+    live = num_samples > 0;
+  }
   if (live) {
     rng_state rng = {ld_stream(&ps.rng_state[slot]), ld_stream(&ps.rng_inc[slot])};
     if (tc.bounces <= 0 && (tc.shader == YH_SHADER_PATH || tc.shader == YH_SHADER_NAIVE)) {
       // the path loop (:1395, :1524) never runs: black sample, alpha 0, camera draws still consumed
-      int px = ld_stream(&ps.pixel[slot]), done = ld_stream(&ps.samples[px]);
+      int  px = ld_stream(&ps.pixel[slot]) & kPixelMask;
+      int* samples = ps.partial ? ps.partial_samples + (size_t)(ld_stream(&ps.pixel[slot]) >> 24) * (size_t)ps.num_pixels : ps.samples;
+      int  done = ld_stream(&samples[px]);
       for (int s = 0; s < num_samples; s++) {
         if (tc.counter) {  // same re-seed as start_sample
-          unsigned long long sidx = (unsigned long long)tc.srank + (unsigned long long)tc.sworld * (unsigned long long)(done + s);
+          unsigned long long ord = ps.ordinal ? (unsigned long long)(ordinal_base + (ld_stream(&ps.pixel[slot]) >> 24) + s * tc.slots)
+                                              : (unsigned long long)(done + s);
+          unsigned long long sidx = (unsigned long long)tc.srank + (unsigned long long)tc.sworld * ord;
           rng.inc   = ld_stream(&ps.rng_base[slot]) + (sidx << 32);
           rng.state = (rng.inc + tc.seed) * 6364136223846793005ULL + rng.inc;
           st_stream(&ps.rng_inc[slot], rng.inc);
         }
         camera_ray(cam, tc, px, rng);
       }
-      st_stream(&ps.samples[px], done + num_samples);
+      st_stream(&samples[px], done + num_samples);
       live = false;
     } else {
       st_stream(&ps.remaining[slot], num_samples - 1);
-      start_sample(ps, cam, tc, slot, rng, ld_stream(&ps.samples[ld_stream(&ps.pixel[slot])]));
+      start_sample(ps, cam, tc, slot, rng, ld_stream(&ps.samples[ld_stream(&ps.pixel[slot]) & kPixelMask]));
     }
     st_stream(&ps.rng_state[slot], rng.state);
   }
@@ -540,15 +569,33 @@ __host__ __device__ inline rng_state rng_skip(rng_state rng, unsigned long long 
 __global__ void k_init_slots(path_state ps, const int* slot_pixel, int num_slots, unsigned long long seed) {
   int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= num_slots) return;
-  int       px     = slot_pixel[slot];
+  int       px     = slot_pixel[slot] & kPixelMask;
   rng_state master = rng_skip(make_rng(1301081), (unsigned long long)px);
   uint32_t  r      = advance_rng(master) & 0x7fffffffu;  // % (1 << 31)
   rng_state rng    = make_rng(seed, (uint64_t)(r / 2 + 1));
   st_stream(&ps.rng_state[slot], rng.state);
   st_stream(&ps.rng_inc[slot], rng.inc);
   st_stream(&ps.rng_base[slot], rng.inc);
-  st_stream(&ps.pixel[slot], px);
+  st_stream(&ps.pixel[slot], slot_pixel[slot]);
   st_stream(&ps.remaining[slot], 0);
+}
+
+// several slots per pixel: the lanes' partial images into the accumulation buffer, in lane order (deterministic)
+__global__ void __launch_bounds__(256) k_fold_partials(float4* accum, int* samples, float4* partial, int* partial_samples, int n, int lanes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 a = accum[i];
+  int    s = samples[i];
+  for (int k = 0; k < lanes; k++) {
+    size_t j = (size_t)k * n + i;
+    float4 b = partial[j];
+    a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
+    s += partial_samples[j];
+    partial[j]         = make_float4(0, 0, 0, 0);
+    partial_samples[j] = 0;
+  }
+  accum[i]   = a;
+  samples[i] = s;
 }
 
 __global__ void k_resolve(const float4* accum, const int* samples, float4* render, int n) {
@@ -655,6 +702,11 @@ struct yh_state {
   int             rank = 0, world = 1;
   bool            counter = false;          // per-sample streams (yh_state_set_sample_shard)
   int             srank = 0, sworld = 1;    // sample indices srank, srank + sworld, ... are rendered here
+  int             slots_per_pixel = 1;      // counter mode only (yh_state_set_sample_slots)
+  int             ordinal_base = 0;         // sample ordinals handed out so far (several slots per pixel)
+  int             num_owned = 0;            // owned pixels (num_slots = num_owned * slots_per_pixel)
+  dev_buffer<int>    ordinal, partial_samples;
+  dev_buffer<float4> partial;
   dev_buffer<float4>             ray_o, ray_d, weight, radiance, accum, render, vol_density, vol_scatter;
   dev_buffer<float>              hit_dist;
   dev_buffer<int4>               hit;
@@ -671,7 +723,8 @@ struct yh_state {
     return {ray_o.ptr + first, ray_d.ptr + first, weight.ptr + first, radiance.ptr + first, hit.ptr + first,
         rng_state.ptr + first, rng_inc.ptr + first, rng_base.ptr + first, remaining.ptr + first, pixel.ptr + first,
         accum.ptr, samples.ptr, vol_density.ptr ? vol_density.ptr + first : nullptr,
-        vol_scatter.ptr ? vol_scatter.ptr + first : nullptr, hit_dist.ptr ? hit_dist.ptr + first : nullptr};
+        vol_scatter.ptr ? vol_scatter.ptr + first : nullptr, hit_dist.ptr ? hit_dist.ptr + first : nullptr,
+        ordinal.ptr ? ordinal.ptr + first : nullptr, partial.ptr, partial_samples.ptr, width * height};
   }
   void drain() {  // nothing of this state is in flight afterwards
     for (auto g : groups)
@@ -732,6 +785,29 @@ static yh_status assign_slots(yh_state* st) {
   if (ngroups > 8) ngroups = 8;
   std::vector<int> first;
   std::vector<int> px = owned_pixels(st->width, st->height, st->rank, st->world, ngroups, &first);
+  st->num_owned = (int)px.size();
+  int S = st->counter ? st->slots_per_pixel : 1;
+  if ((size_t)st->width * st->height > (size_t)kPixelMask) S = 1;  // the lane lives in the top byte of the pixel word
+  st->slots_per_pixel = S;
+  st->ordinal_base    = 0;
+  st->ordinal.release(), st->partial.release(), st->partial_samples.release();
+  if (S > 1) {  // lane-major inside a group: lane k of all its pixels, then lane k + 1 (warps keep compact pixel bundles)
+    std::vector<int> wide, wfirst(1, 0);
+    wide.reserve(px.size() * S);
+    for (int g = 0; g < ngroups; g++) {
+      for (int k = 0; k < S; k++)
+        for (int i = first[g]; i < first[g + 1]; i++) wide.push_back(px[i] | (k << 24));
+      wfirst.push_back((int)wide.size());
+    }
+    px.swap(wide), first.swap(wfirst);
+    size_t np = (size_t)st->width * st->height;
+    YH_CUDA(st->ordinal.alloc(px.size() ? px.size() : 1));
+    YH_CUDA(st->partial.alloc(np * S));
+    YH_CUDA(st->partial_samples.alloc(np * S));
+    YH_CUDA(cudaMemset(st->partial.ptr, 0, st->partial.bytes()));
+    YH_CUDA(cudaMemset(st->partial_samples.ptr, 0, st->partial_samples.bytes()));
+    YH_CUDA(cudaDeviceSynchronize());
+  }
   st->num_slots       = (int)px.size();
   size_t n            = px.size() ? px.size() : 1;
   YH_CUDA(st->ray_o.alloc(n));
@@ -844,7 +920,7 @@ yh_status yh_state_set_shard(yh_state* st, int rank, int world) {
   YH_REQUIRE_DEVICE();
   if (!st || world <= 0 || rank < 0 || rank >= world) return fail(YH_ERR_INVALID, "yh_state_set_shard: bad rank/world");
   st->rank = rank, st->world = world;
-  st->counter = false, st->srank = 0, st->sworld = 1;
+  st->counter = false, st->srank = 0, st->sworld = 1, st->slots_per_pixel = 1;
   cudaMemset(st->accum.ptr, 0, st->accum.bytes());
   cudaMemset(st->samples.ptr, 0, st->samples.bytes());
   cudaDeviceSynchronize();
@@ -856,6 +932,22 @@ yh_status yh_state_set_sample_shard(yh_state* st, int rank, int world) {
   if (!st || world <= 0 || rank < 0 || rank >= world) return fail(YH_ERR_INVALID, "yh_state_set_sample_shard: bad rank/world");
   st->rank = 0, st->world = 1;  // every pixel is rendered here ...
   st->counter = true, st->srank = rank, st->sworld = world;  // ... for the sample indices of this rank
+  cudaMemset(st->accum.ptr, 0, st->accum.bytes());
+  cudaMemset(st->samples.ptr, 0, st->samples.bytes());
+  cudaDeviceSynchronize();
+  return assign_slots(st);
+}
+
+yh_status yh_state_set_sample_slots(yh_state* st, int slots_per_pixel) {
+  YH_REQUIRE_DEVICE();
+  if (!st || slots_per_pixel < 0 || slots_per_pixel > 64) return fail(YH_ERR_INVALID, "yh_state_set_sample_slots: bad argument");
+  if (!st->counter) return fail(YH_ERR_STATE, "yh_state_set_sample_slots: counter mode only (call yh_state_set_sample_shard first)");
+  if (slots_per_pixel == 0) {  // enough paths in flight to fill the device: ~2 M
+    long long np = (long long)st->width * st->height;
+    slots_per_pixel = (int)std::min<long long>(8, std::max<long long>(1, (2000000 + np - 1) / std::max<long long>(1, np)));
+  }
+  st->slots_per_pixel = slots_per_pixel;
+  st->drain();
   cudaMemset(st->accum.ptr, 0, st->accum.bytes());
   cudaMemset(st->samples.ptr, 0, st->samples.bytes());
   cudaDeviceSynchronize();
@@ -897,7 +989,7 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
   }
   dev_scene    sc = st->scene->view();
   trace_consts tc = {st->width, st->height, st->params.bounces, st->params.clamp, st->counter ? 1 : 0, st->srank, st->sworld,
-      (unsigned long long)st->params.seed, st->params.shader};
+      st->slots_per_pixel, (unsigned long long)st->params.seed, st->params.shader};
   int  sms    = sm_count();
   bool prof   = st->profile;  // per-kernel timing: every group runs on ONE stream, nothing overlaps
   int  grid_t = sms * 8, grid_s = sms * 4;
@@ -923,6 +1015,15 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
   cudaStream_t s0 = st->groups[0]->stream;
   YH_CUDA(cudaEventRecord(st->ev_begin, s0));
   int64_t launches = 0, iterations = 0, rounds = 0;
+  // YH_DEBUG_SYNC=1: synchronise after every launch and name the kernel that faulted
+  static const bool debug_sync = getenv("YH_DEBUG_SYNC") != nullptr;
+#define YH_DEBUG_KERNEL(name, stream_)                                                                              \
+  do {                                                                                                               \
+    if (debug_sync) {                                                                                                \
+      cudaError_t e_ = cudaStreamSynchronize(stream_);                                                               \
+      if (e_ != cudaSuccess) return fail(YH_ERR_CUDA, "%s failed in round %lld: %s", name, (long long)rounds, cudaGetErrorString(e_)); \
+    }                                                                                                                \
+  } while (0)
   for (auto g : st->groups) {
     cudaStream_t s = stream_of(g);
     if (s != s0) YH_CUDA(cudaStreamWaitEvent(s, st->ev_begin, 0));
@@ -931,10 +1032,11 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
     YH_CUDA(cudaMemsetAsync(q.stats, 0, 8 * sizeof(unsigned long long), s));
     g->cur = 0, g->done = g->num_slots == 0;
     if (g->done) continue;
-    k_start<<<(g->num_slots + 255) / 256, 256, 0, s>>>(st->ps(g->first_slot), q, st->camera, tc, g->num_slots, num_samples);
+    k_start<<<(g->num_slots + 255) / 256, 256, 0, s>>>(st->ps(g->first_slot), q, st->camera, tc, g->num_slots, num_samples, st->ordinal_base);
+    YH_DEBUG_KERNEL("k_start", s);
     launches++;
   }
-  int64_t min_iters = num_samples;  // every sample needs at least one iteration
+  int64_t min_iters = (num_samples + st->slots_per_pixel - 1) / st->slots_per_pixel;  // every sample of a slot needs at least one iteration
   bool    stopped   = false;
   while (true) {
     bool any = false;
@@ -948,8 +1050,10 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
       k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
       if (prof) ev(s);
       k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur]);
+      YH_DEBUG_KERNEL("k_intersect", s);
       if (prof) ev(s);
       k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
+      YH_DEBUG_KERNEL("k_shade_miss", s);
       switch (tc.shader) {
         case YH_SHADER_NAIVE:
           k_shade<false, YH_SHADER_NAIVE, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
@@ -972,6 +1076,7 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
             k_shade<true, YH_SHADER_PATH, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           }
       }
+      YH_DEBUG_KERNEL("k_shade", s);
       if (prof) ev(s);
       launches += 5;
       iterations++;
@@ -997,7 +1102,7 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
         }
       min_iters = rounds;  // poll the counts from now on
     }
-    if (rounds > (int64_t)num_samples * (st->params.bounces + 2) * 64 + 1024)
+    if (rounds > (int64_t)num_samples * ((st->params.bounces > 4 ? st->params.bounces : 4) + 2) * 64 + 1024)
       return fail(YH_ERR_STATE, "yh_trace_samples: wavefront did not drain after %lld rounds", (long long)rounds);
   }
   // end: the first group's stream waits for the others, then ev_end
@@ -1006,6 +1111,12 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
     if (s == s0) continue;
     YH_CUDA(cudaEventRecord(g->ev_done, s));
     YH_CUDA(cudaStreamWaitEvent(s0, g->ev_done, 0));
+  }
+  if (st->partial.ptr) {  // the lanes' partial images -> accumulation buffer, in lane order
+    int np = st->width * st->height;
+    k_fold_partials<<<(np + 255) / 256, 256, 0, s0>>>(st->accum.ptr, st->samples.ptr, st->partial.ptr, st->partial_samples.ptr, np, st->slots_per_pixel);
+    launches++;
+    st->ordinal_base += num_samples;  // also after a stop request: ordinals are never handed out twice
   }
   YH_CUDA(cudaEventRecord(st->ev_end, s0));
   YH_CUDA(cudaEventSynchronize(st->ev_end));
@@ -1019,7 +1130,7 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
   }
   float ms = 0;
   YH_CUDA(cudaEventElapsedTime(&ms, st->ev_begin, st->ev_end));
-  st->last.samples    = (int64_t)st->num_slots * num_samples - (int64_t)tot[5];  // less the samples a stop request cancelled
+  st->last.samples    = (int64_t)st->num_owned * num_samples - (int64_t)tot[5];  // less the samples a stop request cancelled
   st->last.rays       = (int64_t)tot[0];
   st->last.light_rays = (int64_t)tot[1];
   st->last.iterations = iterations;
@@ -1091,9 +1202,9 @@ yh_status yh_state_download_rng(const yh_state* st, uint64_t* rng) {
   YH_CUDA(cudaMemcpy(inc.data(), st->rng_inc.ptr, 8 * (size_t)st->num_slots, cudaMemcpyDeviceToHost));
   YH_CUDA(cudaMemcpy(px.data(), st->pixel.ptr, 4 * (size_t)st->num_slots, cudaMemcpyDeviceToHost));
   memset(rng, 0, np * 16);
-  for (int i = 0; i < st->num_slots; i++) {
-    rng[2 * (size_t)px[i]]     = s[i];
-    rng[2 * (size_t)px[i] + 1] = inc[i];
+  for (int i = 0; i < st->num_slots; i++) {  // (several slots per pixel: the last lane's generator)
+    rng[2 * (size_t)(px[i] & kPixelMask)]     = s[i];
+    rng[2 * (size_t)(px[i] & kPixelMask) + 1] = inc[i];
   }
   return YH_OK;
 }

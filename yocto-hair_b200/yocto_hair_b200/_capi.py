@@ -136,6 +136,7 @@ PROTOTYPES = {
     "yh_state_size": (C.c_int, [_P, c_int_p, c_int_p]),
     "yh_state_set_shard": (C.c_int, [_P, C.c_int, C.c_int]),
     "yh_state_set_sample_shard": (C.c_int, [_P, C.c_int, C.c_int]),
+    "yh_state_set_sample_slots": (C.c_int, [_P, C.c_int]),
     "yh_shard_pixels": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, c_int_p, C.POINTER(C.c_int64)]),
     "yh_trace_samples": (C.c_int, [_P, C.c_int, _P]),
     "yh_state_stats": (C.c_int, [_P, C.POINTER(TraceStats)]),

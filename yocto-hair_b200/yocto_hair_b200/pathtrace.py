@@ -135,6 +135,11 @@ class DeviceState:
         capi.check(self.lib.yh_state_set_sample_shard(self.handle, rank, world))
         return self
 
+    def set_sample_slots(self, slots_per_pixel: int = 0) -> "DeviceState":
+        """Counter mode: several concurrent path slots per pixel (0 = auto), yh_state_set_sample_slots."""
+        capi.check(self.lib.yh_state_set_sample_slots(self.handle, slots_per_pixel))
+        return self
+
     def set_profiling(self, enabled: bool = True) -> "DeviceState":
         capi.check(self.lib.yh_state_set_profiling(self.handle, int(enabled)))
         return self
