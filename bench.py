@@ -250,6 +250,8 @@ def run_cuda_point(args, hair, ctx):
         st = ds.init_state(cam, params)
         if mode == "samples":
             st.set_sample_shard(rank, world)
+            if args.slots != 1:
+                st.set_sample_slots(args.slots)
         elif world > 1:
             st.set_shard(rank, world)
         return st
@@ -267,6 +269,8 @@ def run_cuda_point(args, hair, ctx):
     width, height = st.width, st.height
     for _ in range(warmup):
         st.trace_samples(spp_rank)
+    if world > 1 and warmup > 0:  # the collective's own warm-up (NCCL sets its channels up on the first call: 25-50 ms once)
+        parallel.reduce_image(*parallel.state_tensors(st, dev), 0)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -459,7 +463,7 @@ def run_cuda(args):
         config = {"workload": r0["text"], "spp_per_step": spp, "sky_texture": args.sky,
                   "sky_size": list(SKY_SIZE) if args.sky and WORKLOADS[args.workload][0] in ("curly", "straight") else None,
                   "parallelism": f"{shard}{world}",
-                  "rng": "counter (per-sample PCG32 streams; statistically equivalent image)" if shard == "samples"
+                  "rng": ("counter (per-sample PCG32 streams; statistically equivalent image); slots per pixel: %s" % (args.slots or "auto")) if shard == "samples"
                          else "reference (one PCG32 stream per pixel; image bit-identical to the CPU reference)",
                   "l2_policy": "working set larger than L2 is not guaranteed; rays are regenerated every step "
                                "(no input is re-read), see DESIGN.md",
@@ -556,11 +560,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
-    ap.add_argument("--spp-step", type=int, default=64, help="samples per pixel per step (CUDA arm): one yh_trace_samples call per rank")
+    ap.add_argument("--spp-step", type=int, default=128, help="samples per pixel per step (CUDA arm): one yh_trace_samples call per rank")
     ap.add_argument("--ref-spp-step", type=int, default=2, help="samples per pixel per step (reference arm)")
     ap.add_argument("--max-split", type=int, default=0)
     ap.add_argument("--shard", default="auto", choices=["auto", "tiles", "samples"],
                     help="multi-GPU sharding: image tiles (reference RNG streams) or sample ranges (counter-mode streams)")
+    ap.add_argument("--slots", type=int, default=0, help="counter mode: concurrent path slots per pixel (0 = auto: fill the device; 1 = one slot per pixel)")
     ap.add_argument("--group", action="store_true", help="one process drives all --gpus through yh_group_* (no torchrun)")
     ap.add_argument("--no-sky", dest="sky", action="store_false", help="uniform environment instead of the sky texture")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -425,6 +425,31 @@ def test_many_instances_follow_the_reference_scene_tree(side, coincident, ref):
     sd.close(); ds.close(); sr.close(); rs.close()
 
 
+@pytest.mark.parametrize("capacity", ["0", "41", ""])
+def test_rays_carried_over_between_launches(capacity, ref, monkeypatch):
+    """The traversal hands the long rays of a launch's tail to the next launch (suspend records, yh_traverse.cuh): with
+    the record buffer off, too small (reservations that do not fit are skipped, the rays finish in place) or at its
+    default size the render is the reference's, bit for bit, and the same number of rays is traced."""
+    if capacity:
+        monkeypatch.setenv("YH_SUSPEND_CAP", capacity)
+    else:
+        monkeypatch.delenv("YH_SUSPEND_CAP", raising=False)
+    scene, cam = synth.curly_hair_scene(60_000)
+    p = make_params(resolution=192)
+    rs = ref.scene(scene)
+    sr = rs.state(cam, p)
+    sr.trace_samples(3)
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    sd = ds.init_state(cam, p)
+    stats = sd.trace_samples(3)
+    _, a_r, s_r, rng_r = sr.download()
+    _, a_d, s_d = sd.download()
+    assert np.array_equal(s_r, s_d) and np.array_equal(a_r.view(np.uint32), a_d.view(np.uint32)) and np.array_equal(rng_r, sd.rng())
+    test_rays_carried_over_between_launches.rays = getattr(test_rays_carried_over_between_launches, "rays", stats.rays)
+    assert stats.rays == test_rays_carried_over_between_launches.rays
+    sd.close(); ds.close(); sr.close(); rs.close()
+
+
 def test_full_size_properties(ref):
     """BASELINE configs[2] geometry (1M curly segments): oracle agreement on a
     ray subset, and shard-union == whole image at the bench resolution's tile grid."""
@@ -489,6 +514,48 @@ def test_counter_mode_bit_identical_to_port_and_shards_add_up(port, ref):
     assert np.array_equal(cnt, s_d)
     assert np.allclose(acc, a_d, rtol=2e-6, atol=1e-6)
     sd.close(); sp.close(); rp.close(); ds.close()
+
+
+def test_counter_mode_with_several_slots_per_pixel():
+    """yh_state_set_sample_slots: S lanes per pixel trace the sample ordinals k, k + S, ... concurrently.  The image holds
+    the same samples as the one-slot counter image (equal up to fp32 summation order), every pixel gets exactly the
+    requested count also when it is not a multiple of S, and the result is deterministic."""
+    scene, cam = synth.straight_hair_scene(20_000)
+    p = make_params(resolution=128)
+    ds = DeviceScene(scene).init_bvh().init_lights()
+    one = ds.init_state(cam, p).set_sample_shard(0, 1)
+    one.trace_samples(6)
+    _, a_one, s_one = one.download()
+    for slots in (2, 4, 0):
+        imgs = []
+        for rep in range(2):
+            st = ds.init_state(cam, p).set_sample_shard(0, 1).set_sample_slots(slots)
+            stats = st.trace_samples(6)
+            assert stats.samples == st.width * st.height * 6
+            _, a, s = st.download()
+            assert (s == 6).all()
+            imgs.append(a)
+            st.close()
+        assert np.array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))  # deterministic
+        assert np.allclose(imgs[0], a_one, rtol=2e-6, atol=1e-6)
+    # two calls hand out the ordinals 0..2 and 3..5: the same six samples
+    st = ds.init_state(cam, p).set_sample_shard(0, 1).set_sample_slots(4)
+    st.trace_samples(3), st.trace_samples(3)
+    _, a, s = st.download()
+    assert (s == 6).all() and np.allclose(a, a_one, rtol=2e-6, atol=1e-6)
+    st.close()
+    # sample shards of a world of 2, four lanes each, add up to the same image
+    acc = np.zeros_like(a_one, dtype=np.float64)
+    for rank in range(2):
+        st = ds.init_state(cam, p).set_sample_shard(rank, 2).set_sample_slots(4)
+        st.trace_samples(3)
+        acc += st.download()[1]
+        st.close()
+    assert np.allclose(acc, a_one, rtol=2e-6, atol=1e-6)
+    with pytest.raises(capi.YhError) as e:  # the reference's one-stream-per-pixel mode has nothing to run side by side
+        ds.init_state(cam, p).set_sample_slots(2)
+    assert e.value.status == capi.YH_ERR_STATE
+    one.close(); ds.close()
 
 
 def test_counter_mode_converges_to_the_reference_image(ref):

@@ -1223,12 +1223,16 @@ yh_status yh_scene_init_lights(yh_scene* sc) {
       int                w = sc->textures[e.tex].width, h = sc->textures[e.tex].height;
       auto&              px = sc->tex_host[e.tex];
       std::vector<float> cdf((size_t)w * h);
+      // sin(theta) depends on the row only: one libm call per row instead of one per texel (the same float either way);
+      // the running sum stays sequential, in the reference's order (:1731-1735)
+      std::vector<float> row_sin(h);
+      for (int iy = 0; iy < h; iy++) row_sin[iy] = std::sin((iy + 0.5f) * pif / h);
+      float run = 0;
       for (size_t i = 0; i < cdf.size(); i++) {
-        int   iy = (int)(i / w);
-        float th = (iy + 0.5f) * pif / h;
         float mx = fmax_(fmax_(px[3 * i], px[3 * i + 1]), px[3 * i + 2]);
-        cdf[i]   = mx * std::sin(th);
-        if (i) cdf[i] += cdf[i - 1];
+        float v  = mx * row_sin[i / w];
+        run      = i ? v + run : v;
+        cdf[i]   = run;
       }
       auto buf = new dev_buffer<float>{};
       sc->light_cdfs.push_back(buf);

@@ -243,15 +243,19 @@ struct wavefront_io {  // by value: references to kernel parameters would force 
 #define YH_INTERSECT_BLOCKS 7
 #endif
 __global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur,
-    const int* active) {
+    const int* active, suspend_io sus) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
   int            n = q.count[cur];
+  if (sus.out_records) {  // rays carried over: read this launch's share, write the next one's (counts [6 + cur], [7 - cur])
+    sus.n_in      = min(q.count[6 + cur], sus.capacity);  // (reservations past the end of the buffer hold nothing)
+    sus.out_count = q.count + 6 + (cur ^ 1);
+  }
   unsigned long long nv = 0, pt = 0;
   __shared__ int smem_park[kParkSlots * kTraceBlock];
   __shared__ int smem_cold[kColdWords * kTraceBlock];
   wavefront_io   io{sc, ps, q, active};
   trace_persistent(sc, io, n, q.count + 5, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x, false,
-      &nv, &pt);
+      &nv, &pt, sus.out_records ? &sus : nullptr);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.stats + 0, (unsigned long long)n);
 #ifdef YH_TRAVERSAL_STATS
   atomicAdd(q.stats + 3, nv);
@@ -545,9 +549,12 @@ __global__ void k_cancel_remaining(path_state ps, int num_slots, unsigned long l
   if ((threadIdx.x & 31) == 0 && left > 0) atomicAdd(cancelled, (unsigned long long)left);
 }
 
+// before the traversal of a round that reads queue `next ^ 1`: its outputs start empty (the next active queue, the three
+// shading queues, the ray cursor and the suspend records the traversal will write, count[6 + next])
 __global__ void k_reset_counts(int* count, int next) {
   count[next] = 0;
   count[2] = count[3] = count[4] = count[5] = 0;
+  count[6 + next] = 0;
 }
 
 // init_state, yocto_pathtrace.cpp:1931-1946: pixel k takes the k-th draw of the
@@ -680,6 +687,8 @@ static void pinned_release(int* p) {
 struct wave_group {
   int                            first_slot = 0, num_slots = 0;
   dev_buffer<int>                q_active0, q_active1, q_miss, q_surface, q_hair, q_count;
+  dev_buffer<int>                sus_records[2];  // rays carried over between launches (suspend_io), ping-pong
+  int                            sus_capacity = 0;
   dev_buffer<unsigned long long> stats;
   cudaStream_t                   stream      = nullptr;
   cudaEvent_t                    ev_done     = nullptr;
@@ -838,6 +847,15 @@ static yh_status assign_slots(yh_state* st) {
     YH_CUDA(grp->q_hair.alloc(m));
     YH_CUDA(grp->q_count.alloc(8));
     YH_CUDA(grp->stats.alloc(8));
+    {  // suspend records: enough for every lane of a resident traversal grid to hand over a ray or two
+      int cap = 1 << 15;
+      if (const char* e = getenv("YH_SUSPEND_CAP")) cap = std::max(0, atoi(e));
+      grp->sus_capacity = (int)std::min<size_t>((size_t)cap, m);
+      if (grp->sus_capacity > 0) {
+        YH_CUDA(grp->sus_records[0].alloc((size_t)grp->sus_capacity * kSuspendWords));
+        YH_CUDA(grp->sus_records[1].alloc((size_t)grp->sus_capacity * kSuspendWords));
+      }
+    }
 
     YH_CUDA(cudaStreamCreateWithFlags(&grp->stream, cudaStreamNonBlocking));
     YH_CUDA(cudaEventCreateWithFlags(&grp->ev_done, cudaEventDisableTiming));
@@ -1049,7 +1067,9 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
       int          next = g->cur ^ 1;
       k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
       if (prof) ev(s);
-      k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur]);
+      suspend_io sus{};
+      if (g->sus_capacity > 0) sus = {g->sus_records[g->cur].ptr, 0, g->sus_records[next].ptr, nullptr, g->sus_capacity};
+      k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur], sus);
       YH_DEBUG_KERNEL("k_intersect", s);
       if (prof) ev(s);
       k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
@@ -1090,7 +1110,7 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
       for (auto g : st->groups) {
         if (g->done) continue;
         YH_CUDA(cudaStreamSynchronize(stream_of(g)));
-        if (g->host_counts[g->cur] == 0) g->done = true;
+        if (g->host_counts[g->cur] == 0 && g->host_counts[6 + g->cur] == 0) g->done = true;  // no active path, no suspended ray
       }
     }
     if (stop && *stop && !stopped) {  // finish the samples in flight, start no new ones

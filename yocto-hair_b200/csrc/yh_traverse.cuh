@@ -510,10 +510,39 @@ enum cold_word {
 };
 constexpr int kColdWords = CW_COUNT;
 
+// Rays carried over from one launch to the next (wavefront only).  A launch ends with a tail: the queue is empty and
+// a few long rays (hundreds of node steps, against ~70 on average) keep a few lanes of a few warps busy while the SMs
+// drain - measured at a third of the traversal time of a 0.8 M-ray launch.  Instead, once a warp knows the queue is
+// exhausted and has no more than kSuspendLanes rays left, it writes their complete walk state (cold words, node,
+// parked leaves, stack) to a record and exits; the next launch of this group picks the records up FIRST, next to its
+// fresh rays, so the long rays run inside the bulk of that launch.  A suspended path simply takes part in the
+// shading one wavefront iteration later; nothing about its result changes.
+#ifndef YH_SUSPEND_LANES
+#define YH_SUSPEND_LANES 12
+#endif
+constexpr int kSuspendLanes = YH_SUSPEND_LANES;
+// ... and only rays that have walked at least this many bursts of kInnerSteps node steps in this launch are handed over,
+// so every launch moves every ray forward (a launch of a few rays would otherwise pass them on untouched)
+#ifndef YH_SUSPEND_MIN_BURSTS
+#define YH_SUSPEND_MIN_BURSTS 12
+#endif
+constexpr int kSuspendMinBursts = YH_SUSPEND_MIN_BURSTS;
+constexpr int kSuspendEmpty = (int)0x80000001;  // SW_CUR of a record that holds no ray
+constexpr int kSuspendWords = 128;  // cold words, cur, park count + 4 entries, stack count, floor count, <= 96 entries
+struct suspend_io {
+  const int* in_records;   // written by the previous launch
+  int        n_in;
+  int*       out_records;  // read by the next launch
+  int*       out_count;
+  int        capacity;
+};
+enum suspend_word { SW_CUR = CW_COUNT, SW_PARK_COUNT, SW_PARK0, SW_STACK_COUNT = SW_PARK0 + YH_PARK_SLOTS, SW_BASE_COUNT, SW_STACK0 };
+static_assert(SW_STACK0 + 96 <= kSuspendWords, "a suspend record holds the whole stack");
+
 template <class IO>
 __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, int n, int* cursor, int* smem_stack,
     int* smem_park, int* smem_cold, bool find_any, unsigned long long* nodes_visited,
-    unsigned long long* prims_tested) {
+    unsigned long long* prims_tested, const suspend_io* sus = nullptr) {
   const unsigned full = 0xffffffffu;
   const int      lane = threadIdx.x & 31;
   int            stack_overflow[kStackLocal];
@@ -538,7 +567,41 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
   slab_consts k = {0, 0, 0, 0, 0, 0, kSelLo, kSelLo, kSelLo, kSelHi, kSelHi, kSelHi};
   const uint4* __restrict__ slots = nullptr;
 
+  const int n_resume = sus ? sus->n_in : 0;  // work items [0, n_resume) are suspended rays, the rest the queue
+  const int n_items  = n + n_resume;
+  bool      keep_on  = false;  // the record buffer is full: finish in place
+  int       bursts   = 0;      // node-step bursts this lane's ray has taken in this launch
   while (true) {
+    // ---- 0. the queue is exhausted and few lanes still hold a ray: hand them to the next launch
+    if (sus && exhausted && !keep_on) {
+      const bool     ripe = have && bursts >= kSuspendMinBursts;
+      const unsigned busy = __ballot_sync(full, have), out = __ballot_sync(full, ripe);
+      const int      nb   = __popc(out);
+      if (nb > 0 && __popc(busy) <= kSuspendLanes) {
+        // Records are reserved with one atomic per warp and never given back (a roll-back would leave holes under
+        // contention).  A reservation that does not fit marks the part of it that lies inside the buffer as empty -
+        // the reader skips such records - and the warp finishes its rays in place.
+        int first = 0;
+        if (lane == 0) first = atomicAdd(sus->out_count, nb);
+        first = __shfl_sync(full, first, 0);
+        const int mine = first + __popc(out & ((1u << lane) - 1));
+        if (first + nb > sus->capacity) {
+          keep_on = true;
+          if (ripe && mine < sus->capacity) sus->out_records[(size_t)mine * kSuspendWords + SW_CUR] = kSuspendEmpty;
+        } else if (ripe) {
+          int* rec = sus->out_records + (size_t)mine * kSuspendWords;
+          for (int w = 0; w < CW_COUNT; w++) rec[w] = cold[w * kTraceBlock];
+          rec[SW_CUR] = cur;
+          const int pc = (int)((park_top - park_base) / kStackStride);
+          rec[SW_PARK_COUNT] = pc;
+          for (int i = 0; i < pc; i++) rec[SW_PARK0 + i] = smem_park[i * kTraceBlock];
+          const int ns = (int)((st.top - st.floor()) / kStackStride);
+          rec[SW_STACK_COUNT] = ns, rec[SW_BASE_COUNT] = (int)((st.base - st.floor()) / kStackStride);
+          for (int e = 0; e < ns; e++) rec[SW_STACK0 + e] = e < kStackShared ? smem_stack[e * kTraceBlock] : stack_overflow[e - kStackShared];
+          have = false;
+        }
+      }
+    }
     // ---- 1. lanes without a ray: write finished records, fetch new rays
     unsigned idle = __ballot_sync(full, !have);
     if (__popc(idle) >= kRefillIdle || idle == full) {
@@ -557,8 +620,28 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
           int   index = base + __popc(idle & ((1u << lane) - 1));
           ray3f wr;
           int   handle;
-          if (index < n && io.load(index, handle, wr)) {
-            have = true, cur = kTraverseDone, park_top = park_base;
+          if (index < n_resume) {  // a ray suspended by the previous launch: restore its walk where it stopped
+            const int* rec = sus->in_records + (size_t)index * kSuspendWords;
+            const int  stored = __ldcs(rec + SW_CUR);
+            if (stored != kSuspendEmpty) {  // (an empty record: a reservation that did not fit, see step 0)
+              for (int w = 0; w < CW_COUNT; w++) cold[w * kTraceBlock] = __ldcs(rec + w);
+              have = true, cur = stored, bursts = 0;
+              const int pc = __ldcs(rec + SW_PARK_COUNT);
+              for (int i = 0; i < pc; i++) smem_park[i * kTraceBlock] = __ldcs(rec + SW_PARK0 + i);
+              park_top = park_base + pc * kStackStride;
+              const int ns = __ldcs(rec + SW_STACK_COUNT);
+              st.base = st.top = st.floor();
+              for (int e = 0; e < ns; e++) st.push(__ldcs(rec + SW_STACK0 + e));
+              st.base = st.floor() + __ldcs(rec + SW_BASE_COUNT) * kStackStride;
+              if (cur >= 0 || pc > 0) {  // a shape is open: its per-ray constants follow from the stored ray
+                const dev_shape& sh = *shape_ptr();
+                shape_ray sr = make_shape_ray(sh, {cwf(CW_OX), cwf(CW_OY), cwf(CW_OZ)}, {cwf(CW_DX), cwf(CW_DY), cwf(CW_DZ)});
+                k = sr.k, slots = sh.slots;
+                tlo = shifted_tmin(cwf(CW_TMIN), cwf(CW_T0)), thi = shifted_tmax(cwf(CW_TMAX), cwf(CW_T0));
+              }
+            }
+          } else if (index < n_items && io.load(index - n_resume, handle, wr)) {
+            have = true, cur = kTraverseDone, park_top = park_base, bursts = 0;
             // the walk over the top-level tree starts at its root; a tree that is ONE leaf (<= 4 objects, the hair
             // scenes) is unrolled here: its objects in order, no box test of its own
             st.base = st.top = st.floor();
@@ -574,7 +657,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
             cw(CW_BOBJ) = -1, cw(CW_BELEM) = -1, put(CW_BU, 0), put(CW_BV, 0), put(CW_BDIST, 0);
           }
         }
-        exhausted = base + cnt >= n;
+        exhausted = base + cnt >= n_items;
         idle      = __ballot_sync(full, !have);
       }
       if (idle == full) break;  // nothing in flight and nothing left to fetch
@@ -697,6 +780,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
 #else
 #pragma unroll
 #endif
+    bursts += (cur >= 0) ? 1 : 0;
     for (int inner = 0; inner < kInnerSteps; inner += kVoteEvery) {
       if (inner > 0 && __popc(__ballot_sync(full, cur >= 0 && park_top <= park_walk)) < kInnerLanes) break;
 #pragma unroll
