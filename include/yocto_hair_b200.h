@@ -188,6 +188,14 @@ typedef struct yh_bvh_stats {
 } yh_bvh_stats;
 yh_status yh_scene_bvh_stats(const yh_scene* scene, yh_bvh_stats* stats);
 
+/* Diagnostics: the order in which the REFERENCE's BVH over shape `shape` holds
+ * its primitives (shape->bvh->primitives after build_bvh, yocto_pathtrace.cpp:
+ * 601-650, :746-752).  The device grows that tree too - only to break exact-t
+ * ties the way the reference does.  `order` (may be null) receives *count
+ * element indices.                                                           */
+yh_status yh_scene_reference_order(const yh_scene* scene, int shape, int* order,
+    int64_t* count);
+
 /* Intersection ------------------------------------------------------------
  * yocto::math::ray3f (libs/yocto/yocto_math.h:1106) and
  * yocto::pathtrace::intersection3f (yocto_pathtrace.h:441-447).             */
@@ -310,8 +318,7 @@ yh_status yh_state_download_rng(const yh_state* state, uint64_t* rng);
  * libnccl.so.2 is loaded on demand, communicators from ncclCommInitAll).
  *   yh_group_create      = yh_scene_create + yh_scene_init_bvh + yh_scene_init_lights
  *                          on every device (devices == NULL: 0 .. num_devices - 1; a
- *                          device listed k times carries k ranks); the host part of the
- *                          build runs once and is shared
+ *                          device listed k times carries k ranks), side by side
  *   yh_group_init_state  = init_state (:1931-1946) on every device + the shard:
  *                          YH_SHARD_TILES   yh_state_set_shard: image tiles, the reference's
  *                                           RNG streams; the summed image is bit-identical

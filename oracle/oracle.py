@@ -75,6 +75,7 @@ class _Oracle:
             ("trace_samples", C.c_double, [_P, C.c_int]),
             ("state_download", None, [_P, _P, _P, _P, _P]),
             ("hardware_concurrency", C.c_int, []),
+            ("shape_order", C.c_int, [_P, C.c_int, _P]),
         ]:
             f = self._fn(name)
             f.restype, f.argtypes = res, args
@@ -150,6 +151,13 @@ class _OracleScene:
         hits = np.zeros((len(rays),), dtype=HIT_DTYPE)
         self.o._fn("intersect_batch")(self.handle, _ptr(rays), len(rays), int(find_any), _ptr(hits), threads)
         return hits
+
+    def shape_order(self, shape: int) -> np.ndarray:
+        """Primitive order of the checker's BVH over `shape` (shape->bvh->primitives after build_bvh)."""
+        n = self.o._fn("shape_order")(self.handle, shape, None)
+        order = np.zeros(max(n, 0), np.int32)
+        self.o._fn("shape_order")(self.handle, shape, _ptr(order))
+        return order
 
     def state(self, camera, params):
         return _OracleState(self, camera, params)

@@ -295,6 +295,14 @@ void ref_scene_destroy(void* h) {
   delete rs->scene;
   delete rs;
 }
+// shape->bvh->primitives: the leaf order of the reference's own tree over this shape (build_bvh, :601-650, :746-752)
+int ref_shape_order(void* h, int shape, int* order) {
+  auto rs = (ref_scene*)h;
+  if (shape < 0 || shape >= (int)rs->scene->shapes.size()) return -1;
+  auto& prims = rs->scene->shapes[shape]->bvh->primitives;
+  if (order) memcpy(order, prims.data(), sizeof(int) * prims.size());
+  return (int)prims.size();
+}
 int64_t ref_scene_bvh_nodes(void* h, int shape) {
   auto rs = (ref_scene*)h;
   if (shape < 0) return (int64_t)rs->scene->bvh->nodes.size();

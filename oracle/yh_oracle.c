@@ -806,6 +806,14 @@ void* yho_scene_create(const yh_scene_desc* d) {
   init_lights(sc);
   return sc;
 }
+/* shape->bvh->primitives after build_bvh (pt:746-752): the leaf order of the reference's tree */
+int yho_shape_order(void* h, int shape, int* order) {
+  scene_t* sc = (scene_t*)h;
+  if (!sc || shape < 0 || shape >= sc->nshapes) return -1;
+  const tree_t* t = &sc->shapes[shape].bvh;
+  if (order) memcpy(order, t->prims, sizeof(int) * (size_t)t->num_prims);
+  return t->num_prims;
+}
 void yho_scene_destroy(void* h) {
   scene_t* sc = (scene_t*)h;
   if (!sc) return;

@@ -290,3 +290,13 @@ def test_port_point_shapes_bit_exact_vs_reference(shader, port, refo):
     assert np.array_equal(s1, s2) and np.array_equal(g1, g2) and np.array_equal(bits(a1), bits(a2))
     for x in (sr, sp, rr, rp):
         x.close()
+
+
+def test_port_tree_order_equals_the_reference(port, refo):
+    """shape->bvh->primitives after build_bvh (the leaf order exact-t ties are broken by): the port's builder, with its
+    restatement of libstdc++'s std::partition, leaves the primitives where the reference's does."""
+    for scene in (synth.hair_block_scene(30_000)[0], synth.curly_hair_scene(60_000, sky=False)[0], synth.points_scene(5_000, 2_000, sky=False)[0]):
+        a, b = refo.scene(scene), port.scene(scene)
+        for k in range(len(scene.shapes)):
+            assert np.array_equal(a.shape_order(k), b.shape_order(k))
+        a.close(); b.close()

@@ -188,17 +188,12 @@ yh_status yh_group_create(const yh_scene_desc* desc, const yh_bvh_params* bvh, c
     last_error_storage() = msg;
     return s;
   };
-  // the first replica starts the (host) computation of the reference leaf order; the others share its result
-  if (cudaSetDevice(devs[0]) != cudaSuccess) return bail(fail(YH_ERR_CUDA, "cudaSetDevice(%d) failed", devs[0]));
-  yh_status s = scene_create(desc, nullptr, &g->m[0].scene);
-  if (s != YH_OK) return bail(s);
+  // every device uploads and builds its own replica, side by side (the whole build runs on the device)
   yh_bvh_params bp{};
   if (bvh) bp = *bvh;
-  s = on_all_members(g, [&](int i) -> yh_status {
-    if (i > 0) {
-      yh_status c = scene_create(desc, g->m[0].scene, &g->m[i].scene);
-      if (c != YH_OK) return c;
-    }
+  yh_status s = on_all_members(g, [&](int i) -> yh_status {
+    yh_status c = yh_scene_create(desc, &g->m[i].scene);
+    if (c != YH_OK) return c;
     yh_status b = yh_scene_init_bvh(g->m[i].scene, &bp);
     if (b != YH_OK) return b;
     b = yh_scene_init_lights(g->m[i].scene);

@@ -356,11 +356,10 @@ __global__ void k_emit_triangles(int n, const int* elems, const float* pos, floa
 
 // ------------------------------------------------------------ host driver --
 
-// Topology of the tree the reference would build for this shape (build_bvh /
-// split_middle, yocto_pathtrace.cpp:564-650): spatial-middle split of the
-// centroid bounds along their largest axis with std::partition, median index
-// when that fails, leaves of <= 4 primitives.  Only the ORDER it induces is
-// kept (see yh_scene.cuh "tie order"); our own traversal never walks it.
+// One split of the reference's builder (build_bvh / split_middle, yocto_pathtrace.cpp:564-650): spatial-middle split
+// of the centroid bounds along their largest axis with std::partition, median index when that fails.  Used on the
+// host for the top-level tree over the OBJECTS (build_scene_tree); the per-shape trees, whose leaf order breaks
+// exact-t ties, are grown on the device (yh_tieorder.cu).
 struct ref_prim {
   vec3f center;
   int   primitive;
@@ -382,98 +381,6 @@ static void reference_split(ref_prim* prims, int start, int end, int& mid, int& 
   mid = (int)(std::partition(prims + start, prims + end, [&](const ref_prim& p) { return key(p) < middle; }) - prims);
   if (mid == start || mid == end) mid = (start + end) / 2;
 }
-// the subtree over prims[start, end) as a node list, root first, child indices local to the list
-// (child < 0: leaf of <= 4 primitives).  Iterative: split chains can be long for degenerate inputs.
-static void reference_subtree(ref_prim* prims, int start, int end, std::vector<int4>& nodes) {
-  nodes.clear();
-  if (end - start <= kRefLeafMax) return;
-  struct item { int node, start, end; };
-  std::vector<item> todo;
-  nodes.push_back({0, 0, -1, -1});
-  todo.push_back({0, start, end});
-  while (!todo.empty()) {
-    item it = todo.back();
-    todo.pop_back();
-    int axis, mid;
-    reference_split(prims, it.start, it.end, mid, axis);
-    int child[2];
-    int range[2][2] = {{it.start, mid}, {mid, it.end}};
-    for (int c = 0; c < 2; c++) {
-      if (range[c][1] - range[c][0] > kRefLeafMax) {
-        child[c] = (int)nodes.size();
-        nodes.push_back({0, 0, -1, -1});
-        todo.push_back({child[c], range[c][0], range[c][1]});
-      } else {
-        child[c] = -1;
-      }
-    }
-    nodes[it.node] = {mid, axis, child[0], child[1]};
-  }
-}
-// top levels in parallel: the two halves of a split are independent (disjoint ranges of prims)
-static std::vector<int4> reference_tree(ref_prim* prims, int start, int end, int depth) {
-  std::vector<int4> nodes;
-  if (depth >= 4 || end - start < (1 << 15)) {
-    reference_subtree(prims, start, end, nodes);
-    return nodes;
-  }
-  int axis, mid;
-  reference_split(prims, start, end, mid, axis);
-  auto left_future = std::async(std::launch::async, reference_tree, prims, start, mid, depth + 1);
-  std::vector<int4> right = reference_tree(prims, mid, end, depth + 1);
-  std::vector<int4> left  = left_future.get();
-  int lofs = 1, rofs = 1 + (int)left.size();
-  nodes.reserve(1 + left.size() + right.size());
-  nodes.push_back({mid, axis, left.empty() ? -1 : lofs, right.empty() ? -1 : rofs});
-  auto append = [&](const std::vector<int4>& sub, int ofs) {
-    for (int4 n : sub) nodes.push_back({n.x, n.y, n.z < 0 ? -1 : n.z + ofs, n.w < 0 ? -1 : n.w + ofs});
-  };
-  append(left, lofs);
-  append(right, rofs);
-  return nodes;
-}
-static void reference_tree_order(const host_shape& sh, std::vector<int>& ref_pos, std::vector<int4>& tie_nodes, bbox3f& root_bbox) {
-  bool lines = sh.is_lines();
-  int  n     = sh.num_elems();
-  auto P     = [&](int v) { return vec3f{sh.positions[3 * v], sh.positions[3 * v + 1], sh.positions[3 * v + 2]}; };
-  // the two linear passes run in chunks on host threads (a million primitives: ~15 ms each on one core)
-  const int nt = n > (1 << 16) ? 8 : 1;
-  auto chunks = [n, nt](auto&& body) {
-    std::vector<std::future<void>> jobs;
-    for (int t = 0; t < nt; t++)
-      jobs.push_back(std::async(nt > 1 ? std::launch::async : std::launch::deferred,
-          [&body, n, nt, t]() { body(t, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt)); }));
-    for (auto& j : jobs) j.get();
-  };
-  std::vector<ref_prim> prims(n);
-  // the root box of the reference's tree is the union of the primitive bounds (:622-624; min / max: any order)
-  std::vector<bbox3f> part_box(nt, bbox3f{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}});
-  chunks([&](int t, int i0, int i1) {
-    bbox3f& acc = part_box[t];
-    for (int i = i0; i < i1; i++) {
-      bbox3f b;
-      if (sh.is_points()) {
-        int a = sh.points[i];
-        b     = point_bounds(P(a), sh.radius[a]);  // :715-721
-      } else if (lines) {
-        int a = sh.lines[2 * i], c = sh.lines[2 * i + 1];
-        b     = line_bounds(P(a), P(c), sh.radius[a], sh.radius[c]);
-      } else {
-        b = triangle_bounds(P(sh.triangles[3 * i]), P(sh.triangles[3 * i + 1]), P(sh.triangles[3 * i + 2]));
-      }
-      prims[i] = {(b.min + b.max) / 2.0f, i};  // center(bbox), yocto_math.h:3008
-      acc = {min3(acc.min, b.min), max3(acc.max, b.max)};
-    }
-  });
-  root_bbox = part_box[0];
-  for (int t = 1; t < nt; t++) root_bbox = {min3(root_bbox.min, part_box[t].min), max3(root_bbox.max, part_box[t].max)};
-  tie_nodes = reference_tree(prims.data(), 0, n, 0);
-  ref_pos.assign(n, 0);
-  chunks([&](int, int i0, int i1) {
-    for (int i = i0; i < i1; i++) ref_pos[prims[i].primitive] = i;
-  });
-}
-
 // ---- quality builder (yh_bvh_params::quality = 1): binned SAH, top down, on the host ----------
 // Same outputs as k_hierarchy (left / right / parents over inner nodes 0 .. R-2, root = 0, leaf
 // children encoded as ~position) plus the permutation of the references, so the device kernels
@@ -910,7 +817,7 @@ static void build_scene_tree(const yh_scene* sc, std::vector<float4>& nodes, std
   for (int i = 0; i < n; i++) {
     const host_shape* s = sc->shapes[sc->objects[i].shape];
     bbox3f b = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};  // invalidb3f
-    if (s->num_elems() > 0 && s->ties) b = transform_bbox_exact(sc->objects[i].frame, s->ties->root_bbox);
+    if (s->num_elems() > 0) b = transform_bbox_exact(sc->objects[i].frame, s->ref_root_bbox);
     prims[i] = {(b.min + b.max) / 2.0f, i};
   }
   struct item { int node, start, end; };
@@ -943,28 +850,17 @@ static void build_scene_tree(const yh_scene* sc, std::vector<float4>& nodes, std
   for (int i = 0; i < n; i++) prims_out[i] = prims[i].primitive;
 }
 
-yh_status yh_scene::sync_ties() const {
-  std::lock_guard<std::mutex> lock(tie_mutex);
-  if (!ties_pending && !scene_tree_pending) return YH_OK;
+yh_status yh_scene::sync_scene_tree() const {
+  std::lock_guard<std::mutex> lock(tree_mutex);
+  if (!scene_tree_pending) return YH_OK;
   auto self = const_cast<yh_scene*>(this);
-  if (ties_pending) {
-    for (auto s : shapes) {
-      if (!s->tie_future.valid()) continue;
-      s->ties = s->tie_future.get();
-      YH_CUDA(s->d_ref_pos.upload(s->ties->ref_pos.data(), s->ties->ref_pos.size()));
-      YH_CUDA(s->d_tie_nodes.upload(s->ties->tie_nodes.data(), s->ties->tie_nodes.size()));
-    }
-    ties_pending = false;
-  }
-  if (scene_tree_pending) {  // needs the objects' padded bounds (init_bvh) and the shapes' exact root boxes (tie tables)
-    std::vector<float4> nodes;
-    std::vector<int>    prims;
-    build_scene_tree(this, nodes, prims);
-    YH_CUDA(self->d_scene_nodes.upload(nodes.data(), nodes.size()));
-    YH_CUDA(self->d_scene_prims.upload(prims.data(), prims.size()));
-    scene_tree_pending = false;
-  }
-  return upload_tables(self);  // the tables carry the new pointers
+  std::vector<float4> nodes;
+  std::vector<int>    prims;
+  build_scene_tree(this, nodes, prims);
+  YH_CUDA(self->d_scene_nodes.upload(nodes.data(), nodes.size()));
+  YH_CUDA(self->d_scene_prims.upload(prims.data(), prims.size()));
+  scene_tree_pending = false;
+  return YH_OK;
 }
 
 yh_scene::~yh_scene() {
@@ -1002,10 +898,11 @@ static yh_status upload_tables(yh_scene* sc) {
   return YH_OK;
 }
 
-yh_status yh::scene_create(const yh_scene_desc* d, const yh_scene* ties_from, yh_scene** out) {
+extern "C" {
+
+yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) {
   YH_REQUIRE_DEVICE();
   if (!d || !out) return fail(YH_ERR_INVALID, "yh_scene_create: null argument");
-  if (ties_from && (int)ties_from->shapes.size() != d->num_shapes) return fail(YH_ERR_INVALID, "yh_scene_create: replica of a different scene");
   *out = nullptr;
   // ---- validate: anything outside the hot-path scope fails loudly ----
   for (int i = 0; i < d->num_materials; i++) {
@@ -1078,20 +975,6 @@ yh_status yh::scene_create(const yh_scene_desc* d, const yh_scene* ties_from, yh
         hs->d_elems.upload(hs->elems().data(), hs->elems().size()) != cudaSuccess)
       return bail(fail(YH_ERR_CUDA, "shape %d: device upload failed: %s", i, cudaGetErrorString(cudaGetLastError())));
   }
-  for (size_t i = 0; i < sc->shapes.size(); i++) {
-    auto hs = sc->shapes[i];
-    if (hs->num_elems() == 0) continue;
-    if (ties_from) {
-      hs->tie_future = ties_from->shapes[i]->tie_future;
-      continue;
-    }
-    hs->tie_future = std::async(std::launch::async, [hs]() -> std::shared_ptr<const host_shape::tie_tables> {
-      auto t = std::make_shared<host_shape::tie_tables>();
-      reference_tree_order(*hs, t->ref_pos, t->tie_nodes, t->root_bbox);
-      return t;
-    }).share();
-  }
-  sc->ties_pending = true;
   for (int i = 0; i < d->num_textures; i++) {
     auto& t = d->textures[i];
     if (!t.colorf || t.width <= 0 || t.height <= 0) return bail(fail(YH_ERR_INVALID, "texture %d is empty", i));
@@ -1139,10 +1022,6 @@ yh_status yh::scene_create(const yh_scene_desc* d, const yh_scene* ties_from, yh
   return YH_OK;
 }
 
-extern "C" {
-
-yh_status yh_scene_create(const yh_scene_desc* d, yh_scene** out) { return yh::scene_create(d, nullptr, out); }
-
 void yh_scene_destroy(yh_scene* scene) { delete scene; }
 
 yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
@@ -1153,6 +1032,8 @@ yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
   sc->stats = yh_bvh_stats{};
   for (auto s : sc->shapes) {
     yh_status st = build_shape_bvh(*s, max_split, params ? params->quality : 0);
+    if (st != YH_OK) return st;
+    st = build_tie_order(*s);  // the reference's leaf order (exact-t ties) and its exact root box, on the device
     if (st != YH_OK) return st;
     sc->stats.num_primitives += s->num_elems();
     sc->stats.num_references += s->num_refs;
@@ -1169,12 +1050,28 @@ yh_status yh_scene_init_bvh(yh_scene* sc, const yh_bvh_params* params) {
   for (auto& o : sc->objects)
     if (o.bbox.min.x <= o.bbox.max.x) sc->world_bbox = {min3(sc->world_bbox.min, o.bbox.min), max3(sc->world_bbox.max, o.bbox.max)};
   if (!(sc->world_bbox.min.x <= sc->world_bbox.max.x)) sc->world_bbox = {{0, 0, 0}, {0, 0, 0}};
+  sc->bvh_built = true;
   {
-    std::lock_guard<std::mutex> lock(sc->tie_mutex);
+    std::lock_guard<std::mutex> lock(sc->tree_mutex);
     sc->scene_tree_pending = true;  // its node boxes are unions of the bounds just computed
   }
-  sc->bvh_built = true;
+  yh_status st = sc->sync_scene_tree();
+  if (st != YH_OK) return st;
   return upload_tables(sc);
+}
+
+yh_status yh_scene_reference_order(const yh_scene* sc, int shape, int* order, int64_t* count) {
+  YH_REQUIRE_DEVICE();
+  if (!sc || shape < 0 || shape >= (int)sc->shapes.size() || !count) return fail(YH_ERR_INVALID, "yh_scene_reference_order: bad argument");
+  if (!sc->bvh_built) return fail(YH_ERR_STATE, "yh_scene_reference_order: call yh_scene_init_bvh first");
+  const host_shape* s = sc->shapes[shape];
+  int               n = s->num_elems();
+  *count = n;
+  if (!order || n == 0) return YH_OK;
+  std::vector<int> ref_pos(n);
+  YH_CUDA(cudaMemcpy(ref_pos.data(), s->d_ref_pos.ptr, 4 * (size_t)n, cudaMemcpyDeviceToHost));
+  for (int e = 0; e < n; e++) order[ref_pos[e]] = e;
+  return YH_OK;
 }
 
 yh_status yh_scene_bvh_stats(const yh_scene* sc, yh_bvh_stats* stats) {

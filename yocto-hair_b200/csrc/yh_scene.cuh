@@ -23,14 +23,14 @@
 //                  t, the reference keeps the one its own BVH visits last
 //                  (intersect_line accepts t == tmax, yocto_math.h:3450).  So
 //                  the topology of the reference's tree (split_middle,
-//                  yocto_pathtrace.cpp:564-595) is kept beside ours: ref_pos[e] =
+//                  yocto_pathtrace.cpp:564-595), grown on the device by
+//                  yh_tieorder.cu, is kept beside ours: ref_pos[e] =
 //                  position of element e in the reference's leaf order, and
 //                  tie_nodes[k] = {mid, axis, left, right} of its internal
 //                  nodes (child < 0: leaf).  Only ties read them.
 //   shading data : the reference's own arrays (positions, normals = hair
 //                  tangents, lines / triangles) for eval_position / eval_normal.
 #pragma once
-#include <future>
 #include <mutex>
 #include <vector>
 
@@ -152,20 +152,9 @@ struct host_shape {
   bool is_lines() const { return points.empty() && !lines.empty(); }
   int  kind() const { return is_points() ? 2 : is_lines() ? 1 : 0; }  // 0 triangles, 1 lines, 2 points
   const std::vector<int>& elems() const { return is_points() ? points : is_lines() ? lines : triangles; }
-  // The reference's leaf order (tie tables) is a host computation of ~25 ms per million primitives: it starts in
-  // yh_scene_create, runs beside the uploads, the device BVH build, the light tables and the state set-up, and
-  // is joined by the first call that traverses (yh_scene::sync_ties()).
-  struct tie_tables {
-    std::vector<int>  ref_pos;
-    std::vector<int4> tie_nodes;
-    bbox3f            root_bbox;  // the reference's shape->bvh->nodes[0].bbox: exact union of the primitive bounds
-  };
-  std::shared_ptr<const tie_tables> ties;  // set once the future was joined (sync_ties)
-  // shared: the replicas of one scene on several devices (yh_group) compute the tables once
-  std::shared_future<std::shared_ptr<const tie_tables>> tie_future;
-  ~host_shape() {
-    if (tie_future.valid()) tie_future.wait();
-  }
+  // exact root box of the reference's tree (union of the primitive bounds), from yh_tieorder.cu: the top-level tree
+  // over the objects is built from it
+  bbox3f ref_root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
 };
 
 }  // namespace yh
@@ -189,23 +178,20 @@ struct yh_scene {
   yh::dev_buffer<yh::dev_light>       d_lights;
   yh::dev_buffer<float4>              d_scene_nodes;  // top-level tree (dev_scene::scene_nodes)
   yh::dev_buffer<int>                 d_scene_prims;
-  mutable bool                        scene_tree_pending = true;  // (re)built by sync_ties after init_bvh
+  mutable bool                        scene_tree_pending = true;  // (re)built by sync_scene_tree in init_bvh
   bool bvh_built = false, lights_built = false;
   bool has_volumes = false;  // some material is refractive (!thin && transmission): paths carry a volume state
   int  device = 0;
   yh::bbox3f   world_bbox{{0, 0, 0}, {0, 0, 0}};  // union of the objects' padded bounds (yh_scene_init_bvh)
   yh_bvh_stats stats{};
   yh::dev_scene view() const;
-  // joins the host threads that compute the reference leaf order and uploads their tables (once); every entry
-  // point that launches a traversal calls it first
-  yh_status sync_ties() const;
-  mutable std::mutex tie_mutex;
-  mutable bool       ties_pending = false;
+  // (re)builds the top-level tree over the objects after yh_scene_init_bvh
+  yh_status sync_scene_tree() const;
+  mutable std::mutex tree_mutex;
   ~yh_scene();
 };
 
 namespace yh {
-// yh_scene_create; with `ties_from` (a scene created from the SAME description, on any device) the reference leaf
-// order is not computed again but shared with it
-yh_status scene_create(const yh_scene_desc* desc, const yh_scene* ties_from, yh_scene** out);
+// yh_tieorder.cu: fills sh.d_ref_pos / sh.d_tie_nodes / sh.ref_root_bbox (the reference's leaf order, on the device)
+yh_status build_tie_order(host_shape& sh);
 }

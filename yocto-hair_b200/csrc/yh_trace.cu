@@ -1001,10 +1001,6 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
   if (!st || num_samples < 0) return fail(YH_ERR_INVALID, "yh_trace_samples: bad argument");
   st->last = yh_trace_stats{};
   if (num_samples == 0 || st->num_slots == 0) return YH_OK;
-  {
-    yh_status ts = st->scene->sync_ties();
-    if (ts != YH_OK) return ts;
-  }
   dev_scene    sc = st->scene->view();
   trace_consts tc = {st->width, st->height, st->params.bounces, st->params.clamp, st->counter ? 1 : 0, st->srank, st->sworld,
       st->slots_per_pixel, (unsigned long long)st->params.seed, st->params.shader};
@@ -1235,10 +1231,6 @@ yh_status yh_intersect_batch_dev(const yh_scene* scene, const yh_ray* rays_dev, 
   if (!scene || n < 0 || (n > 0 && (!rays_dev || !hits_dev))) return fail(YH_ERR_INVALID, "yh_intersect_batch_dev: bad argument");
   if (!scene->bvh_built) return fail(YH_ERR_STATE, "yh_intersect_batch: call yh_scene_init_bvh first");
   if (n == 0) return YH_OK;
-  {
-    yh_status ts = scene->sync_ties();
-    if (ts != YH_OK) return ts;
-  }
   cudaEvent_t e0, e1;
   YH_CUDA(cudaEventCreate(&e0));
   YH_CUDA(cudaEventCreate(&e1));

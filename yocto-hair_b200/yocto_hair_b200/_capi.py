@@ -128,6 +128,7 @@ PROTOTYPES = {
     "yh_scene_destroy": (None, [_P]),
     "yh_scene_init_bvh": (C.c_int, [_P, C.POINTER(BvhParams)]),
     "yh_scene_init_lights": (C.c_int, [_P]),
+    "yh_scene_reference_order": (C.c_int, [_P, C.c_int, c_int_p, C.POINTER(C.c_int64)]),
     "yh_scene_bvh_stats": (C.c_int, [_P, C.POINTER(BvhStats)]),
     "yh_intersect_batch": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P]),
     "yh_intersect_batch_dev": (C.c_int, [_P, _P, C.c_int64, C.c_int, _P, c_float_p]),

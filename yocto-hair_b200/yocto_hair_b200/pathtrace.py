@@ -66,6 +66,14 @@ class DeviceScene:
         capi.check(self.lib.yh_scene_init_lights(self.handle))
         return self
 
+    def reference_order(self, shape: int) -> np.ndarray:
+        """Primitive order of the reference's BVH over `shape`, as the device restates it (yh_scene_reference_order)."""
+        n = C.c_int64()
+        capi.check(self.lib.yh_scene_reference_order(self.handle, shape, None, C.byref(n)))
+        order = np.zeros(n.value, np.int32)
+        capi.check(self.lib.yh_scene_reference_order(self.handle, shape, order.ctypes.data_as(capi.c_int_p), C.byref(n)))
+        return order
+
     def bvh_stats(self) -> capi.BvhStats:
         s = capi.BvhStats()
         capi.check(self.lib.yh_scene_bvh_stats(self.handle, C.byref(s)))
