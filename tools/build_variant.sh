@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/../yocto-hair_b200/csrc"
 mkdir -p variants
 name=$1; shift
-for f in yh_bsdf yh_scene yh_trace yh_group; do
+for f in $(ls yh_*.cu | sed "s/\.cu$//"); do
   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo --fmad=false -Xcompiler -fPIC,-ffp-contract=off -Xptxas -v "$@" -c $f.cu -o variants/$name.$f.o 2> variants/$name.$f.log &
 done
 wait
