@@ -242,11 +242,12 @@ struct wavefront_io {  // by value: references to kernel parameters would force 
 #ifndef YH_INTERSECT_BLOCKS
 #define YH_INTERSECT_BLOCKS 7
 #endif
+template <bool CAN_SUSPEND>
 __global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(dev_scene sc, path_state ps, queues q, int cur,
     const int* active, suspend_io sus) {
   __shared__ int smem_stack[kStackShared * kTraceBlock];
   int            n = q.count[cur];
-  if (sus.out_records) {  // rays carried over: read this launch's share, write the next one's (counts [6 + cur], [7 - cur])
+  if (CAN_SUSPEND) {  // rays carried over: read this launch's share, write the next one's (counts [6 + cur], [7 - cur])
     sus.n_in      = min(q.count[6 + cur], sus.capacity);  // (reservations past the end of the buffer hold nothing)
     sus.out_count = q.count + 6 + (cur ^ 1);
   }
@@ -254,8 +255,8 @@ __global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(
   __shared__ int smem_park[kParkSlots * kTraceBlock];
   __shared__ int smem_cold[kColdWords * kTraceBlock];
   wavefront_io   io{sc, ps, q, active};
-  trace_persistent(sc, io, n, q.count + 5, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x, false,
-      &nv, &pt, sus.out_records ? &sus : nullptr);
+  trace_persistent<CAN_SUSPEND>(sc, io, n, q.count + 5, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x, false,
+      &nv, &pt, &sus);
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(q.stats + 0, (unsigned long long)n);
 #ifdef YH_TRAVERSAL_STATS
   atomicAdd(q.stats + 3, nv);
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kTraceBlock) k_intersect_batch(dev_scene sc, c
   __shared__ int smem_park[kParkSlots * kTraceBlock];
   __shared__ int smem_cold[kColdWords * kTraceBlock];
   batch_io       io{rays, hits};
-  trace_persistent(sc, io, n, cursor, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x,
+  trace_persistent<false>(sc, io, n, cursor, smem_stack + threadIdx.x, smem_park + threadIdx.x, smem_cold + threadIdx.x,
       find_any != 0, nullptr, nullptr);
 }
 
@@ -847,8 +848,12 @@ static yh_status assign_slots(yh_state* st) {
     YH_CUDA(grp->q_hair.alloc(m));
     YH_CUDA(grp->q_count.alloc(8));
     YH_CUDA(grp->stats.alloc(8));
-    {  // suspend records: enough for every lane of a resident traversal grid to hand over a ray or two
-      int cap = 1 << 15;
+    {  // Suspend records (yh_traverse.cuh): the long rays of a launch's tail go to the next launch.  It pays when a
+       // launch is small against the device - the tail is then a large part of it (C2: +9 %) - and costs about a
+       // percent when launches are large (C3, C5: more, smaller wavefront iterations), so groups above kSuspendMaxSlots
+       // slots run the plain kernel.  YH_SUSPEND_CAP (records per group, 0 = off) overrides.
+      const size_t kSuspendMaxSlots = 600000;
+      int cap = m <= kSuspendMaxSlots ? 1 << 15 : 0;
       if (const char* e = getenv("YH_SUSPEND_CAP")) cap = std::max(0, atoi(e));
       grp->sus_capacity = (int)std::min<size_t>((size_t)cap, m);
       if (grp->sus_capacity > 0) {
@@ -1007,7 +1012,7 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
   int  sms    = sm_count();
   bool prof   = st->profile;  // per-kernel timing: every group runs on ONE stream, nothing overlaps
   int  grid_t = sms * 8, grid_s = sms * 4;
-  int  grid_i = persistent_grid((const void*)k_intersect);
+  int  grid_i = persistent_grid((const void*)k_intersect<false>);
   // the groups share the device: each group's persistent traversal grid takes its share of the resident blocks
   int  ngroups = (int)st->groups.size();
   int  grid_div = 1;
@@ -1063,9 +1068,12 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
       int          next = g->cur ^ 1;
       k_reset_counts<<<1, 1, 0, s>>>(q.count, next);
       if (prof) ev(s);
-      suspend_io sus{};
-      if (g->sus_capacity > 0) sus = {g->sus_records[g->cur].ptr, 0, g->sus_records[next].ptr, nullptr, g->sus_capacity};
-      k_intersect<<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur], sus);
+      if (g->sus_capacity > 0) {
+        suspend_io sus = {g->sus_records[g->cur].ptr, 0, g->sus_records[next].ptr, nullptr, g->sus_capacity};
+        k_intersect<true><<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur], sus);
+      } else {
+        k_intersect<false><<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur], suspend_io{});
+      }
       YH_DEBUG_KERNEL("k_intersect", s);
       if (prof) ev(s);
       k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);

@@ -539,7 +539,10 @@ struct suspend_io {
 enum suspend_word { SW_CUR = CW_COUNT, SW_PARK_COUNT, SW_PARK0, SW_STACK_COUNT = SW_PARK0 + YH_PARK_SLOTS, SW_BASE_COUNT, SW_STACK0 };
 static_assert(SW_STACK0 + 96 <= kSuspendWords, "a suspend record holds the whole stack");
 
-template <class IO>
+// CAN_SUSPEND is a template parameter, not a run-time test: the mere presence of the hand-over code in the loop costs
+// the traversal 5 % (instruction cache; measured on C3 with the buffer switched off), so launches that do not use it
+// run an instantiation without it.
+template <bool CAN_SUSPEND, class IO>
 __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, int n, int* cursor, int* smem_stack,
     int* smem_park, int* smem_cold, bool find_any, unsigned long long* nodes_visited,
     unsigned long long* prims_tested, const suspend_io* sus = nullptr) {
@@ -567,13 +570,13 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
   slab_consts k = {0, 0, 0, 0, 0, 0, kSelLo, kSelLo, kSelLo, kSelHi, kSelHi, kSelHi};
   const uint4* __restrict__ slots = nullptr;
 
-  const int n_resume = sus ? sus->n_in : 0;  // work items [0, n_resume) are suspended rays, the rest the queue
+  const int n_resume = CAN_SUSPEND ? sus->n_in : 0;  // work items [0, n_resume) are suspended rays, the rest the queue
   const int n_items  = n + n_resume;
   bool      keep_on  = false;  // the record buffer is full: finish in place
   int       bursts   = 0;      // node-step bursts this lane's ray has taken in this launch
   while (true) {
     // ---- 0. the queue is exhausted and few lanes still hold a ray: hand them to the next launch
-    if (sus && exhausted && !keep_on) {
+    if (CAN_SUSPEND && exhausted && !keep_on) {
       const bool     ripe = have && bursts >= kSuspendMinBursts;
       const unsigned busy = __ballot_sync(full, have), out = __ballot_sync(full, ripe);
       const int      nb   = __popc(out);
@@ -620,7 +623,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
           int   index = base + __popc(idle & ((1u << lane) - 1));
           ray3f wr;
           int   handle;
-          if (index < n_resume) {  // a ray suspended by the previous launch: restore its walk where it stopped
+          if (CAN_SUSPEND && index < n_resume) {  // a ray suspended by the previous launch: restore its walk where it stopped
             const int* rec = sus->in_records + (size_t)index * kSuspendWords;
             const int  stored = __ldcs(rec + SW_CUR);
             if (stored != kSuspendEmpty) {  // (an empty record: a reservation that did not fit, see step 0)
