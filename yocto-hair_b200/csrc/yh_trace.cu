@@ -231,9 +231,14 @@ struct wavefront_io {  // by value: references to kernel parameters would force 
     st_stream(&ps.hit[slot], make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y)));
     if (ps.hit_dist) st_stream(&ps.hit_dist[slot], h.distance);
     int kind     = !h.hit ? 0 : (sc.shapes[sc.objects[h.object].shape].is_lines ? 2 : 1);
-    queue_push(q.miss, q.count + 2, kind == 0, slot);
-    queue_push(q.surface, q.count + 3, kind == 1, slot);
-    queue_push(q.hair, q.count + 4, kind == 2, slot);
+    // one append for the three shading queues (miss, surface, hair are consecutive in q.count): lanes that go to the
+    // same queue share one atomic
+    int*     queue = kind == 0 ? q.miss : (kind == 1 ? q.surface : q.hair);
+    unsigned peers = __match_any_sync(__activemask(), kind);
+    int      lane = threadIdx.x & 31, leader = __ffs(peers) - 1, base = 0;
+    if (lane == leader) base = atomicAdd(q.count + 2 + kind, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    queue[base + __popc(peers & ((1u << lane) - 1))] = slot;
   }
 };
 

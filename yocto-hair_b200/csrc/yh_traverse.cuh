@@ -410,12 +410,11 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
   return hit;
 }
 
-// conservative ray / box test for the object level
-__device__ __forceinline__ bool hits_box(const ray3f& ray, const bbox3f& b) {
-  float idx = 1.0f / ray.d.x, idy = 1.0f / ray.d.y, idz = 1.0f / ray.d.z;
-  float a0 = (b.min.x - ray.o.x) * idx, b0 = (b.max.x - ray.o.x) * idx;
-  float a1 = (b.min.y - ray.o.y) * idy, b1 = (b.max.y - ray.o.y) * idy;
-  float a2 = (b.min.z - ray.o.z) * idz, b2 = (b.max.z - ray.o.z) * idz;
+// conservative ray / box test for the object level (inv = 1 / direction, formed once per ray)
+__device__ __forceinline__ bool hits_box(const ray3f& ray, const vec3f& inv, const bbox3f& b) {
+  float a0 = (b.min.x - ray.o.x) * inv.x, b0 = (b.max.x - ray.o.x) * inv.x;
+  float a1 = (b.min.y - ray.o.y) * inv.y, b1 = (b.max.y - ray.o.y) * inv.y;
+  float a2 = (b.min.z - ray.o.z) * inv.z, b2 = (b.max.z - ray.o.z) * inv.z;
   float tn = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fmaxf(fminf(a2, b2), ray.tmin));
   float tf = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fminf(fmaxf(a2, b2), ray.tmax));
   return tn * 0.999999f <= tf * 1.000001f;
@@ -720,6 +719,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
       }
       vec3f wo, wd;
       io.reload(handle, wo, wd);
+      const vec3f winv = {1.0f / wd.x, 1.0f / wd.y, 1.0f / wd.z};
       bool opened = false;
       // intersect_scene_bvh, :960-1028: depth-first over the top-level tree, the child on the ray's near side of the
       // split axis first, the objects of a leaf in order.  Entries >= 0 are nodes, < 0 objects (~index).
@@ -730,12 +730,12 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         ray3f wr = {wo, wd, tmin, tmax};
         if (entry >= 0) {
           const float4 lo = __ldg(&sc.scene_nodes[2 * entry]), hi = __ldg(&sc.scene_nodes[2 * entry + 1]);
-          if (!hits_box(wr, {{lo.x, lo.y, lo.z}, {hi.x, hi.y, hi.z}})) continue;
+          if (!hits_box(wr, winv, {{lo.x, lo.y, lo.z}, {hi.x, hi.y, hi.z}})) continue;
           const int a = __float_as_int(lo.w), b = __float_as_int(hi.w);
           if (b & 0x100) {
             const int  axis = b & 3;
-            const float dc  = axis == 0 ? wd.x : (axis == 1 ? wd.y : wd.z);
-            if ((1.0f / dc) < 0) st.push(a), st.push(a + 1);  // :983-989
+            const float dinv = axis == 0 ? winv.x : (axis == 1 ? winv.y : winv.z);
+            if (dinv < 0) st.push(a), st.push(a + 1);  // ray_dsign[node.axis], :983-989
             else st.push(a + 1), st.push(a);
           } else {
             for (int k = (b >> 16) - 1; k >= 0; k--) st.push(~__ldg(sc.scene_prims + a + k));
@@ -745,7 +745,7 @@ __device__ __forceinline__ void trace_persistent(const dev_scene& sc, IO& io, in
         }
         obj = ~entry;
         const dev_object& ob = sc.objects[obj];
-        if (!hits_box(wr, ob.bbox)) continue;
+        if (!hits_box(wr, winv, ob.bbox)) continue;
         const dev_shape& sh = sc.shapes[ob.shape];
         if (sh.num_refs == 0) continue;
         vec3f     o = transform_point(ob.inv_frame, wo), d = transform_vector(ob.inv_frame, wd);
