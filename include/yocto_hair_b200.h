@@ -403,7 +403,8 @@ yh_status yh_rng_floats(uint64_t seed, uint64_t seq, int n, float* out);
 
 /* libm replicas evaluated on the device (parity diagnostics).
  * fn: 0 expf 1 logf 2 sinf 3 cosf 4 atan2f(x=a,y=b) 5 acosf 6 asin(double)->float
- *     7 sinh(double)->double stored as two floats hi/lo is NOT provided; see tests. */
+ *     7 (float)(1 / (sinh(1/a) * 2a)) in double  8 fmodf(a, b)
+ *     9 / 10 / 11: the double sinh(1/a) * 2a of mp() as an exact hi / mid / lo float expansion */
 yh_status yh_libm_batch(int fn, const float* a, const float* b, int64_t n,
     float* out);
 

@@ -505,6 +505,11 @@ void yho_libm_batch(int fn, const float* a, const float* b, int64_t n, float* ou
       case 6: out[i] = (float)asin((double)a[i]); break;
       case 7: out[i] = (float)(1.0 / (sinh((double)(1 / a[i])) * 2 * a[i])); break;
       case 8: out[i] = fmodf(a[i], b[i]); break;
+      case 9: case 10: case 11: { /* the double denominator of mp() (ye:205-206) as an exact three-float expansion */
+        double den = sinh((double)(1 / a[i])) * 2 * a[i];
+        float  hi = (float)den, mid = (float)(den - (double)hi), lo = (float)(den - (double)hi - (double)mid);
+        out[i] = fn == 9 ? hi : (fn == 10 ? mid : lo);
+      } break;
       default: out[i] = 0;
     }
   }

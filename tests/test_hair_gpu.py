@@ -54,6 +54,45 @@ def test_libm_bit_exact(ref, lib):
     assert np.array_equal(hair.libm(4, a, b).view(np.uint32), ref.libm(4, a, b).view(np.uint32))
 
 
+def test_double_asin_and_sinh_over_their_whole_float_domains(ref):
+    """safe_asin and mp() take asin / sinh in DOUBLE and round once to float (yocto_extension.cpp:111, :205-206); the device
+    uses CUDA's double routines there, glibc's are the reference's.  Their inputs are floats, so the claim "same bits" can be
+    checked over the whole domain instead of a sample: every float in [2^-12, 1] of both signs for asin (below that asin(x)
+    rounds to x for any faithful routine: sampled), and every float v in (0.1, 110] - the range of hair_brdf::v[] on the
+    sinh branch of mp() - for the double denominator sinh(1 / v) * 2 v, compared as an exact three-float expansion."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def host(fn, a):  # glibc through the checker, all host threads (ctypes releases the GIL)
+        parts = np.array_split(a, 32)
+        with ThreadPoolExecutor(16) as ex:
+            return np.concatenate(list(ex.map(lambda p: ref.libm(fn, p), parts)))
+
+    def floats_between(lo, hi):
+        b0, b1 = np.float32(lo).view(np.uint32), np.float32(hi).view(np.uint32)
+        return np.arange(int(b0), int(b1) + 1, dtype=np.uint32).view(np.float32)
+
+    chunk = 1 << 25
+    x = floats_between(2.0 ** -12, 1.0)
+    total = 0
+    for k in range(0, len(x), chunk):
+        for sign in (1.0, -1.0):
+            a = np.ascontiguousarray(x[k:k + chunk] * np.float32(sign))
+            d, r = hair.libm(6, a), host(6, a)
+            assert np.array_equal(d.view(np.uint32), r.view(np.uint32)), "asin differs near %r" % a[np.nonzero(d.view(np.uint32) != r.view(np.uint32))[0][:4]]
+            total += len(a)
+    tiny = np.random.default_rng(2).uniform(-2.0 ** -12, 2.0 ** -12, 1_000_000).astype(np.float32)
+    assert np.array_equal(hair.libm(6, tiny).view(np.uint32), host(6, tiny).view(np.uint32))
+    v = floats_between(np.nextafter(np.float32(0.1), np.float32(1)), 110.0)
+    for k in range(0, len(v), chunk):
+        a = np.ascontiguousarray(v[k:k + chunk])
+        for fn in (9, 10, 11):
+            d, r = hair.libm(fn, a), host(fn, a)
+            bad = np.nonzero(d.view(np.uint32) != r.view(np.uint32))[0]
+            assert bad.size == 0, "sinh denominator part %d differs for v = %r (%d values)" % (fn, a[bad[:4]], bad.size)
+        total += len(a)
+    print("asin + sinh denominators compared bit for bit on %d inputs" % total)
+
+
 def test_eval_hair_brdf(data, ref):
     dev = hair.eval_hair_brdf(data["materials"], data["v"], data["normals"], data["tangents"])
     d, r = hair.brdf_view(dev)[:, :27], hair.brdf_view(data["ref_brdf"])[:, :27]  # skip frame origin (+-0)

@@ -64,3 +64,25 @@ def test_atan2f_bit_exact(hostlib):
     both_nan = np.isnan(ours) & np.isnan(libc)
     bad = (ours.view(np.uint32) != libc.view(np.uint32)) & ~both_nan
     assert not bad.any(), f"atan2f: {bad.sum()} mismatches at {a[bad][:4]}, {b[bad][:4]}"
+
+
+def test_double_sinh_is_glibcs_over_the_domain_of_mp(hostlib):
+    """mp() (yocto_extension.cpp:205-206) divides by sinh(1 / v) * 2 v in DOUBLE.  yh_libm.cuh restates glibc's
+    e_sinh.c over s_expm1.c (the FMA variant its ifunc selects on the oracle's CPU); here the DOUBLE results are compared
+    bit for bit with glibc's sinh for a dense sample of the float arguments v in (0.1, 110] - every 64th float, 1.3 M
+    values; the GPU test walks all 85 M - and outside it."""
+    hostlib.yh_host_sinh_batch.argtypes = [C.c_int, _P, C.c_long, _P]
+    hostlib.yh_host_sinh_batch.restype = None
+
+    def sinh_bits(which, v):
+        v = np.ascontiguousarray(v, np.float32)
+        out = np.zeros(len(v), np.uint64)
+        hostlib.yh_host_sinh_batch(which, v.ctypes.data_as(_P), len(v), out.ctypes.data_as(_P))
+        return out
+
+    b0, b1 = np.float32(0.1).view(np.uint32), np.float32(110.0).view(np.uint32)
+    v = np.arange(int(b0), int(b1) + 1, 64, dtype=np.uint32).view(np.float32)
+    assert np.array_equal(sinh_bits(0, v), sinh_bits(1, v))
+    rng = np.random.default_rng(4)
+    wide = np.concatenate([rng.uniform(0.046, 0.1, 200_000), rng.uniform(110, 1e6, 200_000), np.exp(rng.uniform(-3, 30, 200_000))]).astype(np.float32)
+    assert np.array_equal(sinh_bits(0, wide), sinh_bits(1, wide))

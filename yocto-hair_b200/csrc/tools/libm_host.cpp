@@ -6,6 +6,14 @@
 #include "yh_libm.cuh"
 
 extern "C" {
+// double sinh of x = 1 / v as mp() takes it (v float): which 0 = restatement (yh::sinh_d), 1 = glibc; raw double bits out
+void yh_host_sinh_batch(int which, const float* v, long n, unsigned long long* out) {
+  for (long i = 0; i < n; i++) {
+    double x = (double)(1.0f / v[i]);
+    double r = which == 0 ? yh::sinh_d(x) : sinh(x);
+    memcpy(&out[i], &r, 8);
+  }
+}
 // fn: 0 expf 1 logf 2 sinf 3 cosf 4 atan2f(a,b) 5 acosf; which: 0 = restatement, 1 = glibc
 void yh_host_libm_batch(int fn, int which, const float* a, const float* b, long n, float* out) {
   for (long i = 0; i < n; i++) {

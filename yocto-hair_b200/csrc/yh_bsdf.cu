@@ -119,6 +119,11 @@ __global__ void k_libm(int fn, const float* a, const float* b, int64_t count, fl
       case 6: r = (float)asin_d((double)a[i]); break;
       case 7: r = (float)(1.0 / (sinh_d((double)div_(1.0f, a[i])) * 2.0 * (double)a[i])); break;
       case 8: r = fmodf_(a[i], b[i]); break;
+      case 9: case 10: case 11: {  // the DOUBLE denominator of mp(), sinh(1 / v) * 2 * v, as an exact three-float expansion
+        double den = sinh_d((double)div_(1.0f, a[i])) * 2.0 * (double)a[i];
+        float  hi = (float)den, mid = (float)(den - (double)hi), lo = (float)(den - (double)hi - (double)mid);
+        r = fn == 9 ? hi : (fn == 10 ? mid : lo);
+      } break;
     }
     out[i] = r;
   }
@@ -358,7 +363,7 @@ yh_status yh_rng_floats(uint64_t seed, uint64_t seq, int n, float* out) {
 
 yh_status yh_libm_batch(int fn, const float* a, const float* b, int64_t n, float* out) {
   YH_REQUIRE_DEVICE();
-  if (fn < 0 || fn > 8 || n < 0 || (n > 0 && (!a || !out))) return fail(YH_ERR_INVALID, "yh_libm_batch: bad argument");
+  if (fn < 0 || fn > 11 || n < 0 || (n > 0 && (!a || !out))) return fail(YH_ERR_INVALID, "yh_libm_batch: bad argument");
   if (n == 0) return YH_OK;
   dev_buffer<float> da, dbb, dout;
   YH_CUDA(up(da, a, n));

@@ -11,10 +11,10 @@
 //   atan2f / atanf / acosf     = Sun fdlibm float code,
 //       sysdeps/ieee754/flt-32/{e_atan2f,s_atanf,e_acosf}.c: float arithmetic,
 //       so it must run without FMA contraction (this TU: --fmad=false).
-//   asin / sinh (double)       = CUDA's double routines (<= 2 ulp in double);
-//       every call site rounds the result to float, so the float agrees with
-//       glibc's except when the exact value lies within ~1e-16 relative of a
-//       float rounding boundary.
+//   asin (double)              = CUDA's double routine; the call site rounds to
+//       float and the floats agree with glibc's over the whole float domain.
+//   sinh (double)              = glibc's e_sinh.c / s_expm1.c (fdlibm) restated in
+//       double arithmetic without contraction: the double itself is glibc's.
 // Why: mp() sums terms of magnitude 1/v (up to ~3000) in fp32, so a 1-ulp
 // difference in logf moves the BSDF by ~1e-4 relative.  1e-5 parity needs the
 // same bits out of libm, not merely "accurate" functions.
@@ -377,8 +377,121 @@ YH_HD float fmodf_(float a, float b) {
 #endif
 }
 
-// double asin / sinh: see the header comment.
+// double asin: CUDA's routine; every call site rounds the result to float, and the floats agree with glibc's for EVERY
+// float argument in [-1, 1] (tests/test_hair_gpu.py::test_double_asin_and_sinh_over_their_whole_float_domains).
 YH_HD double asin_d(double x) { return ::asin(x); }
-YH_HD double sinh_d(double x) { return ::sinh(x); }
+
+// double sinh as glibc computes it (sysdeps/ieee754/dbl-64/e_sinh.c over s_expm1.c, the fdlibm routines; glibc 2.39
+// has no FMA variant of either, so every multiply-add is two roundings).  mp() divides by sinh(1 / v) * 2 v in double
+// (yocto_extension.cpp:205-206); CUDA's own ::sinh differs from glibc's in the last bits of the double for 1.4 % of
+// the arguments, which can move the float quotient across a rounding boundary once in ~10^10 calls.  With the same
+// operations in the same order the denominator carries glibc's bits for every float v (checked exhaustively over
+// (0.1, 110], host and device).
+YH_HD uint32_t d_hi(double x) { return (uint32_t)(d2u(x) >> 32); }
+YH_HD double   d_with_hi(double x, uint32_t hi) { return u2d((d2u(x) & 0xffffffffull) | ((uint64_t)hi << 32)); }
+YH_HD double   ddiv(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __ddiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+// s_expm1.c.  On a CPU with FMA + AVX2 glibc's ifunc picks __expm1_fma, in which GCC contracted the multiply-adds
+// marked dfma below (read off the disassembly of libm-2.39: vfmadd / vfnmadd / vfmsub at exactly these places; k, the
+// sums of differences and the exponent arithmetic are not fused).  YH_LIBM_FMA = 0 gives the baseline variant.
+// e_sinh.c itself has no FMA variant.
+YH_HD double expm1_d(double x) {
+  const double one = 1.0, huge = 1.0e+300, o_threshold = 7.09782712893383973096e+02, ln2_hi = 6.93147180369123816490e-01,
+               ln2_lo = 1.90821492927058770002e-10, invln2 = 1.44269504088896338700e+00, Q1 = -3.33333333333331316428e-02,
+               Q2 = 1.58730158725481460165e-03, Q3 = -7.93650757867487942473e-05, Q4 = 4.00821782732936239552e-06,
+               Q5 = -2.01099218183624371326e-07;
+  double   y, hi, lo, c = 0, t, e, hxs, hfx, r1, h2, h4, R1, R2, R3;
+  int      k;
+  uint32_t hx  = d_hi(x);
+  uint32_t xsb = hx & 0x80000000u;
+  hx &= 0x7fffffffu;
+  if (hx >= 0x4043687Au) {  // |x| >= 56 ln2
+    if (hx >= 0x40862E42u) {  // |x| >= 709.78
+      if (hx >= 0x7ff00000u) {
+        if (((hx & 0xfffffu) | (uint32_t)d2u(x)) != 0) return dadd(x, x);  // NaN
+        return xsb == 0 ? x : -1.0;                                       // exp(+-inf) - 1
+      }
+      if (x > o_threshold) return dmul(huge, huge);
+    }
+    if (xsb != 0) return -1.0;  // x < -56 ln2 (the reference raises inexact here)
+  }
+  if (hx > 0x3fd62e42u) {      // |x| > 0.5 ln2
+    if (hx < 0x3FF0A2B2u) {    // and |x| < 1.5 ln2
+      if (xsb == 0) hi = dadd(x, -ln2_hi), lo = ln2_lo, k = 1;
+      else hi = dadd(x, ln2_hi), lo = -ln2_lo, k = -1;
+    } else {
+      k  = (int)dadd(dmul(invln2, x), xsb == 0 ? 0.5 : -0.5);
+      t  = (double)k;
+      hi = dfma(-t, ln2_hi, x);
+      lo = dmul(t, ln2_lo);
+    }
+    x = dadd(hi, -lo);
+    c = dadd(dadd(hi, -x), -lo);
+  } else if (hx < 0x3c900000u) {  // |x| < 2^-54
+    t = dadd(huge, x);
+    return dadd(x, -dadd(t, -dadd(huge, x)));
+  } else {
+    k = 0;
+  }
+  hfx = dmul(0.5, x);
+  hxs = dmul(x, hfx);
+  R1  = dfma(hxs, Q1, one);
+  h2  = dmul(hxs, hxs);
+  R2  = dfma(hxs, Q3, Q2);
+  h4  = dmul(h2, h2);
+  R3  = dfma(hxs, Q5, Q4);
+  r1  = dfma(h4, R3, dfma(h2, R2, R1));
+  t   = dfma(-r1, hfx, 3.0);
+  e   = dmul(hxs, ddiv(dadd(r1, -t), dfma(-x, t, 6.0)));
+  if (k == 0) return dadd(x, -dfma(x, e, -hxs));
+  e = dfma(x, dadd(e, -c), -c);
+  e = dadd(e, -hxs);
+  if (k == -1) return dfma(0.5, dadd(x, -e), -0.5);
+  if (k == 1) {
+    if (x < -0.25) return dmul(-2.0, dadd(e, -dadd(x, 0.5)));
+    return dfma(2.0, dadd(x, -e), one);
+  }
+  if (k <= -2 || k > 56) {
+    y = dadd(one, -dadd(e, -x));
+    y = d_with_hi(y, d_hi(y) + ((uint32_t)k << 20));
+    return dadd(y, -one);
+  }
+  t = one;
+  if (k < 20) {
+    t = d_with_hi(t, 0x3ff00000u - (0x200000u >> k));  // 1 - 2^-k
+    y = dadd(t, -dadd(e, -x));
+    y = d_with_hi(y, d_hi(y) + ((uint32_t)k << 20));
+  } else {
+    t = d_with_hi(t, (uint32_t)(0x3ff - k) << 20);  // 2^-k
+    y = dadd(x, -dadd(e, t));
+    y = dadd(y, one);
+    y = d_with_hi(y, d_hi(y) + ((uint32_t)k << 20));
+  }
+  return y;
+}
+YH_HD_CALL double sinh_d(double x) {  // e_sinh.c
+  const double one = 1.0, shuge = 1.0e307;
+  uint32_t jx = d_hi(x), ix = jx & 0x7fffffffu;
+  if (ix >= 0x7ff00000u) return dadd(x, x);
+  double h = (jx & 0x80000000u) ? -0.5 : 0.5;
+  double ax = u2d(d2u(x) & 0x7fffffffffffffffull);
+  if (ix < 0x40360000u) {  // |x| < 22
+    if (ix < 0x3e300000u && dadd(shuge, x) > one) return x;  // |x| < 2^-28
+    double t = expm1_d(ax);
+    if (ix < 0x3ff00000u) return dmul(h, dadd(dmul(2.0, t), -ddiv(dmul(t, t), dadd(t, one))));
+    return dmul(h, dadd(t, ddiv(t, dadd(t, one))));
+  }
+  // |x| >= 22 does not occur on this path (x = 1 / v, v > 0.1); CUDA's routine keeps the function total
+#if defined(__CUDA_ARCH__)
+  return ::sinh(x);
+#else
+  return __builtin_sinh(x);
+#endif
+}
 
 }  // namespace yh

@@ -517,7 +517,7 @@ constexpr int kColdWords = CW_COUNT;
 // fresh rays, so the long rays run inside the bulk of that launch.  A suspended path simply takes part in the
 // shading one wavefront iteration later; nothing about its result changes.
 #ifndef YH_SUSPEND_LANES
-#define YH_SUSPEND_LANES 12
+#define YH_SUSPEND_LANES 4
 #endif
 constexpr int kSuspendLanes = YH_SUSPEND_LANES;
 // ... and only rays that have walked at least this many bursts of kInnerSteps node steps in this launch are handed over,
