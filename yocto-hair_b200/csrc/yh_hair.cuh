@@ -55,10 +55,11 @@ YH_HD vec3f sigma_a_from_reflectance(const vec3f& c, float beta_n) {
   return q * q;
 }
 
-// eval_hair_brdf, yocto_extension.cpp:127-177
-YH_HD hair_brdf eval_hair_brdf(const hair_material& material, float v, const vec3f& normal,
-    const vec3f& tangent) {
-  hair_brdf brdf;
+// eval_hair_brdf, yocto_extension.cpp:127-177, in two parts: what depends on the MATERIAL only (absorption, the
+// longitudinal variances v[], the azimuthal scale s, the scale-tilt terms: :131-146, :151-167) and what depends on the
+// hit (h, gamma_o, the frame: :148-149, :169-175).  The wavefront evaluates the first part once per material
+// (dev_material::hair_proto, k_material_hair_consts) instead of once per vertex - same operations, same bits.
+YH_HD void hair_brdf_material_part(const hair_material& material, hair_brdf& brdf) {
   brdf.sigma_a = {0, 0, 0};
   if (nonzero(material.sigma_a)) {
     brdf.sigma_a = material.sigma_a;
@@ -71,8 +72,6 @@ YH_HD hair_brdf eval_hair_brdf(const hair_material& material, float v, const vec
   float beta_n = material.beta_n;
   brdf.alpha   = material.alpha;
   brdf.eta     = material.eta;
-  brdf.h       = -1 + 2 * v;
-  brdf.gamma_o = safe_asin(brdf.h);
   brdf.v[0]    = sqr(0.726f * beta_m + 0.812f * sqr(beta_m) + 3.7f * pow20_(beta_m));
   brdf.v[1]    = 0.25f * brdf.v[0];
   brdf.v[2]    = 4 * brdf.v[0];
@@ -84,7 +83,17 @@ YH_HD hair_brdf eval_hair_brdf(const hair_material& material, float v, const vec
     brdf.sin_2k_alpha[i] = 2 * brdf.cos_2k_alpha[i - 1] * brdf.sin_2k_alpha[i - 1];
     brdf.cos_2k_alpha[i] = sqr(brdf.cos_2k_alpha[i - 1]) - sqr(brdf.sin_2k_alpha[i - 1]);
   }
+}
+YH_HD void hair_brdf_hit_part(hair_brdf& brdf, float v, const vec3f& normal, const vec3f& tangent) {
+  brdf.h             = -1 + 2 * v;
+  brdf.gamma_o       = safe_asin(brdf.h);
   brdf.world_to_brdf = inverse_rigid(frame_fromzx(normal, tangent));
+}
+YH_HD hair_brdf eval_hair_brdf(const hair_material& material, float v, const vec3f& normal,
+    const vec3f& tangent) {
+  hair_brdf brdf;
+  hair_brdf_material_part(material, brdf);
+  hair_brdf_hit_part(brdf, v, normal, tangent);
   return brdf;
 }
 
@@ -109,14 +118,18 @@ YH_HD float log_i0(float x) {
   else
     return logf_(i0(x));
 }
-// :201-207.  The v > 0.1 branch mixes in a double sinh: float / (double*int*float).
-YH_HD_CALL float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v) {
+// :201-207.  The v > 0.1 branch mixes in a double sinh: float / (double*int*float).  That denominator depends on v
+// alone, i.e. on the material: mp_den() forms it, and the wavefront passes the per-material value in (hair_den).
+YH_HD double mp_den(float v) { return sinh_d((double)div_(1.0f, v)) * 2.0 * (double)v; }
+YH_HD_CALL float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v, double den) {
   float a = div_(cos_theta_i * cos_theta_o, v);
   float b = div_(sin_theta_i * sin_theta_o, v);
   if (v <= 0.1f)
     return expf_(log_i0(a) - b - div_(1.0f, v) + 0.6931f + logf_(div_(1.0f, (2 * v))));
-  double den = sinh_d((double)div_(1.0f, v)) * 2.0 * (double)v;
   return (float)((double)(expf_(-b) * i0(a)) / den);
+}
+YH_HD float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v) {
+  return mp(cos_theta_i, cos_theta_o, sin_theta_i, sin_theta_o, v, v <= 0.1f ? 0.0 : mp_den(v));
 }
 
 // fresnel_dielectric(eta, {0,0,1}, {0,0,cos_theta}), yocto_math.h:4215-4235
@@ -327,7 +340,7 @@ YH_HD float sample_hair_scattering_pdf(const hair_brdf& brdf, const hair_wo_term
 // reference's arithmetic, and feeds both sums in the reference's order, so f
 // and pdf carry the bits the two separate calls produce.
 YH_HD void eval_hair_scattering_and_pdf(const hair_brdf& brdf, const hair_wo_terms& t, const vec3f& incoming_,
-    vec3f& f, float& pdf) {
+    vec3f& f, float& pdf, const double* den) {  // den[p] = mp_den(brdf.v[p]) (read only where v[p] > 0.1)
   vec3f incoming    = transform_direction(brdf.world_to_brdf, incoming_);
   float sin_theta_i = incoming.x;
   float cos_theta_i = safe_sqrt(1 - sqr(sin_theta_i));
@@ -339,12 +352,12 @@ YH_HD void eval_hair_scattering_and_pdf(const hair_brdf& brdf, const hair_wo_ter
     float sin_theta_op, cos_theta_op;
     tilt(brdf, p, t.sin_theta_o, t.cos_theta_o, sin_theta_op, cos_theta_op);
     cos_theta_op = fabs_(cos_theta_op);
-    float m = mp(cos_theta_i, cos_theta_op, sin_theta_i, sin_theta_op, brdf.v[p]);
+    float m = mp(cos_theta_i, cos_theta_op, sin_theta_i, sin_theta_op, brdf.v[p], den[p]);
     float n = np(phi, p, brdf.s, brdf.gamma_o, t.gamma_t);
     f = f + m * t.ap[p] * n;
     pdf += m * t.ap_pdf[p] * n;
   }
-  float m = mp(cos_theta_i, t.cos_theta_o, sin_theta_i, t.sin_theta_o, brdf.v[p_max]);
+  float m = mp(cos_theta_i, t.cos_theta_o, sin_theta_i, t.sin_theta_o, brdf.v[p_max], den[p_max]);
   f = f + m * t.ap[p_max] / (2 * pif);
   pdf += m * t.ap_pdf[p_max] * div_(1.0f, (2 * pif));
 }

@@ -760,6 +760,18 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   return YH_OK;
 }
 
+// per-material part of eval_hair_brdf + the denominators of mp(), with the device's own arithmetic
+__global__ void k_material_hair_consts(dev_material* materials, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dev_material& m  = materials[i];
+  hair_material hm = {m.sigma_a, m.beta_m, m.beta_n, m.alpha, m.eta, m.color, m.eumelanin, m.pheomelanin};
+  hair_brdf     b{};
+  hair_brdf_material_part(hm, b);
+  m.hair_proto = b;
+  for (int p = 0; p <= p_max; p++) m.hair_den[p] = b.v[p] <= 0.1f ? 0.0 : mp_den(b.v[p]);
+}
+
 // transform_bbox(frame, bbox), yocto_math.h:3172-3182: the exact form the reference feeds to its top-level builder
 static bbox3f transform_bbox_exact(const frame3f& f, const bbox3f& b) {
   bbox3f out = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
@@ -891,6 +903,11 @@ static yh_status upload_tables(yh_scene* sc) {
   }
   YH_CUDA(sc->d_shapes.upload(ds.data(), ds.size()));
   YH_CUDA(sc->d_materials.upload(sc->materials.data(), sc->materials.size()));
+  if (!sc->materials.empty()) {
+    k_material_hair_consts<<<((int)sc->materials.size() + 63) / 64, 64>>>(sc->d_materials.ptr, (int)sc->materials.size());
+    YH_CUDA(cudaGetLastError());
+    YH_CUDA(cudaDeviceSynchronize());
+  }
   YH_CUDA(sc->d_objects.upload(sc->objects.data(), sc->objects.size()));
   YH_CUDA(sc->d_textures.upload(sc->textures.data(), sc->textures.size()));
   YH_CUDA(sc->d_environments.upload(sc->environments.data(), sc->environments.size()));

@@ -35,6 +35,7 @@
 #include <vector>
 
 #include "yh_common.cuh"
+#include "yh_hair.cuh"
 #include "yh_intersect.cuh"
 
 namespace yh {
@@ -79,6 +80,10 @@ struct dev_material {
   float eumelanin, pheomelanin;
   vec3f sigma_a;
   float beta_m, beta_n, alpha, eta;
+  // what eval_hair_brdf derives from the material alone (hair_brdf_material_part) and the double denominators of mp()
+  // for its four lobes, filled on the DEVICE by k_material_hair_consts after every upload of the table
+  hair_brdf hair_proto;
+  double    hair_den[4];
 };
 
 struct dev_object {

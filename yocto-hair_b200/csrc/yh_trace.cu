@@ -415,9 +415,8 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     surface_brdf  sb;
     bool          delta = false;
     if (HAIR) {
-      hair_material hm = {mat.sigma_a, mat.beta_m, mat.beta_n, mat.alpha, mat.eta, mat.color, mat.eumelanin,
-          mat.pheomelanin};
-      hb = eval_hair_brdf(hm, uv.y, normal, tangent);  // :474-490
+      hb = mat.hair_proto;  // eval_hair_brdf, :474-490: the material's part comes from the table, the hit's part here
+      hair_brdf_hit_part(hb, uv.y, normal, tangent);
       ht = hair_prepare_wo(hb, outgoing);
     } else {
       surface_material sm = {base, specular, metallic, roughness, mat.ior, transmission, mat.thin != 0 || mat.transmission == 0};
@@ -429,7 +428,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       vec3f f;
       if (HAIR) {
         float unused_pdf;
-        eval_hair_scattering_and_pdf(hb, ht, outgoing, f, unused_pdf);
+        eval_hair_scattering_and_pdf(hb, ht, outgoing, f, unused_pdf, mat.hair_den);
       } else {
         f = eval_brdfcos(sb, normal, outgoing, outgoing);
       }
@@ -464,7 +463,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       incoming  = sample_lights(sc, position, rl, rel, ruv);
     }
     if (HAIR) {
-      eval_hair_scattering_and_pdf(hb, ht, incoming, brdfcos, brdf_pdf);  // :1071-1073, :1219-1221
+      eval_hair_scattering_and_pdf(hb, ht, incoming, brdfcos, brdf_pdf, mat.hair_den);  // :1071-1073, :1219-1221
     } else {
       brdfcos  = eval_brdfcos(sb, normal, outgoing, incoming);
       brdf_pdf = sample_brdfcos_pdf(sb, normal, outgoing, incoming);
