@@ -111,25 +111,48 @@ YH_HD float i0(float x) {
   }
   return val;
 }
-// :194-199
-YH_HD float log_i0(float x) {
+// :194-199.  log(2 pi) is the same call with the same argument every time: log_2pi carries its value.
+YH_HD float log_i0(float x, float log_2pi) {
   if (x > 12)
-    return x + 0.5f * (-logf_(2 * pif) + logf_(div_(1.0f, x)) + div_(1.0f, (8 * x)));
+    return x + 0.5f * (-log_2pi + logf_(div_(1.0f, x)) + div_(1.0f, (8 * x)));
   else
     return logf_(i0(x));
 }
-// :201-207.  The v > 0.1 branch mixes in a double sinh: float / (double*int*float).  That denominator depends on v
-// alone, i.e. on the material: mp_den() forms it, and the wavefront passes the per-material value in (hair_den).
+YH_HD float log_i0(float x) { return log_i0(x, logf_(2 * pif)); }
+
+// What the lobes compute from the MATERIAL's numbers alone (the variances v[] and the logistic scale s), gathered so
+// that the wavefront forms each value once per material (dev_material::hair_k, k_material_hair_consts) and not once per
+// lobe per vertex.  Every field is the result of the very call the reference makes at that place, with the same
+// argument, so using the stored value changes no bit:
+//   mp(), :201-207      sinh(1 / v) * 2 * v   (double: float / (double*int*float)), 1 / v, log(1 / (2 v))
+//   log_i0(), :196      log(2 pi)
+//   trimmed_logistic(), :243-245 and sample_trimmed_logistic(), :359-363, always called with [a, b] = [-pi, pi]:
+//                       logistic_cdf(-pi, s) and logistic_cdf(pi, s) - logistic_cdf(-pi, s)
+//   sample_hair_scattering(), :436   exp(-2 / v[p])
+struct hair_consts {
+  double mp_den[p_max + 1];      // read only where v[p] > 0.1
+  float  inv_v[p_max + 1];       // read only where v[p] <= 0.1, like the next
+  float  log_inv_2v[p_max + 1];
+  float  exp_m2_inv_v[p_max + 1];
+  float  log_2pi;
+  float  cdf_lo, cdf_width;
+};
 YH_HD double mp_den(float v) { return sinh_d((double)div_(1.0f, v)) * 2.0 * (double)v; }
-YH_HD_CALL float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v, double den) {
+YH_HD_CALL float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v, double den,
+    float inv_v, float log_inv_2v, float log_2pi) {
   float a = div_(cos_theta_i * cos_theta_o, v);
   float b = div_(sin_theta_i * sin_theta_o, v);
-  if (v <= 0.1f)
-    return expf_(log_i0(a) - b - div_(1.0f, v) + 0.6931f + logf_(div_(1.0f, (2 * v))));
+  if (v <= 0.1f) return expf_(log_i0(a, log_2pi) - b - inv_v + 0.6931f + log_inv_2v);
   return (float)((double)(expf_(-b) * i0(a)) / den);
 }
+YH_HD float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v, int p,
+    const hair_consts& k) {
+  return mp(cos_theta_i, cos_theta_o, sin_theta_i, sin_theta_o, v, k.mp_den[p], k.inv_v[p], k.log_inv_2v[p], k.log_2pi);
+}
 YH_HD float mp(float cos_theta_i, float cos_theta_o, float sin_theta_i, float sin_theta_o, float v) {
-  return mp(cos_theta_i, cos_theta_o, sin_theta_i, sin_theta_o, v, v <= 0.1f ? 0.0 : mp_den(v));
+  bool small = v <= 0.1f;
+  return mp(cos_theta_i, cos_theta_o, sin_theta_i, sin_theta_o, v, small ? 0.0 : mp_den(v),
+      small ? div_(1.0f, v) : 0.0f, small ? logf_(div_(1.0f, (2 * v))) : 0.0f, logf_(2 * pif));
 }
 
 // fresnel_dielectric(eta, {0,0,1}, {0,0,cos_theta}), yocto_math.h:4215-4235
@@ -148,14 +171,21 @@ YH_HD float fresnel_dielectric_cos(float eta, float cos_theta) {
 }
 
 // ap(), :209-230
-YH_HD void ap(float cos_theta_o, float eta, float h, const vec3f& T, vec3f out[p_max + 1]) {
+// The Fresnel term depends on (cos_theta_o, eta, h) only - not on the transmittance T - so the two ap() calls of one
+// shading point (eval :291 and compute_ap_pdf :391, which differ in T alone) share it: ap_fresnel() once, ap_from() twice.
+YH_HD float ap_fresnel(float cos_theta_o, float eta, float h) {
   float cos_gamma_o = safe_sqrt(1 - h * h);
   float cos_theta   = cos_theta_o * cos_gamma_o;
-  float f           = fresnel_dielectric_cos(eta, cos_theta);
+  return fresnel_dielectric_cos(eta, cos_theta);
+}
+YH_HD void ap_from(float f, const vec3f& T, vec3f out[p_max + 1]) {
   out[0]            = {f, f, f};
   out[1]            = sqr(1 - f) * T;
   for (int p = 2; p < p_max; p++) out[p] = out[p - 1] * T * f;
   out[p_max] = out[p_max - 1] * f * T / (vec3f{1.f, 1.f, 1.f} - T * f);
+}
+YH_HD void ap(float cos_theta_o, float eta, float h, const vec3f& T, vec3f out[p_max + 1]) {
+  ap_from(ap_fresnel(cos_theta_o, eta, h), T, out);
 }
 
 YH_HD float phi_p(int p, float gamma_o, float gamma_t) {  // :232-234
@@ -163,17 +193,25 @@ YH_HD float phi_p(int p, float gamma_o, float gamma_t) {  // :232-234
 }
 YH_HD float logistic(float x, float s) {  // :236-239
   x = fabs_(x);
-  return div_(expf_(div_(-x, s)), (s * sqr(1 + expf_(div_(-x, s)))));
+  float e = expf_(div_(-x, s));  // the reference writes the call twice; same argument, same value
+  return div_(e, (s * sqr(1 + e)));
 }
 YH_HD float logistic_cdf(float x, float s) { return div_(1.0f, (1 + expf_(div_(-x, s)))); }  // :241
 YH_HD float trimmed_logistic(float x, float s, float a, float b) {  // :243-245
   return div_(logistic(x, s), (logistic_cdf(b, s) - logistic_cdf(a, s)));
 }
-YH_HD_CALL float np(float phi, int p, float s, float gamma_o, float gamma_t) {  // :247-253
+YH_HD float np_dphi(float phi, int p, float gamma_o, float gamma_t) {
   float dphi = phi - phi_p(p, gamma_o, gamma_t);
   while (dphi > pif) dphi -= 2 * pif;
   while (dphi < -pif) dphi += 2 * pif;
-  return trimmed_logistic(dphi, s, -pif, pif);
+  return dphi;
+}
+YH_HD_CALL float np(float phi, int p, float s, float gamma_o, float gamma_t) {  // :247-253
+  return trimmed_logistic(np_dphi(phi, p, gamma_o, gamma_t), s, -pif, pif);
+}
+// the same with the denominator of trimmed_logistic(., s, -pi, pi) taken from the material's constants
+YH_HD_CALL float np(float phi, int p, float s, float gamma_o, float gamma_t, float cdf_width) {
+  return div_(logistic(np_dphi(phi, p, gamma_o, gamma_t), s), cdf_width);
 }
 
 // hair scale tilt for lobe p, :297-322 (shared by eval / sample / pdf)
@@ -196,7 +234,7 @@ YH_HD void tilt(const hair_brdf& brdf, int p, float sin_theta_o, float cos_theta
 
 // compute_ap_pdf, :365-397: note sin_theta_o = safe_sqrt(1 - cos^2) here, which
 // is |sin_theta_o| up to rounding, so Ap is evaluated again for the pdf.
-YH_HD void hair_ap_pdf(const hair_brdf& brdf, float cos_theta_o, float ap_pdf[p_max + 1]) {
+YH_HD void hair_ap_pdf(const hair_brdf& brdf, float cos_theta_o, float f, float ap_pdf[p_max + 1]) {
   float sin_theta_o = safe_sqrt(1 - cos_theta_o * cos_theta_o);
   float sin_theta_t = div_(sin_theta_o, brdf.eta);
   float cos_theta_t = safe_sqrt(1 - sqr(sin_theta_t));
@@ -205,7 +243,7 @@ YH_HD void hair_ap_pdf(const hair_brdf& brdf, float cos_theta_o, float ap_pdf[p_
   float cos_gamma_t = safe_sqrt(1 - sqr(sin_gamma_t));
   vec3f T           = exp3(-brdf.sigma_a * div_(2 * cos_gamma_t, cos_theta_t));
   vec3f a[p_max + 1];
-  ap(cos_theta_o, brdf.eta, brdf.h, T, a);
+  ap_from(f, T, a);
   float sum_y = 0.0f;
   for (int i = 0; i <= p_max; i++) sum_y += luminance(a[i]);
   for (int i = 0; i <= p_max; i++) ap_pdf[i] = div_(luminance(a[i]), sum_y);
@@ -235,8 +273,9 @@ YH_HD hair_wo_terms hair_prepare_wo(const hair_brdf& brdf, const vec3f& outgoing
   float cos_gamma_t = safe_sqrt(1 - sqr(sin_gamma_t));
   t.gamma_t         = safe_asin(sin_gamma_t);
   vec3f T           = exp3(-brdf.sigma_a * div_(2 * cos_gamma_t, cos_theta_t));
-  ap(t.cos_theta_o, brdf.eta, brdf.h, T, t.ap);
-  hair_ap_pdf(brdf, t.cos_theta_o, t.ap_pdf);
+  float f = ap_fresnel(t.cos_theta_o, brdf.eta, brdf.h);
+  ap_from(f, T, t.ap);
+  hair_ap_pdf(brdf, t.cos_theta_o, f, t.ap_pdf);
   return t;
 }
 // eval_hair_scattering, :255-336
@@ -276,14 +315,32 @@ YH_HD vec2f demux_float(float f) {
   uint32_t b0 = compact1by1((uint32_t)v), b1 = compact1by1((uint32_t)(v >> 1));
   return {div_((float)b0, 65536.0f), div_((float)b1, 65536.0f)};
 }
-YH_HD float sample_trimmed_logistic(float u, float s, float a, float b) {  // :359-363
-  float k = logistic_cdf(b, s) - logistic_cdf(a, s);
-  float x = -s * logf_(div_(1.0f, (u * k + logistic_cdf(a, s))) - 1);
+YH_HD float sample_trimmed_logistic(float u, float s, float a, float b, float cdf_lo, float cdf_width) {
+  float x = -s * logf_(div_(1.0f, (u * cdf_width + cdf_lo)) - 1);
   return clampf(x, a, b);
+}
+YH_HD float sample_trimmed_logistic(float u, float s, float a, float b) {  // :359-363
+  return sample_trimmed_logistic(u, s, a, b, logistic_cdf(a, s), logistic_cdf(b, s) - logistic_cdf(a, s));
+}
+YH_HD hair_consts make_hair_consts(const hair_brdf& brdf) {
+  hair_consts k;
+  for (int p = 0; p <= p_max; p++) {
+    float v = brdf.v[p];
+    bool small = v <= 0.1f;
+    k.mp_den[p]       = small ? 0.0 : mp_den(v);
+    k.inv_v[p]        = small ? div_(1.0f, v) : 0.0f;
+    k.log_inv_2v[p]   = small ? logf_(div_(1.0f, (2 * v))) : 0.0f;
+    k.exp_m2_inv_v[p] = expf_(div_(-2.0f, v));
+  }
+  k.log_2pi   = logf_(2 * pif);
+  k.cdf_lo    = logistic_cdf(-pif, brdf.s);
+  k.cdf_width = logistic_cdf(pif, brdf.s) - k.cdf_lo;
+  return k;
 }
 
 // sample_hair_scattering, :399-479
-YH_HD vec3f sample_hair_scattering(const hair_brdf& brdf, const hair_wo_terms& t, const vec2f& rn) {
+YH_HD vec3f sample_hair_scattering(const hair_brdf& brdf, const hair_wo_terms& t, const vec2f& rn,
+    const hair_consts& k) {
   vec2f u0 = demux_float(rn.x), u1 = demux_float(rn.y);
   const float* ap_pdf = t.ap_pdf;
   int p = 0;
@@ -295,20 +352,23 @@ YH_HD vec3f sample_hair_scattering(const hair_brdf& brdf, const hair_wo_terms& t
   tilt(brdf, p, t.sin_theta_o, t.cos_theta_o, sin_theta_op, cos_theta_op);
   u1.x            = fmax_(u1.x, 1e-5f);
   float vp        = brdf.v[p];
-  float cos_theta = 1 + vp * logf_(u1.x + (1 - u1.x) * expf_(div_(-2.0f, vp)));
+  float cos_theta = 1 + vp * logf_(u1.x + (1 - u1.x) * k.exp_m2_inv_v[p]);
   float sin_theta = safe_sqrt(1 - sqr(cos_theta));
   float cos_phi   = cosf_(2 * pif * u1.y);
   float sin_theta_i = -cos_theta * sin_theta_op + sin_theta * cos_phi * cos_theta_op;
   float cos_theta_i = safe_sqrt(1 - sqr(sin_theta_i));
   float dphi;
   if (p < p_max)
-    dphi = phi_p(p, brdf.gamma_o, t.gamma_t) + sample_trimmed_logistic(u0.y, brdf.s, -pif, pif);
+    dphi = phi_p(p, brdf.gamma_o, t.gamma_t) + sample_trimmed_logistic(u0.y, brdf.s, -pif, pif, k.cdf_lo, k.cdf_width);
   else
     dphi = 2 * pif * u0.y;
   float phi_i    = t.phi_o + dphi;
   vec3f incoming = {sin_theta_i, cos_theta_i * cosf_(phi_i), cos_theta_i * sinf_(phi_i)};
   // inverse(world_to_brdf) is the rigid inverse again = its transpose (:478)
   return transform_direction(transpose_rot(brdf.world_to_brdf), incoming);
+}
+YH_HD vec3f sample_hair_scattering(const hair_brdf& brdf, const hair_wo_terms& t, const vec2f& rn) {
+  return sample_hair_scattering(brdf, t, rn, make_hair_consts(brdf));
 }
 YH_HD vec3f sample_hair_scattering(const hair_brdf& brdf, const vec3f& outgoing, const vec2f& rn) {
   return sample_hair_scattering(brdf, hair_prepare_wo(brdf, outgoing), rn);
@@ -340,7 +400,7 @@ YH_HD float sample_hair_scattering_pdf(const hair_brdf& brdf, const hair_wo_term
 // reference's arithmetic, and feeds both sums in the reference's order, so f
 // and pdf carry the bits the two separate calls produce.
 YH_HD void eval_hair_scattering_and_pdf(const hair_brdf& brdf, const hair_wo_terms& t, const vec3f& incoming_,
-    vec3f& f, float& pdf, const double* den) {  // den[p] = mp_den(brdf.v[p]) (read only where v[p] > 0.1)
+    vec3f& f, float& pdf, const hair_consts& k) {
   vec3f incoming    = transform_direction(brdf.world_to_brdf, incoming_);
   float sin_theta_i = incoming.x;
   float cos_theta_i = safe_sqrt(1 - sqr(sin_theta_i));
@@ -352,12 +412,12 @@ YH_HD void eval_hair_scattering_and_pdf(const hair_brdf& brdf, const hair_wo_ter
     float sin_theta_op, cos_theta_op;
     tilt(brdf, p, t.sin_theta_o, t.cos_theta_o, sin_theta_op, cos_theta_op);
     cos_theta_op = fabs_(cos_theta_op);
-    float m = mp(cos_theta_i, cos_theta_op, sin_theta_i, sin_theta_op, brdf.v[p], den[p]);
-    float n = np(phi, p, brdf.s, brdf.gamma_o, t.gamma_t);
+    float m = mp(cos_theta_i, cos_theta_op, sin_theta_i, sin_theta_op, brdf.v[p], p, k);
+    float n = np(phi, p, brdf.s, brdf.gamma_o, t.gamma_t, k.cdf_width);
     f = f + m * t.ap[p] * n;
     pdf += m * t.ap_pdf[p] * n;
   }
-  float m = mp(cos_theta_i, t.cos_theta_o, sin_theta_i, t.sin_theta_o, brdf.v[p_max], den[p_max]);
+  float m = mp(cos_theta_i, t.cos_theta_o, sin_theta_i, t.sin_theta_o, brdf.v[p_max], p_max, k);
   f = f + m * t.ap[p_max] / (2 * pif);
   pdf += m * t.ap_pdf[p_max] * div_(1.0f, (2 * pif));
 }

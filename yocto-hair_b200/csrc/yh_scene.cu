@@ -769,7 +769,7 @@ __global__ void k_material_hair_consts(dev_material* materials, int n) {
   hair_brdf     b{};
   hair_brdf_material_part(hm, b);
   m.hair_proto = b;
-  for (int p = 0; p <= p_max; p++) m.hair_den[p] = b.v[p] <= 0.1f ? 0.0 : mp_den(b.v[p]);
+  m.hair_k = make_hair_consts(b);
 }
 
 // transform_bbox(frame, bbox), yocto_math.h:3172-3182: the exact form the reference feeds to its top-level builder

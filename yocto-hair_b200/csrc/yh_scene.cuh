@@ -80,10 +80,11 @@ struct dev_material {
   float eumelanin, pheomelanin;
   vec3f sigma_a;
   float beta_m, beta_n, alpha, eta;
-  // what eval_hair_brdf derives from the material alone (hair_brdf_material_part) and the double denominators of mp()
-  // for its four lobes, filled on the DEVICE by k_material_hair_consts after every upload of the table
-  hair_brdf hair_proto;
-  double    hair_den[4];
+  // what eval_hair_brdf derives from the material alone (hair_brdf_material_part) and what the lobes derive from that
+  // (hair_consts: the denominators of mp(), the normalisation of the trimmed logistic, ...), filled on the DEVICE by
+  // k_material_hair_consts after every upload of the table
+  hair_brdf   hair_proto;
+  hair_consts hair_k;
 };
 
 struct dev_object {

@@ -428,7 +428,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       vec3f f;
       if (HAIR) {
         float unused_pdf;
-        eval_hair_scattering_and_pdf(hb, ht, outgoing, f, unused_pdf, mat.hair_den);
+        eval_hair_scattering_and_pdf(hb, ht, outgoing, f, unused_pdf, mat.hair_k);
       } else {
         f = eval_brdfcos(sb, normal, outgoing, outgoing);
       }
@@ -454,7 +454,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
     if (SHADER == YH_SHADER_NAIVE || rand1f(rng) < 0.5f) {
       vec2f rn  = rand2f(rng);
       float rnl = rand1f(rng);
-      if (HAIR) incoming = sample_hair_scattering(hb, ht, rn);  // :1133-1135
+      if (HAIR) incoming = sample_hair_scattering(hb, ht, rn, mat.hair_k);  // :1133-1135
       else incoming = sample_brdfcos(sb, normal, outgoing, rnl, rn);
     } else {
       vec2f ruv = rand2f(rng);
@@ -463,7 +463,7 @@ __device__ __forceinline__ bool shade_vertex(const dev_scene& sc, const path_sta
       incoming  = sample_lights(sc, position, rl, rel, ruv);
     }
     if (HAIR) {
-      eval_hair_scattering_and_pdf(hb, ht, incoming, brdfcos, brdf_pdf, mat.hair_den);  // :1071-1073, :1219-1221
+      eval_hair_scattering_and_pdf(hb, ht, incoming, brdfcos, brdf_pdf, mat.hair_k);  // :1071-1073, :1219-1221
     } else {
       brdfcos  = eval_brdfcos(sb, normal, outgoing, incoming);
       brdf_pdf = sample_brdfcos_pdf(sb, normal, outgoing, incoming);
