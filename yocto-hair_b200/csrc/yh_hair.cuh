@@ -106,7 +106,8 @@ YH_HD float i0(float x) {
   float x2i = 1;
 #pragma unroll
   for (int i = 0; i < 10; i++) {
-    val += div_(x2i, den[i]);
+    // 1, 4 and 64 are powers of two: the quotient is the exact product (div_pow2)
+    val += i == 0 ? x2i : i == 1 ? div_pow2(x2i, 0.25f) : i == 2 ? div_pow2(x2i, 0.015625f) : div_(x2i, den[i]);
     x2i *= x * x;
   }
   return val;
@@ -167,7 +168,7 @@ YH_HD float fresnel_dielectric_cos(float eta, float cos_theta) {
   float t2 = eta * cosw;
   float rs = div_((cosw - t1), (cosw + t1));
   float rp = div_((t0 - t2), (t0 + t2));
-  return div_((rs * rs + rp * rp), 2.0f);
+  return div_pow2((rs * rs + rp * rp), 0.5f);
 }
 
 // ap(), :209-230
@@ -313,7 +314,7 @@ YH_HD uint32_t compact1by1(uint32_t x) {
 YH_HD vec2f demux_float(float f) {
   uint64_t v = (uint64_t)(f * 4294967296.0f);
   uint32_t b0 = compact1by1((uint32_t)v), b1 = compact1by1((uint32_t)(v >> 1));
-  return {div_((float)b0, 65536.0f), div_((float)b1, 65536.0f)};
+  return {div_pow2((float)b0, 1.0f / 65536.0f), div_pow2((float)b1, 1.0f / 65536.0f)};
 }
 YH_HD float sample_trimmed_logistic(float u, float s, float a, float b, float cdf_lo, float cdf_width) {
   float x = -s * logf_(div_(1.0f, (u * cdf_width + cdf_lo)) - 1);

@@ -94,6 +94,9 @@ YH_HD vec3f normalize(const vec3f& a) {  // :2037 (returns the input when its le
 }
 YH_HD vec3f orthonormalize(const vec3f& a, const vec3f& b) { return normalize(a - b * dot(a, b)); }  // :2056
 YH_HD float max3(const vec3f& a) { return fmax_(fmax_(a.x, a.y), a.z); }  // :2092
+// x / 2^k written as x * 2^-k: both are the correctly rounded value of the same real number, so every bit agrees for
+// every x (zero, denormal, infinite included); the generic division is 8 instructions and a range check, this is one.
+YH_HD float div_pow2(float x, float inv_pow2) { return x * inv_pow2; }
 YH_HD float mean3(const vec3f& a) { return div_((a.x + a.y + a.z), 3.0f); }
 YH_HD bool  isfinite3(const vec3f& a) { return isfinite_(a.x) && isfinite_(a.y) && isfinite_(a.z); }
 YH_HD vec3f min3(const vec3f& a, const vec3f& b) { return {fmin_(a.x, b.x), fmin_(a.y, b.y), fmin_(a.z, b.z)}; }

@@ -31,7 +31,7 @@ YH_HD float fresnel_dielectric(float eta, const vec3f& normal, const vec3f& outg
   float t2 = eta * cosw;
   float rs = div_((cosw - t1), (cosw + t1));
   float rp = div_((t0 - t2), (t0 + t2));
-  return div_((rs * rs + rp * rp), 2.0f);
+  return div_pow2((rs * rs + rp * rp), 0.5f);
 }
 // fresnel_conductor, :4238-4263: the reference works on vec3f, every operation is per component
 YH_HD vec3f fresnel_conductor(const vec3f& eta, const vec3f& etak, const vec3f& normal, const vec3f& outgoing) {
@@ -45,13 +45,13 @@ YH_HD vec3f fresnel_conductor(const vec3f& eta, const vec3f& etak, const vec3f& 
     float t0       = eta2 - etak2 - sin2;
     float a2plusb2 = sqrt_(t0 * t0 + 4 * eta2 * etak2);
     float t1       = a2plusb2 + cos2;
-    float a        = sqrt_(div_((a2plusb2 + t0), 2.0f));
+    float a        = sqrt_(div_pow2((a2plusb2 + t0), 0.5f));
     float t2       = 2 * a * cosw;
     float rs       = div_((t1 - t2), (t1 + t2));
     float t3       = cos2 * a2plusb2 + sin2 * sin2;
     float t4       = t2 * sin2;
     float rp       = div_(rs * (t3 - t4), (t3 + t4));
-    return div_((rp + rs), 2.0f);
+    return div_pow2((rp + rs), 0.5f);
   };
   return {one(eta.x, etak.x), one(eta.y, etak.y), one(eta.z, etak.z)};
 }

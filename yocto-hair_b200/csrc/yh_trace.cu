@@ -116,7 +116,7 @@ __device__ __forceinline__ ray3f camera_ray(const dev_camera& cam, const trace_c
   vec3f e  = {0, 0, 0};
   if (cam.aperture != 0) {  // sample_disk, yocto_math.h:4897-4901
     float r = sqrt_(luv.y), phi = 2 * pif * luv.x;
-    e = {div_(cosf_(phi) * r * cam.aperture, 2.0f), div_(sinf_(phi) * r * cam.aperture, 2.0f), 0};
+    e = {div_pow2(cosf_(phi) * r * cam.aperture, 0.5f), div_pow2(sinf_(phi) * r * cam.aperture, 0.5f), 0};
   }
   vec3f p = dc * cam.focus / fabs_(dc.z);
   vec3f d = normalize(p - e);
