@@ -1127,12 +1127,12 @@ yh_status yh_scene_init_lights(yh_scene* sc) {
     auto buf = new dev_buffer<float>{};
     sc->light_cdfs.push_back(buf);
     YH_CUDA(buf->upload(cdf.data(), cdf.size()));
-    sc->lights.push_back({oi, -1, buf->ptr, nt, nullptr, 0, 0.0f, 0.0f});
+    sc->lights.push_back({oi, -1, buf->ptr, nt, nullptr, 0, 0.0f, 0.0f, nullptr});
   }
   for (int ei = 0; ei < (int)sc->environments.size(); ei++) {
     auto& e = sc->environments[ei];
     if (e.emission == vec3f{0, 0, 0}) continue;
-    dev_light l{-1, ei, nullptr, 0, nullptr, 0, 0.0f, 0.0f};
+    dev_light l{-1, ei, nullptr, 0, nullptr, 0, 0.0f, 0.0f, nullptr};
     if (e.tex >= 0) {
       int                w = sc->textures[e.tex].width, h = sc->textures[e.tex].height;
       auto&              px = sc->tex_host[e.tex];
@@ -1152,6 +1152,13 @@ yh_status yh_scene_init_lights(yh_scene* sc) {
       sc->light_cdfs.push_back(buf);
       YH_CUDA(buf->upload(cdf.data(), cdf.size()));
       l.cdf = buf->ptr, l.cdf_size = (int)cdf.size();
+      std::vector<float> row_angle(h);
+      for (int j = 0; j < h; j++)
+        row_angle[j] = div_(2 * pif, (float)w) * div_(pif, (float)h) * sinf_(div_(pif * (j + 0.5f), (float)h));
+      auto abuf = new dev_buffer<float>{};
+      sc->light_cdfs.push_back(abuf);
+      YH_CUDA(abuf->upload(row_angle.data(), row_angle.size()));
+      l.row_angle = abuf->ptr;
       // guide table (one bucket per texel)
       float back = cdf.back();
       int   G    = (int)cdf.size();

@@ -117,6 +117,9 @@ struct dev_light {
   const int*   guide;
   int          guide_size;
   float        guide_w, guide_inv_w;
+  // textured environments: the solid angle of a texel of row j, sample_lights_pdf's `angle` (:1347-1349), which
+  // depends on the row alone - formed once per row with the same operations instead of once per vertex
+  const float* row_angle;
 };
 
 struct dev_scene {

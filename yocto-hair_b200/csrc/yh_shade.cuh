@@ -238,9 +238,7 @@ __device__ __forceinline__ float sample_lights_pdf(const dev_scene& sc, const ve
         int   idx  = j * t.width + i;
         float c    = idx == 0 ? __ldg(light.cdf) : __ldg(light.cdf + idx) - __ldg(light.cdf + idx - 1);
         float prob = div_(c, __ldg(light.cdf + light.cdf_size - 1));
-        float angle = div_(2 * pif, (float)t.width) * div_(pif, (float)t.height) *
-                      sinf_(div_(pif * (j + 0.5f), (float)t.height));
-        pdf += div_(prob, angle);
+        pdf += div_(prob, __ldg(light.row_angle + j));  // the texel's solid angle, a function of the row (init_lights)
       } else {
         pdf += div_(1.0f, (4 * pif));
       }
