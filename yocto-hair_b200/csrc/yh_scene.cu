@@ -538,7 +538,7 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   bool lines = sh.is_lines();
   int  kind  = sh.kind();
   int  n     = sh.num_elems();
-  sh.root_leaf = 0, sh.num_refs = 0, sh.num_nodes = 0;
+  sh.root_leaf = 0, sh.num_refs = 0, sh.num_nodes = 0, sh.tiny_count = 0;
   sh.root_bbox = {{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};
   if (n == 0) return YH_OK;
   // YH_BUILD_TIMING=1: phase times of this build on stderr (host clock; each mark synchronises the device)
@@ -757,6 +757,27 @@ static yh_status build_shape_bvh(host_shape& sh, int max_split, int quality) {
   sh.root_bbox = {{rb.lo.x, rb.lo.y, rb.lo.z}, {rb.hi.x, rb.hi.y, rb.hi.z}};
   YH_CUDA(cudaDeviceSynchronize());
   mark("root box");
+  // a tree of at most kTinyRefs leaves (the quad of an area light): its leaf slots, so that the light-pdf rays test the
+  // primitives directly instead of walking boxes around two triangles (intersect_shape)
+  sh.tiny_count = 0;
+  if (R <= kTinyRefs) {
+    std::vector<uint4> slots(2 * num_slots);
+    YH_CUDA(cudaMemcpy(slots.data(), sh.d_slots.ptr, slots.size() * sizeof(uint4), cudaMemcpyDeviceToHost));
+    std::vector<int> open = {0};
+    while (!open.empty() && sh.tiny_count <= kTinyRefs) {
+      int node = open.back();
+      open.pop_back();
+      uint4 hi = slots[2 * (size_t)node + 1];  // words 4-7: w6 = first child, w7 bits 31 / 30 = child 0 / 1 is a leaf
+      int   child = (int)hi.z;
+      for (int c = 1; c >= 0; c--) {
+        bool leaf = c == 0 ? (int)hi.w < 0 : (int)(hi.w << 1) < 0;
+        if (child + c < 0 || child + c >= (int)num_slots) { sh.tiny_count = kTinyRefs + 1; break; }
+        if (leaf) { if (sh.tiny_count < kTinyRefs) sh.tiny_slots[sh.tiny_count] = child + c; sh.tiny_count++; }
+        else open.push_back(child + c);
+      }
+    }
+    if (sh.tiny_count != R) sh.tiny_count = 0;  // not the expected tree: keep the general walk
+  }
   return YH_OK;
 }
 
@@ -893,7 +914,9 @@ static yh_status upload_tables(yh_scene* sc) {
     dev_shape d{};
     d.slots = s->d_slots.ptr, d.tris = s->d_prims.ptr, d.slot_elem = s->d_slot_elem.ptr;
     d.ref_pos = s->d_ref_pos.ptr, d.tie_nodes = s->d_tie_nodes.ptr, d.num_tie_nodes = (int)s->d_tie_nodes.count;
-    d.root_leaf = s->root_leaf, d.num_refs = s->num_refs, d.is_lines = s->is_lines() ? 1 : 0, d.is_points = s->is_points() ? 1 : 0;
+    d.root_leaf = s->root_leaf, d.tiny_count = s->tiny_count, d.num_refs = s->num_refs;
+    for (int t = 0; t < 4; t++) d.tiny_slots[t] = s->tiny_slots[t];
+    d.is_lines = s->is_lines() ? 1 : 0, d.is_points = s->is_points() ? 1 : 0;
     d.scale = s->scale, d.grid_origin = s->grid_origin, d.grid_step = s->grid_step;
     d.has_normals = s->normals.empty() ? 0 : 1;
     d.positions = s->d_positions.ptr, d.normals = s->d_normals.ptr, d.elems = s->d_elems.ptr;

@@ -41,6 +41,7 @@
 namespace yh {
 
 constexpr int kDefaultSplit = 4;  // default yh_bvh_params::max_split
+constexpr int kTinyRefs = 4;    // shapes of up to this many leaves are tested without their boxes (light quads)
 constexpr int kRefLeafMax = 4;  // the reference's bvh_max_prims (yocto_pathtrace.cpp:598)
 
 struct dev_shape {
@@ -51,6 +52,8 @@ struct dev_shape {
   const int4*   tie_nodes;  // internal nodes of the reference's tree: mid, axis, left, right
   int           num_tie_nodes;
   int           root_leaf;  // the tree is a single leaf (slot 0)
+  int           tiny_count;     // 2..kTinyRefs leaves in all: their slots, tested directly by intersect_shape
+  int           tiny_slots[4];
   vec3f         grid_origin, grid_step;
   int           num_refs;
   float         scale;      // largest |coordinate| of the shape: boxes are padded by 2e-6 * scale
@@ -152,6 +155,7 @@ struct host_shape {
   dev_buffer<int>    d_slot_elem, d_ref_pos;
   dev_buffer<int4>   d_tie_nodes;
   int                root_leaf = 0, num_refs = 0, num_nodes = 0;
+  int                tiny_count = 0, tiny_slots[4] = {0, 0, 0, 0};
   float              scale = 0;
   vec3f              grid_origin{0, 0, 0}, grid_step{1, 1, 1};
   bbox3f             root_bbox{{flt_max, flt_max, flt_max}, {-flt_max, -flt_max, -flt_max}};

@@ -362,8 +362,6 @@ constexpr int kTraverseDone = (int)0x80000000;
 __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray, trav_stack& st, int& ref, vec2f& uv,
     bool find_any, unsigned long long* nodes_visited, unsigned long long* prims_tested) {
   if (sh.num_refs == 0) return false;
-  shape_ray sr = make_shape_ray(sh, ray.o, ray.d);
-  if (!sr.valid) return false;
   bool     hit      = false;
   int      kind     = sh.is_lines ? 1 : (sh.is_points ? 2 : 0);
   unsigned dsign    = ray_dsign(ray.d);
@@ -379,6 +377,15 @@ __device__ __forceinline__ bool intersect_shape(const dev_shape& sh, ray3f& ray,
     leaf(0);
     return hit;
   }
+  if (sh.tiny_count) {  // a handful of primitives (the two triangles of a light quad): the boxes only cull, the exact
+    for (int i = 0; i < sh.tiny_count; i++) {  // tests decide, and the closest hit does not depend on their order
+      leaf(sh.tiny_slots[i]);
+      if (find_any && hit) return true;
+    }
+    return hit;
+  }
+  shape_ray sr = make_shape_ray(sh, ray.o, ray.d);
+  if (!sr.valid) return false;
   const unsigned base = st.mark();
   int            cur  = 0;
   while (true) {
