@@ -790,18 +790,22 @@ static std::vector<int> owned_pixels(int w, int h, int rank, int world, int ngro
 #ifndef YH_WAVE_GROUPS
 #define YH_WAVE_GROUPS 2
 #endif
+constexpr long long kOneGroupBelowSlots = 800000;
 static yh_status assign_slots(yh_state* st) {
   int ngroups = YH_WAVE_GROUPS;
   if (const char* e = getenv("YH_WAVE_GROUPS")) ngroups = atoi(e);
-  long long owned_estimate = (long long)st->width * st->height / st->world;
-  if (owned_estimate < 4 * 65536) ngroups = 1;  // small images: one group already under-fills the device
+  int S = st->counter ? st->slots_per_pixel : 1;
+  if ((size_t)st->width * st->height > (size_t)kPixelMask) S = 1;  // the lane lives in the top byte of the pixel word
+  // Two groups overlap one group's shading with the other's traversal, but each then runs half as wide.  Measured
+  // (profiles/r02_s4_exp_wave_groups.txt): below ~0.8 M slots one group wins (291 k: +2 %, 518 k: +3-4 %), above it two
+  // do (1.64 M: +7 %); three or four never.
+  long long slots_estimate = (long long)st->width * st->height / st->world * S;
+  if (slots_estimate < kOneGroupBelowSlots && !getenv("YH_WAVE_GROUPS")) ngroups = 1;
   if (ngroups < 1) ngroups = 1;
   if (ngroups > 8) ngroups = 8;
   std::vector<int> first;
   std::vector<int> px = owned_pixels(st->width, st->height, st->rank, st->world, ngroups, &first);
   st->num_owned = (int)px.size();
-  int S = st->counter ? st->slots_per_pixel : 1;
-  if ((size_t)st->width * st->height > (size_t)kPixelMask) S = 1;  // the lane lives in the top byte of the pixel word
   st->slots_per_pixel = S;
   st->ordinal_base    = 0;
   st->ordinal.release(), st->partial.release(), st->partial_samples.release();
