@@ -69,6 +69,13 @@ struct queues {
   int* hair;
   // counts: [0] active cur, [1] active next, [2] miss, [3] surface, [4] hair
   int* count;
+  // The traversal does not append to the three shading queues: it sets bit `slot` in the bitmap of the hit's kind
+  // (kind_bits + kind * kind_words), and k_enumerate_kinds turns the bitmaps into the queues, 1024 slots at a time.
+  // The queues are then sorted by slot inside every run of up to 1024 entries, so the lanes of a shading warp read
+  // and write NEIGHBOURING path-state records (a queue in completion order scatters them: one 16-byte record per
+  // 32-byte sector).  Measured with the hair queue sorted by a radix sort: k_shade<hair> -15 % on C3.
+  unsigned* kind_bits;
+  int       kind_words;  // words per bitmap, a multiple of 32
   // statistics: [0] rays, [1] light rays, [2] samples, [3] nodes, [4] prims
   unsigned long long* stats;
 };
@@ -231,14 +238,7 @@ struct wavefront_io {  // by value: references to kernel parameters would force 
     st_stream(&ps.hit[slot], make_int4(h.object, h.element, __float_as_int(h.uv.x), __float_as_int(h.uv.y)));
     if (ps.hit_dist) st_stream(&ps.hit_dist[slot], h.distance);
     int kind     = !h.hit ? 0 : (sc.shapes[sc.objects[h.object].shape].is_lines ? 2 : 1);
-    // one append for the three shading queues (miss, surface, hair are consecutive in q.count): lanes that go to the
-    // same queue share one atomic
-    int*     queue = kind == 0 ? q.miss : (kind == 1 ? q.surface : q.hair);
-    unsigned peers = __match_any_sync(__activemask(), kind);
-    int      lane = threadIdx.x & 31, leader = __ffs(peers) - 1, base = 0;
-    if (lane == leader) base = atomicAdd(q.count + 2 + kind, __popc(peers));
-    base = __shfl_sync(peers, base, leader);
-    queue[base + __popc(peers & ((1u << lane) - 1))] = slot;
+    atomicOr(q.kind_bits + (size_t)kind * q.kind_words + (slot >> 5), 1u << (slot & 31));  // result unused: a RED
   }
 };
 
@@ -267,6 +267,38 @@ __global__ void __launch_bounds__(kTraceBlock, YH_INTERSECT_BLOCKS) k_intersect(
   atomicAdd(q.stats + 3, nv);
   atomicAdd(q.stats + 4, pt);
 #endif
+}
+
+// Bitmaps of the traversal -> shading queues (queues::kind_bits).  One warp per run of 32 words (1024 slots) and kind
+// (blockIdx.y): lane l owns word l, the warp reserves the run's entries with one atomic and every lane writes the
+// slots of its word in ascending order behind those of the lanes before it; the words are cleared on the way, so the
+// bitmaps are empty again when the round's shading kernels start.
+__global__ void __launch_bounds__(128) k_enumerate_kinds(queues q) {
+  const int kind = blockIdx.y, lane = threadIdx.x & 31;
+  unsigned* bits = q.kind_bits + (size_t)kind * q.kind_words;
+  int*      queue = kind == 0 ? q.miss : (kind == 1 ? q.surface : q.hair);
+  const int runs = q.kind_words >> 5;
+  for (int run = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); run < runs; run += gridDim.x * (blockDim.x >> 5)) {
+    unsigned* wp   = bits + run * 32 + lane;
+    unsigned  word = *wp;
+    if (word) *wp = 0;
+    const int c = __popc(word);
+    int       inc = c;
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    if (total == 0) continue;
+    int base = 0;
+    if (lane == 31) base = atomicAdd(q.count + 2 + kind, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    int out = base + inc - c, first = (run * 32 + lane) * 32;
+    while (word) {
+      queue[out++] = first + __ffs(word) - 1;
+      word &= word - 1;
+    }
+  }
 }
 
 // miss: radiance += weight * eval_environment, break (:1398-1401)
@@ -692,6 +724,8 @@ static void pinned_release(int* p) {
 struct wave_group {
   int                            first_slot = 0, num_slots = 0;
   dev_buffer<int>                q_active0, q_active1, q_miss, q_surface, q_hair, q_count;
+  dev_buffer<unsigned>           kind_bits;  // 3 bitmaps of kind_words words (queues::kind_bits)
+  int                            kind_words = 0;
   dev_buffer<int>                sus_records[2];  // rays carried over between launches (suspend_io), ping-pong
   int                            sus_capacity = 0;
   dev_buffer<unsigned long long> stats;
@@ -700,7 +734,7 @@ struct wave_group {
   int*                           host_counts = nullptr;  // pinned
   int                            cur = 0;
   bool                           done = false;
-  queues qs() { return {{q_active0.ptr, q_active1.ptr}, q_miss.ptr, q_surface.ptr, q_hair.ptr, q_count.ptr, stats.ptr}; }
+  queues qs() { return {{q_active0.ptr, q_active1.ptr}, q_miss.ptr, q_surface.ptr, q_hair.ptr, q_count.ptr, kind_bits.ptr, kind_words, stats.ptr}; }
   ~wave_group() {
     if (host_counts) pinned_release(host_counts);
     if (ev_done) cudaEventDestroy(ev_done);
@@ -854,6 +888,9 @@ static yh_status assign_slots(yh_state* st) {
     YH_CUDA(grp->q_miss.alloc(m));
     YH_CUDA(grp->q_surface.alloc(m));
     YH_CUDA(grp->q_hair.alloc(m));
+    grp->kind_words = (int)((m + 1023) / 1024) * 32;
+    YH_CUDA(grp->kind_bits.alloc((size_t)3 * grp->kind_words));
+    YH_CUDA(cudaMemset(grp->kind_bits.ptr, 0, grp->kind_bits.bytes()));
     YH_CUDA(grp->q_count.alloc(8));
     YH_CUDA(grp->stats.alloc(8));
     {  // Suspend records (yh_traverse.cuh): the long rays of a launch's tail go to the next launch.  It pays when a
@@ -1083,6 +1120,8 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
         k_intersect<false><<<grid_ig, kTraceBlock, 0, s>>>(sc, ps, q, g->cur, q.active[g->cur], suspend_io{});
       }
       YH_DEBUG_KERNEL("k_intersect", s);
+      k_enumerate_kinds<<<dim3((unsigned)std::max(1, std::min(q.kind_words / 128, sms * 4)), 3), 128, 0, s>>>(q);
+      YH_DEBUG_KERNEL("k_enumerate_kinds", s);
       if (prof) ev(s);
       k_shade_miss<<<grid_s, 256, 0, s>>>(sc, ps, q, st->camera, tc, next);
       YH_DEBUG_KERNEL("k_shade_miss", s);
@@ -1110,7 +1149,7 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
       }
       YH_DEBUG_KERNEL("k_shade", s);
       if (prof) ev(s);
-      launches += 5;
+      launches += 6;
       iterations++;
       g->cur = next;
     }
