@@ -8,14 +8,14 @@
 // quota is met), so every lane stays busy until the tail of the call.
 //
 // Per iteration:
-//   k_intersect      one thread per active slot: closest hit, then the slot id
-//                    is appended to the miss / surface / hair queue
-//                    (warp ballot + one atomic per warp).
-//   k_shade_miss     environment radiance, finish sample, regenerate.
-//   k_shade_surface  diffuse surfaces (sphere, floor, area lights).
-//   k_shade_hair     hair BSDF: sample / eval / pdf, MIS with the lights.
+//   k_intersect        persistent warps fetch the active slots' rays: closest hit, the hit record goes to the slot and
+//                      the slot's bit is set in the bitmap of the hit's kind (miss / surface / hair).
+//   k_enumerate_kinds  bitmaps -> the three shading queues, in slot order inside runs of 1024 slots.
+//   k_shade_miss       environment radiance, finish sample, regenerate.
+//   k_shade<false>     surfaces and points (all material lobes, volumes with VOL).
+//   k_shade<true>      hair BSDF: sample / eval / pdf, MIS with the lights.
 // Each shading kernel appends surviving or regenerated slots to the next
-// iteration's active queue.
+// iteration's active queue (one warp-aggregated atomic per warp).
 #include <cmath>
 #include <algorithm>
 #include <cstdlib>
