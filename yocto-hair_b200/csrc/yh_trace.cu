@@ -1100,6 +1100,9 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
     YH_DEBUG_KERNEL("k_start", s);
     launches++;
   }
+  // a scene without triangles / points (or without lines) never fills that kind's queue: its kernel is not launched
+  bool any_lines = false, any_surface = false;
+  for (auto& o : st->scene->objects) (st->scene->shapes[o.shape]->is_lines() ? any_lines : any_surface) = true;
   int64_t min_iters = (num_samples + st->slots_per_pixel - 1) / st->slots_per_pixel;  // every sample of a slot needs at least one iteration
   bool    stopped   = false;
   while (true) {
@@ -1127,29 +1130,29 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
       YH_DEBUG_KERNEL("k_shade_miss", s);
       switch (tc.shader) {
         case YH_SHADER_NAIVE:
-          k_shade<false, YH_SHADER_NAIVE, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-          k_shade<true, YH_SHADER_NAIVE, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          if (any_surface) k_shade<false, YH_SHADER_NAIVE, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          if (any_lines) k_shade<true, YH_SHADER_NAIVE, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           break;
         case YH_SHADER_EYELIGHT:
-          k_shade<false, YH_SHADER_EYELIGHT, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-          k_shade<true, YH_SHADER_EYELIGHT, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          if (any_surface) k_shade<false, YH_SHADER_EYELIGHT, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          if (any_lines) k_shade<true, YH_SHADER_EYELIGHT, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           break;
         case YH_SHADER_NORMAL:
-          k_shade<false, YH_SHADER_NORMAL, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-          k_shade<true, YH_SHADER_NORMAL, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          if (any_surface) k_shade<false, YH_SHADER_NORMAL, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+          if (any_lines) k_shade<true, YH_SHADER_NORMAL, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           break;
         default:
           if (st->scene->has_volumes) {  // only trace_path follows volumes; the volume-free kernels stay as they were
-            k_shade<false, YH_SHADER_PATH, true><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-            k_shade<true, YH_SHADER_PATH, true><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+            if (any_surface) k_shade<false, YH_SHADER_PATH, true><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+            if (any_lines) k_shade<true, YH_SHADER_PATH, true><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           } else {
-            k_shade<false, YH_SHADER_PATH, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
-            k_shade<true, YH_SHADER_PATH, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+            if (any_surface) k_shade<false, YH_SHADER_PATH, false><<<grid_s, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
+            if (any_lines) k_shade<true, YH_SHADER_PATH, false><<<grid_t, kTraceBlock, 0, s>>>(sc, ps, q, st->camera, tc, next);
           }
       }
       YH_DEBUG_KERNEL("k_shade", s);
       if (prof) ev(s);
-      launches += 6;
+      launches += 4 + (any_surface ? 1 : 0) + (any_lines ? 1 : 0);
       iterations++;
       g->cur = next;
     }
