@@ -1094,6 +1094,8 @@ static yh_status trace_samples_impl(yh_state* st, int num_samples, const volatil
     queues q = g->qs();
     YH_CUDA(cudaMemsetAsync(q.count, 0, 8 * sizeof(int), s));
     YH_CUDA(cudaMemsetAsync(q.stats, 0, 8 * sizeof(unsigned long long), s));
+    // empty after every complete round; cleared anyway so that a call that ended in an error leaves nothing behind
+    YH_CUDA(cudaMemsetAsync(q.kind_bits, 0, (size_t)3 * q.kind_words * sizeof(unsigned), s));
     g->cur = 0, g->done = g->num_slots == 0;
     if (g->done) continue;
     k_start<<<(g->num_slots + 255) / 256, 256, 0, s>>>(st->ps(g->first_slot), q, st->camera, tc, g->num_slots, num_samples, st->ordinal_base);
